@@ -1,0 +1,213 @@
+"""Round engine: the reference's driver loop (src/federated.py:21-95) re-designed as one process per GPU.
+
+Reference                                   | here
+------------------------------------------- | --------------------------------------------------------------------
+agents trained sequentially on 1 device     | participant j of a round trains on rank ``j % world`` (all ranks hold
+(src/federated.py:68-72)                    | the device-resident dataset, so any rank can host any agent)
+``agent_updates_dict`` of fp64 updates      | each agent's parameters land in a symmetric-memory slot; updates are
+(src/federated.py:67,70)                    | formed inside the aggregation kernel
+``vector_to_parameters(deepcopy(global))``  | the aggregation kernel multicasts the new global params (fp32 + bf16)
+(src/federated.py:72)                       | into every rank's ``w_global``; trainers start each round from it
+``aggregator.aggregate_updates``            | ``FusedAggregator.aggregate`` -- one kernel, P2P reads + NVLS stores
+evaluation every ``snap`` rounds            | same metrics, device-side confusion matrix, batches strided over ranks
+
+Timed region of the headline metric "FL rounds/sec" = ``run_round`` (local training of all sampled agents +
+aggregation + parameter hand-off), evaluation excluded -- BASELINE.md section 2.
+"""
+from __future__ import annotations
+
+import math
+import random
+
+import numpy as np
+import torch
+
+from . import ops
+from .agent import Agent
+from .aggregation import Aggregation
+from .data import distribute_data, get_datasets, make_poisoned_val
+from .models import get_layout
+from .options import print_exp_details
+from .parallel import FusedAggregator, init_distributed
+from .trainers import make_trainer
+from .utils import MetricLogger, PhaseTimer, get_loss_n_accuracy, load_checkpoint, save_checkpoint
+
+
+class FLEngine:
+    def __init__(self, args, ctx=None, datasets=None, verbose=True):
+        self.args = args
+        self.ctx = ctx if ctx is not None else init_distributed(args.device, args.backend if args.backend in ("nccl", "gloo") else None)
+        ctx = self.ctx
+        args.device = ctx.device
+        dev = ctx.device
+        self.verbose = verbose and ctx.is_main
+        torch.manual_seed(args.seed); np.random.seed(args.seed); random.seed(args.seed)
+        if self.verbose:
+            print_exp_details(args)
+
+        # ---- data (device resident), partition, poisoned validation set (src/federated.py:34-45) ------------
+        if datasets is None:
+            datasets = get_datasets(args.data, args.data_dir, args.synthetic, args.synthetic_val, args.seed, dev)
+        self.train_dataset, self.val_dataset = datasets
+        self.train_dataset.to(dev); self.val_dataset.to(dev)
+        self.poisoned_val = make_poisoned_val(self.val_dataset, args)
+        self.layout = get_layout(args.model)
+        self.n_classes = self.train_dataset.meta.n_classes
+
+        # ---- agents (src/federated.py:49-56) --------------------------------------------------------------------
+        self.agents, self.agent_data_sizes = [], {}
+        if args.data == "fedemnist" and not args.synthetic:
+            for _id in range(args.num_agents):
+                self.agents.append(Agent(_id, args, seed=args.seed))
+        else:
+            groups = distribute_data(self.train_dataset, args, n_classes=self.n_classes)
+            for _id in range(args.num_agents):
+                self.agents.append(Agent(_id, args, self.train_dataset, groups[_id], seed=args.seed))
+        for a in self.agents:
+            self.agent_data_sizes[a.id] = a.n_data
+        self.n_part = max(1, math.floor(args.num_agents * args.agent_frac))
+        max_slots = (self.n_part + ctx.world - 1) // ctx.world
+        max_shard = max(a.n_data for a in self.agents)
+
+        # ---- parameters: flat, symmetric ---------------------------------------------------------------------
+        backend = args.backend
+        if backend in ("nccl", "gloo") and not ctx.is_dist:
+            backend = "local"
+        if backend == "auto" and ctx.is_dist and ctx.backend == "gloo":
+            backend = "gloo"
+        self.fused = FusedAggregator(ctx, self.layout.n_total, self.layout.n_vote, max_slots, backend)
+        init = torch.zeros(self.layout.n_total, dtype=torch.float32)
+        self.layout.init_(init, args.seed)
+        self.fused.w_global.copy_(init.to(dev))
+        if self.fused.w_bf16 is not None:
+            self.fused.w_bf16.copy_(self.fused.w_global.to(torch.bfloat16))
+        self.w_global = self.fused.w_global
+
+        self.trainer = make_trainer(args.trainer, self.layout, args, dev, max_shard)
+        self.logger = MetricLogger(args, enabled=ctx.is_main and bool(args.log_dir))
+        self.aggregator = Aggregation(self.agent_data_sizes, self.layout.n_params, self.poisoned_val, args,
+                                      self.logger, self.layout, self.fused)
+        self.timer = PhaseTimer(dev)
+        self.round_loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.cum_poison_acc_mean = 0.0
+        self.start_round = 1
+        self._stream_src = None
+        if args.resume:
+            ck = load_checkpoint(args.resume, self.w_global, self.layout)
+            self.start_round = ck["round"] + 1
+            self.cum_poison_acc_mean = ck["extra"].get("cum_poison_acc_mean", 0.0)
+        ctx.barrier()
+
+    # ---- sampling (src/federated.py:68; seeded here) ---------------------------------------------------------
+    def sample_agents(self, rnd: int):
+        rs = np.random.RandomState((self.args.seed * 1_000_003 + rnd) % (2 ** 31))
+        return [int(a) for a in rs.choice(self.args.num_agents, self.n_part, replace=False)]
+
+    # ---- end-to-end input streaming (bench "e2e"): shards come from pinned host memory every round ----------
+    def enable_input_streaming(self):
+        """Keep a pinned host copy of every agent's shard; ``run_round(stream_inputs=True)`` then re-uploads the
+        shards this rank trains each round (what a deployment feeding fresh client data would do)."""
+        self._stream_src = {}
+        for a in self.agents:
+            self._stream_src[a.id] = (a.dataset.data[a.idxs].cpu().pin_memory(), a.dataset.targets[a.idxs].cpu().pin_memory())
+        return sum(x.numel() * x.element_size() + y.numel() * y.element_size() for x, y in self._stream_src.values())
+
+    def _upload_shard(self, agent):
+        x, y = self._stream_src[agent.id]
+        dx = x.to(self.ctx.device, non_blocking=True)
+        dy = y.to(self.ctx.device, non_blocking=True)
+        agent.dataset.data.index_copy_(0, agent.idxs, dx)
+        agent.dataset.targets.index_copy_(0, agent.idxs, dy)
+        return x.numel() * x.element_size() + y.numel() * y.element_size()
+
+    # ---- one federated round (src/federated.py:66-74) --------------------------------------------------------
+    def run_round(self, rnd: int, stream_inputs: bool = False):
+        chosen = self.sample_agents(rnd)
+        ctx, fused = self.ctx, self.fused
+        self.round_loss.zero_()
+        steps = 0
+        h2d = 0
+        self.timer.start("local_train")
+        for j, aid in enumerate(chosen):
+            r, s = fused.slot_owner(j)
+            if r != ctx.rank:
+                continue
+            agent = self.agents[aid]
+            if stream_inputs:
+                h2d += self._upload_shard(agent)
+            st = agent.local_train(self.trainer, self.w_global, fused.slots[s], rnd)
+            self.round_loss += st["loss_sum"]
+            steps += st["steps"]
+        self.timer.stop("local_train")
+        self.timer.start("aggregate")
+        self.aggregator.aggregate_slots(chosen, rnd)
+        self.timer.stop("aggregate")
+        return {"chosen": chosen, "steps": steps, "h2d_bytes": h2d}
+
+    def round_result(self):
+        """Device->host read of the round's result: (mean local training loss on this rank, flipped-coordinate count)."""
+        vals = torch.cat([self.round_loss.double(), self.fused.flipped.double()]).cpu()
+        return float(vals[0]), int(vals[1])
+
+    # ---- evaluation (src/federated.py:78-92) ---------------------------------------------------------------
+    def evaluate(self, rnd: int):
+        args = self.args
+        fwd = self.trainer.eval_forward(self.w_global)
+        kw = dict(bs=args.bs, num_classes=self.n_classes, ctx=self.ctx)
+        val_loss, (val_acc, per_class) = get_loss_n_accuracy(fwd, self.val_dataset, **kw)
+        poison_loss, (poison_acc, _) = get_loss_n_accuracy(fwd, self.poisoned_val, **kw)
+        self.cum_poison_acc_mean += poison_acc
+        out = {"val_loss": val_loss, "val_acc": val_acc, "per_class_acc": per_class,
+               "poison_loss": poison_loss, "poison_acc": poison_acc,
+               "base_class_acc": float(per_class[args.base_class]),
+               # reference divides by rnd, not by the number of evaluations (src/federated.py:91; quirk 6 kept)
+               "cum_poison_acc_mean": self.cum_poison_acc_mean / rnd}
+        lg = self.logger
+        lg.add_scalar("Validation/Loss", val_loss, rnd)
+        lg.add_scalar("Validation/Accuracy", val_acc, rnd)
+        lg.add_scalar("Poison/Base_Class_Accuracy", out["base_class_acc"], rnd)
+        lg.add_scalar("Poison/Poison_Accuracy", poison_acc, rnd)
+        lg.add_scalar("Poison/Poison_Loss", poison_loss, rnd)
+        lg.add_scalar("Poison/Cumulative_Poison_Accuracy_Mean", out["cum_poison_acc_mean"], rnd)
+        if self.verbose:
+            print(f"| Val_Loss/Val_Acc: {val_loss:.3f} / {val_acc:.3f} |")
+            print(f"| Val_Per_Class_Acc: {per_class} ")
+            print(f"| Poison Loss/Poison Acc: {poison_loss:.3f} / {poison_acc:.3f} |")
+        return out
+
+    # ---- the training loop --------------------------------------------------------------------------------
+    def fit(self, rounds: int | None = None):
+        args = self.args
+        rounds = rounds if rounds is not None else args.rounds
+        history = []
+        it = range(self.start_round, rounds + 1)
+        if self.verbose:
+            try:
+                from tqdm import tqdm
+                it = tqdm(it)
+            except Exception:  # noqa: BLE001
+                pass
+        for rnd in it:
+            info = self.run_round(rnd)
+            rec = {"steps": info["steps"]}
+            if rnd % args.snap == 0:
+                ev = self.evaluate(rnd)
+                rec.update({k: v for k, v in ev.items() if k != "per_class_acc"})
+            loss, flipped = self.round_result()
+            rec["train_loss"] = loss / max(1, info["steps"])
+            rec["frac_flipped"] = flipped / max(1, self.layout.n_vote)
+            rec.update({f"ms_{k}": v for k, v in self.timer.elapsed().items()})
+            if args.profile_phases and self.verbose:
+                print({k: round(v, 3) for k, v in rec.items() if k.startswith("ms_")})
+            self.logger.record(rnd, **rec)
+            history.append({"round": rnd, **rec})
+            if args.checkpoint and self.ctx.is_main and ((args.ckpt_every and rnd % args.ckpt_every == 0) or rnd == rounds):
+                save_checkpoint(args.checkpoint, self.w_global, rnd, args, self.layout,
+                                {"cum_poison_acc_mean": self.cum_poison_acc_mean})
+        if self.verbose:
+            print("Training has finished!")
+        return history
+
+    def close(self):
+        self.logger.close()
+        self.fused.close()

@@ -1,0 +1,65 @@
+// Host-callable launchers of the sm_100a kernels (raw pointers + stream; no torch headers so the .cu
+// translation units compile in seconds).  Python bindings live in binding.cpp.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace rlr {
+
+struct AggParams {
+    const float* const* w_agents;   // [K] device pointers: each participant's flat params (local or peer-mapped)
+    const double* weights;          // [K] data sizes n_k
+    const float* scales;            // [K] optional per-agent update scale (server clipping) or nullptr
+    double total_weight;            // sum_k n_k
+    const float* w_global;          // current global params (local copy)
+    float* const* out_ptrs;         // [n_out] destinations of the new global params (1 = local or multicast)
+    __nv_bfloat16* const* out_bf16_ptrs;  // optional bf16 shadows (same count) or nullptr
+    int n_out;
+    int use_multimem;               // out_ptrs[0] is an NVLS multicast address
+    int K;
+    long long begin, end;           // coordinate slice owned by this rank (multiples of 4)
+    long long n_vote;               // coordinates >= n_vote: plain weighted mean (BN statistics)
+    int mode;                       // 0 avg, 1 comed, 2 sign
+    int theta;                      // RLR threshold (0 = off)
+    float server_lr;
+    float noise_std;
+    uint64_t seed, noise_stream;
+    unsigned long long* flipped;    // optional counter of coordinates with negated lr
+    uint32_t* const* flag_ptrs;     // [world] peer-mapped signal words, 2*world per rank (in / out barrier)
+    uint32_t* local_sync;           // [2] intra-GPU: ready flag, finished-CTA counter
+    int rank, world;
+    uint32_t epoch;                 // monotonically increasing per call
+};
+cudaError_t launch_fused_aggregate(const AggParams& p, int num_sms, cudaStream_t st);
+cudaError_t launch_update_sqnorm(const float* const* w_agents, const float* w_global, long long n, int K, double* out,
+                                 int num_sms, cudaStream_t st);
+
+// ---- data path ---------------------------------------------------------------------------------------
+// out_kind: 0 fp32, 1 bf16.  nchw: output layout NCHW (Cpad ignored) else NHWC with channels padded to c_pad.
+cudaError_t launch_gather_normalize(const void* data, int in_is_float, const int64_t* idx, const int* cursor,
+                                    const int64_t* targets, void* out, int out_kind, int64_t* out_labels, int B, int H,
+                                    int W, int C, int c_pad, int nchw, const float* mean, const float* stdv,
+                                    cudaStream_t st);
+cudaError_t launch_stamp_pixels(void* data, int is_float, const int64_t* sel, int S, const int* rows, const int* cols,
+                                const float* vals, int P, int H, int W, int C, int mode, cudaStream_t st);
+cudaError_t launch_advance_cursor(int* cursor, int delta, cudaStream_t st);
+
+// ---- optimiser over flat buffers -------------------------------------------------------------------------
+cudaError_t launch_round_init(const float* w_global, float* w_local, __nv_bfloat16* w_bf16, float* mom, long long n,
+                              cudaStream_t st);
+cudaError_t launch_sqnorm(const float* x, long long n, double* out /*accumulates*/, int num_sms, cudaStream_t st);
+cudaError_t launch_sgd_step(float* w, const float* g, float* m, const float* w0, __nv_bfloat16* w_bf16, long long n,
+                            float lr, float momentum, float max_grad_norm, const double* g_sqnorm, double* d_sqnorm,
+                            int num_sms, cudaStream_t st);
+cudaError_t launch_pgd_project(float* w, const float* w0, __nv_bfloat16* w_bf16, long long n, float clip,
+                               const double* d_sqnorm, int num_sms, cudaStream_t st);
+
+// ---- loss / evaluation -----------------------------------------------------------------------------------
+// logits [B,C] (kind 0 fp32 / 1 bf16); writes dlogits (same kind, scaled by 1/B) and accumulates loss_sum / correct.
+cudaError_t launch_softmax_xent(const void* logits, int kind, const int64_t* labels, void* dlogits, float* loss_sum,
+                                int* correct, int B, int C, float grad_scale, cudaStream_t st);
+cudaError_t launch_eval_metrics(const void* logits, int kind, const int64_t* labels, int B, int C, double* loss_sum,
+                                long long* confusion /*[C*C]*/, cudaStream_t st);
+
+}  // namespace rlr

@@ -1,0 +1,129 @@
+"""Fused aggregate + server-step + broadcast across GPUs (the product path of SURVEY.md 5.8).
+
+Per-rank symmetric slab layout (byte offsets identical on every rank):
+
+    [ flags: uint32[2*world] (+pad to 4 KiB) | w_global fp32[n] | w_global bf16[n] | slot_0 fp32[n] | slot_1 ... ]
+
+``w_global`` is what every local trainer reads at the start of a round; ``slot_j`` receives the parameters of the
+j-th agent this rank trained.  One launch of ``fused_aggregate_kernel`` per rank then (i) waits until every rank has
+signalled "slots ready", (ii) reads the owned coordinate slice of every participant's slot straight from the owning
+GPU's HBM over NVLink, (iii) computes sign vote / aggregator / RLR flip / server step, (iv) stores the new global
+slice into EVERY rank's ``w_global`` (+bf16 shadow) with NVLS multicast stores (or per-peer P2P stores), and (v)
+signals/awaits "slice landed".  No NCCL call, no host synchronisation, no materialised update vectors.
+
+With ``backend in {nccl, gloo}`` (the baseline transport) the slots are all-gathered and the same kernel runs on the
+gathered copies locally; on CPU it runs the fp64 oracle.
+"""
+from __future__ import annotations
+
+import torch
+
+from .. import ops
+from .symm import SymmetricBuffer
+
+FLAG_BYTES = 4096
+
+
+class FusedAggregator:
+    def __init__(self, ctx, n_total: int, n_vote: int, max_slots: int, backend: str = "auto", with_bf16: bool = True):
+        self.ctx = ctx
+        self.n, self.n_vote, self.max_slots = int(n_total), int(n_vote), int(max_slots)
+        dev = ctx.device
+        if backend == "auto":
+            backend = "fused" if (dev.type == "cuda") else ("gloo" if ctx.is_dist else "local")
+        if backend == "fused" and dev.type != "cuda":
+            raise ValueError("backend=fused needs CUDA devices")
+        self.backend = backend
+        self.with_bf16 = with_bf16 and dev.type == "cuda"
+        n = self.n
+        self.off_flags = 0
+        self.off_wg = FLAG_BYTES
+        self.off_wb = self.off_wg + 4 * n
+        self.off_slots = self.off_wb + 2 * n
+        nbytes = self.off_slots + 4 * n * self.max_slots
+        use_symm = backend == "fused" and ctx.is_dist
+        self.buf = SymmetricBuffer(ctx, nbytes) if use_symm else SymmetricBuffer(_Solo(ctx), nbytes)
+        self.w_global = self.buf.tensor(self.off_wg, n, torch.float32)
+        self.w_bf16 = self.buf.tensor(self.off_wb, n, torch.bfloat16) if self.with_bf16 else None
+        self.slots = [self.buf.tensor(self.off_slots + 4 * n * j, n, torch.float32) for j in range(self.max_slots)]
+        self.flipped = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.epoch = 0
+        self._tables = {}
+        if use_symm:
+            world = ctx.world
+            self.local_sync = torch.zeros(2, dtype=torch.int32, device=dev)
+            self.flag_ptrs = ops.PtrTable([self.buf.peer_ptr(r, self.off_flags) for r in range(world)], dev)
+            mc = self.buf.mc_ptr(self.off_wg)
+            self.use_multimem = bool(mc)
+            if self.use_multimem:
+                self.out_ptrs = ops.PtrTable([mc], dev)
+                self.out_bf16_ptrs = ops.PtrTable([self.buf.mc_ptr(self.off_wb)], dev) if self.with_bf16 else None
+            else:
+                self.out_ptrs = ops.PtrTable([self.buf.peer_ptr(r, self.off_wg) for r in range(world)], dev)
+                self.out_bf16_ptrs = (ops.PtrTable([self.buf.peer_ptr(r, self.off_wb) for r in range(world)], dev)
+                                      if self.with_bf16 else None)
+            # coordinate slices: multiples of 4, cover [0, n)
+            per = (n // 4 + world - 1) // world * 4
+            self.begin = min(n, ctx.rank * per)
+            self.end = min(n, self.begin + per)
+
+    # ---------------------------------------------------------------------------------------------------------
+    def slot_owner(self, j: int):
+        """(rank, local slot) of the j-th participant of a round."""
+        return j % self.ctx.world, j // self.ctx.world
+
+    def _agent_table(self, n_part: int):
+        if n_part not in self._tables:
+            ptrs = []
+            for j in range(n_part):
+                r, s = self.slot_owner(j)
+                ptrs.append(self.buf.peer_ptr(r, self.off_slots + 4 * self.n * s))
+            self._tables[n_part] = ops.PtrTable(ptrs, self.ctx.device)
+        return self._tables[n_part]
+
+    def aggregate(self, weights, mode, theta, server_lr, noise_std=0.0, seed=0, rnd=0, scales=None):
+        """Aggregate the first ``len(weights)`` participants (participant j lives in ``slot_owner(j)``) and update
+        ``w_global`` on every rank.  Returns nothing; ``self.flipped`` accumulates the flipped-coordinate count."""
+        n_part = len(weights)
+        ctx, dev = self.ctx, self.ctx.device
+        self.flipped.zero_()
+        if self.backend == "fused" and ctx.is_dist:
+            self.epoch += 1
+            wt = torch.as_tensor(weights, dtype=torch.float64).to(dev)
+            sc = torch.as_tensor(scales, dtype=torch.float32).to(dev) if scales is not None else None
+            ops.ext().fused_aggregate(
+                self._agent_table(n_part).tensor, wt, sc, float(sum(float(x) for x in weights)), self.w_global.data_ptr(),
+                self.out_ptrs.tensor, self.out_bf16_ptrs.tensor if self.out_bf16_ptrs else None, self.use_multimem,
+                self.begin, self.end, self.n_vote, ops.MODE_IDS[mode], int(theta), float(server_lr), float(noise_std),
+                int(seed), int(rnd), self.flipped, self.flag_ptrs.tensor, self.local_sync, ctx.rank, ctx.world, self.epoch)
+            return
+        # ---- baseline transports / single process: gather participant params, run the kernel locally ------------
+        if ctx.is_dist:
+            mine = torch.stack(self.slots, 0)                       # [max_slots, n]
+            allp = ctx.all_gather(mine)                             # [world, max_slots, n]
+            agents = [allp[j % ctx.world, j // ctx.world] for j in range(n_part)]
+        else:
+            agents = [self.slots[j] for j in range(n_part)]
+        ops.fused_aggregate(self.w_global, agents, weights, mode, theta, server_lr, noise_std, seed, rnd, self.n_vote,
+                            scales, out=self.w_global, out_bf16=self.w_bf16, flipped=self.flipped)
+
+    def update_norms(self, n_part: int):
+        """||w_j - w_global|| for every participant (float64 [n_part]), computed where the slot lives."""
+        ctx = self.ctx
+        mine = [j for j in range(n_part) if self.slot_owner(j)[0] == ctx.rank]
+        local = torch.zeros(n_part, dtype=torch.float64, device=ctx.device)
+        if mine:
+            norms = ops.update_norms(self.w_global, [self.slots[self.slot_owner(j)[1]] for j in mine])
+            local[torch.as_tensor(mine, device=ctx.device)] = norms ** 2
+        ctx.all_reduce_sum(local)
+        return local.sqrt()
+
+    def close(self):
+        self.buf.close()
+
+
+class _Solo:
+    """Context stand-in that makes SymmetricBuffer allocate plain local memory."""
+
+    def __init__(self, ctx):
+        self.device, self.world, self.rank, self.is_dist, self.is_main = ctx.device, 1, 0, False, True
