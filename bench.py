@@ -1,0 +1,225 @@
+"""Headline benchmark: FL rounds/sec (device-timed, max over ranks) -- CIFAR-10 ResNet-18, FedAvg, bf16,
+num_agents = number of GPUs, local_ep=2, bs=256, 50,000 synthetic CIFAR-shaped training images (BASELINE.json).
+
+    python bench.py [--gpus N --steps K --warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A "step" is one federated round = every agent trains local_ep epochs on its shard (one agent per GPU, all GPUs in
+parallel) + fused aggregation / server step / parameter hand-off.  Total work per round is fixed (the 50k-image
+dataset is split over the agents), so scaling is STRONG.  Evaluation is outside the timed region for both arms
+(BASELINE.md section 2).  Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=3)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", type=str, default="ours", choices=("ours", "reference"))
+    p.add_argument("--model", type=str, default="resnet18")
+    p.add_argument("--data", type=str, default="cifar10")
+    p.add_argument("--train_size", type=int, default=50000)
+    p.add_argument("--local_ep", type=int, default=2)
+    p.add_argument("--bs", type=int, default=256)
+    p.add_argument("--aggr", type=str, default="avg")
+    p.add_argument("--theta", type=int, default=0)
+    p.add_argument("--num_corrupt", type=int, default=0)
+    p.add_argument("--poison_frac", type=float, default=0.0)
+    p.add_argument("--trainer", type=str, default="auto")
+    p.add_argument("--backend", type=str, default="auto")
+    p.add_argument("--dtype", type=str, default="bf16")
+    p.add_argument("--no_e2e", action="store_true")
+    return p.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason sampler running DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                       "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:  # noqa: BLE001
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
+                for nm, v in zip(names, r[5:9]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:  # noqa: BLE001
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        load = [s for s, pw in zip(sm, power) if pw > 0.5 * max(power)] or sm
+        return {"sm_mhz": statistics.median(load), "sm_max_mhz": max(mx), "power_w_max": max(power),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def config_dict(a, n, impl):
+    return {"model": a.model, "dataset": f"{a.data} (synthetic, {a.train_size} train images)", "num_agents": n,
+            "agents_per_gpu": 1 if impl == "ours" else n, "global_batch": a.bs * n if impl == "ours" else a.bs,
+            "local_batch": a.bs, "local_ep": a.local_ep, "aggr": a.aggr, "robustLR_threshold": a.theta,
+            "num_corrupt": a.num_corrupt, "seq_len": None,
+            "parallelism": f"agent-parallel: {n} agent(s) on {n} GPU(s)" if impl == "ours" else f"{n} agent(s) sequential on 1 GPU (reference design)",
+            "l2_policy": "inputs larger than L2: each step streams a fresh batch from the 150 MB device-resident dataset plus "
+                         "4x45 MB flat parameter/grad/momentum buffers and >100 MB of activations (L2 = 126 MB)",
+            "timed_region": "local training of all agents + aggregation + parameter hand-off; evaluation excluded"}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # the reference is a single-process, single-GPU simulation: extra ranks have nothing to do
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import run_reference as rr
+    if not rr.reference_available():
+        from install_reference import install
+        if not install():
+            print(json.dumps({"impl": "reference", "unavailable": "baseline/_ref missing and /root/reference not mounted"}))
+            return
+    import torch
+    if not torch.cuda.is_available():
+        print(json.dumps({"impl": "reference", "unavailable": "no CUDA device visible"}))
+        return
+    clocks = ClockSampler(0)
+    t0 = time.time()
+    res = rr.run(data=a.data, model=a.model, num_agents=a.gpus, local_ep=a.local_ep, bs=a.bs, aggr=a.aggr,
+                 train_size=a.train_size, steps=a.steps, warmup=a.warmup, theta=a.theta, num_corrupt=a.num_corrupt,
+                 poison_frac=a.poison_frac, device="cuda:0")
+    ck = clocks.stop()
+    out = {"impl": "reference", "metric": "fl_rounds_per_sec", "value": res["rounds_per_s"], "unit": "rounds/s",
+           "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": res["ms_per_round"],
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "fp32 (reference has no AMP; cuDNN TF32 convs)",
+           "data": "synthetic", "config": config_dict(a, a.gpus, "reference"), "clocks": ck,
+           "e2e": {"value": a.steps / res["wall_s"], "unit": "rounds/s", "h2d_bytes_per_step": res["h2d_bytes_per_round"],
+                   "d2h_bytes_per_step": 0, "note": "wall clock of the same rounds; the reference copies every batch from pageable host memory"},
+           "gpu_launches": 0,
+           "note": ("unmodified reference Agent/Aggregation loop on 1 GPU"
+                    + ("; ResNet-18/VGG-11 are not in the reference: plain torch.nn definition from baseline/torch_models.py" if a.model in ("resnet18", "vgg11") else "")),
+           "wall_s_total": time.time() - t0}
+    print(json.dumps(out))
+
+
+def run_ours(a):
+    import torch
+    from rlr_b200.engine import FLEngine
+    from rlr_b200.options import make_args
+    from rlr_b200.parallel import init_distributed
+
+    ctx = init_distributed(None, None)
+    n = ctx.world
+    if n != a.gpus and ctx.is_main:
+        print(f"[bench] warning: --gpus {a.gpus} but WORLD_SIZE={n}; using {n}", file=sys.stderr)
+    args = make_args(data=a.data, model=a.model, num_agents=n, local_ep=a.local_ep, bs=a.bs, aggr=a.aggr,
+                     robustLR_threshold=a.theta, num_corrupt=a.num_corrupt, poison_frac=a.poison_frac,
+                     synthetic=a.train_size, synthetic_val=1000, snap=10 ** 9, rounds=10 ** 9, log_dir="",
+                     trainer=a.trainer, backend=a.backend, dtype=a.dtype, seed=0)
+    eng = FLEngine(args, ctx=ctx, verbose=False)
+    dev = ctx.device
+    cuda = dev.type == "cuda"
+
+    def sync():
+        ctx.barrier()
+        if cuda:
+            torch.cuda.synchronize(dev)
+
+    def timed(k, first_round, stream):
+        sync()
+        if cuda:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        t0 = time.perf_counter()
+        h2d = d2h = 0
+        res = None
+        for r in range(k):
+            info = eng.run_round(first_round + r, stream_inputs=stream)
+            h2d += info["h2d_bytes"]
+            if stream:
+                res = eng.round_result()            # device -> host read of the round's result
+                d2h += 16
+        if cuda:
+            e1.record()
+        sync()
+        ms = e0.elapsed_time(e1) if cuda else (time.perf_counter() - t0) * 1e3
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        ctx.all_reduce_max(t)
+        return float(t.item()), h2d, d2h, res, info
+
+    for r in range(a.warmup):
+        eng.run_round(r + 1)
+    eng.timer.elapsed()  # drop warm-up spans
+    clocks = ClockSampler(dev.index or 0) if (ctx.is_main and cuda) else None
+    ms, _, _, _, info = timed(a.steps, a.warmup + 1, False)
+    ck = clocks.stop() if clocks else {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["cpu run"]}
+    phases = eng.timer.elapsed()
+    e2e = None
+    if not a.no_e2e:
+        eng.enable_input_streaming()
+        eng.run_round(10_000, stream_inputs=True)  # warm the streaming path
+        ms2, h2d, d2h, res, _ = timed(a.steps, 10_001, True)
+        tot = torch.tensor([float(h2d), float(d2h)], dtype=torch.float64, device=dev)
+        ctx.all_reduce_sum(tot)
+        e2e = {"value": a.steps * 1e3 / ms2, "unit": "rounds/s", "h2d_bytes_per_step": tot[0].item() / a.steps,
+               "d2h_bytes_per_step": tot[1].item() / a.steps, "ms_per_step": ms2 / a.steps,
+               "note": "every round re-uploads each trained shard (uint8 images + labels) from pinned host memory and reads "
+                       "the round's training-loss / flipped-coordinate result back to the host",
+               "last_result": {"train_loss_sum": res[0], "flipped": res[1]} if res else None}
+    launches = eng.trainer.launches_per_step() * info["steps"] * a.steps + 2 * a.steps  # + round_init + fused aggregate
+    if ctx.is_main:
+        out = {"impl": "ours", "metric": "fl_rounds_per_sec", "value": a.steps * 1e3 / ms, "unit": "rounds/s", "n_gpus": n,
+               "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
+               "scaling": "strong", "vs_baseline": None, "dtype": a.dtype if cuda else "fp32", "data": "synthetic",
+               "config": {**config_dict(a, n, "ours"), "trainer": eng.trainer.name, "agg_backend": eng.fused.backend,
+                          "symm_provider": eng.fused.buf.provider, "multicast": bool(getattr(eng.fused, "use_multimem", False)),
+                          "local_steps_per_round_per_gpu": info["steps"], "n_params": eng.layout.n_params},
+               "clocks": ck, "e2e": e2e, "gpu_launches": int(launches),
+               "phase_ms_per_round_rank0": {k: v / a.steps for k, v in phases.items()}}
+        print(json.dumps(out))
+    eng.close()
+    if ctx.is_dist:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -108,8 +108,9 @@ class FLEngine:
         """Keep a pinned host copy of every agent's shard; ``run_round(stream_inputs=True)`` then re-uploads the
         shards this rank trains each round (what a deployment feeding fresh client data would do)."""
         self._stream_src = {}
+        pin = (lambda t: t.cpu().pin_memory()) if self.ctx.device.type == "cuda" else (lambda t: t.cpu().clone())
         for a in self.agents:
-            self._stream_src[a.id] = (a.dataset.data[a.idxs].cpu().pin_memory(), a.dataset.targets[a.idxs].cpu().pin_memory())
+            self._stream_src[a.id] = (pin(a.dataset.data[a.idxs]), pin(a.dataset.targets[a.idxs]))
         return sum(x.numel() * x.element_size() + y.numel() * y.element_size() for x, y in self._stream_src.values())
 
     def _upload_shard(self, agent):

@@ -46,9 +46,10 @@ class DistContext:
         """[world, *t.shape] tensor of every rank's ``t``."""
         if not self.is_dist:
             return t.unsqueeze(0)
-        out = torch.empty((self.world, *t.shape), dtype=t.dtype, device=t.device)
-        dist.all_gather_into_tensor(out, t.contiguous())
-        return out
+        flat = t.contiguous().view(-1)
+        out = torch.empty(self.world * flat.numel(), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, flat)
+        return out.view(self.world, *t.shape)
 
     def all_gather_object(self, obj):
         if not self.is_dist:

@@ -116,6 +116,11 @@ class TorchTrainer:
             out.copy_(self.w)
         return {"loss_sum": self.loss_sum, "steps": steps}
 
+    def launches_per_step(self):
+        """Number of OUR kernels per local step (gather, cursor, ||g||^2, fused SGD [+ PGD]); forward/backward of this
+        trainer are torch/cuDNN library calls and are not counted."""
+        return (4 + (1 if self.args.clip > 0 else 0)) if self.device.type == "cuda" else 0
+
     @torch.no_grad()
     def eval_forward(self, w):
         """``forward(x)`` closure evaluating parameters ``w`` in eval mode (running BN statistics)."""
