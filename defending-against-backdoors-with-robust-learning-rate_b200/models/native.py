@@ -1,0 +1,472 @@
+"""Native (no-autograd) executor of the model IR and the trainer built on it.
+
+``NativeNet`` compiles an IR program (models/graph.py) into a static plan of fused forward ops and their hand-derived
+backward ops over pre-allocated NHWC bf16 activation buffers, with parameters read from the flat fp32 buffer ``w``
+(bf16 operand shadow ``wb``) and gradients written straight into the flat fp32 buffer ``g`` -- no autograd graph, no
+per-tensor optimizer state, no zero_grad (every gradient is overwritten).  The plan fuses
+
+    conv(+bias)(+ReLU)            conv -> per-channel sum / sum^2 (BatchNorm statistics) in the GEMM epilogue
+    BN(batch stats) + residual add + ReLU in one pass; BN backward in two (reduce, apply) passes
+    avg-pool + flatten + linear head + softmax cross-entropy
+
+Each primitive has two back-ends selected per op in ``self.impl``: ``"sm100"`` -- the hand-written tcgen05/TMA
+kernels of ops/csrc (gemm.cu / conv.cu / norm.cu) -- and ``"aten"`` -- the same math through library calls on the
+same buffers, used as the in-place numerical oracle for the kernels (tests/test_gpu_native.py) and for shapes a
+kernel does not cover yet.  ``NativeTrainer`` captures the whole step (gather -> forward -> loss -> backward -> fused
+clip+SGD) in CUDA graphs, like ``TorchTrainer``.
+
+Reference call sites replaced: src/models.py:22-31,47-58 (forward), src/agent.py:46-51 (loss/backward/clip/step).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+from .. import ops
+from .graph import FlatLayout
+
+ACT = torch.bfloat16   # default activation / GEMM-operand dtype on GPU (tests may run the plan in fp32 on CPU)
+
+
+def native_supported(layout: FlatLayout) -> bool:
+    return all(nd.op in ("conv", "bn", "relu", "maxpool", "avgpool", "flatten", "dropout", "linear", "save", "add")
+               for nd in layout.nodes)
+
+
+class _Op:
+    """One fused plan entry."""
+    __slots__ = ("kind", "node", "name", "attrs", "x", "y", "res", "relu", "saved", "acc_dx", "need_dx", "in_shape", "out_shape")
+
+    def __init__(self, kind, **kw):
+        self.kind = kind
+        self.node = self.name = self.x = self.y = self.res = None
+        self.attrs, self.relu, self.saved, self.acc_dx, self.need_dx = {}, False, {}, False, True
+        self.in_shape = self.out_shape = None
+        for k, v in kw.items():
+            setattr(self, k, v)
+
+
+class NativeNet:
+    def __init__(self, layout: FlatLayout, device, max_batch: int, impl: str | dict = "auto", seed: int = 0, act_dtype=None):
+        self.layout, self.device, self.max_batch = layout, torch.device(device), int(max_batch)
+        self.act_dtype = act_dtype or ACT
+        default = ("sm100" if self.device.type == "cuda" else "aten") if impl == "auto" else impl
+        self.impl = dict(conv_fwd=default, conv_dgrad=default, conv_wgrad=default, bn=default, pool=default,
+                         linear=default, dropout=default) if not isinstance(impl, dict) else dict(impl)
+        self.seed = seed
+        self.step_counter = torch.zeros(1, dtype=torch.int64, device=device)  # Philox offset for dropout
+        self._build_plan()
+        self._alloc()
+
+    # ------------------------------------------------------------------------------------------------------------
+    # planning: shape inference + fusion
+    # ------------------------------------------------------------------------------------------------------------
+    def _build_plan(self):
+        nodes = self.layout.nodes
+        C, H, W = self.layout.in_shape
+        shape = {"x": (H, W, C)}          # per-slot current (H,W,C) or (F,) after flatten
+        ver = {"x": 0}                    # per-slot version counter -> tensor ids "slot@v"
+        tid = lambda s: f"{s}@{ver[s]}"
+        self.tshape = {tid("x"): shape["x"]}
+        plan, consumed = [], set()
+        pending_bn = {}
+        alias = {}
+
+        def new_out(slot, shp):
+            ver[slot] = ver.get(slot, -1) + 1
+            shape[slot] = shp
+            self.tshape[tid(slot)] = shp
+            return tid(slot)
+
+        def next_same_slot(i, slot):
+            for j in range(i + 1, len(nodes)):
+                if j in consumed:
+                    continue
+                nd = nodes[j]
+                if nd.op == "save":
+                    if nd.inp == slot:
+                        return None, None  # value is captured: do not fuse across
+                    continue
+                if nd.inp == slot or nd.out == slot:
+                    return j, nd
+            return None, None
+
+        for i, nd in enumerate(nodes):
+            if i in consumed:
+                continue
+            a = nd.attrs
+            if nd.op == "save":
+                ver[nd.out] = ver.get(nd.out, -1) + 1
+                alias[f"{nd.out}@{ver[nd.out]}"] = tid(nd.inp)
+                shape[nd.out] = shape[nd.inp]
+                self.tshape[f"{nd.out}@{ver[nd.out]}"] = shape[nd.inp]
+                continue
+            src = alias.get(tid(nd.inp), tid(nd.inp))
+            if nd.op == "conv":
+                h, w, c = shape[nd.inp]
+                k, s, p = a["k"], a.get("stride", 1), a.get("pad", 0)
+                ho, wo = (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
+                op = _Op("conv", node=i, name=nd.name, attrs=a, x=src, in_shape=(h, w, c), out_shape=(ho, wo, a["cout"]))
+                j, nx = next_same_slot(i, nd.out)
+                want_stats = nx is not None and nx.op == "bn"
+                if nx is not None and nx.op == "relu":
+                    op.relu = True
+                    consumed.add(j)
+                op.saved["want_stats"] = want_stats
+                op.y = new_out(nd.out, op.out_shape)
+                plan.append(op)
+            elif nd.op == "bn":
+                shp = shape[nd.inp]
+                op = _Op("bn", node=i, name=nd.name, attrs=a, x=src, in_shape=shp, out_shape=shp)
+                j, nx = next_same_slot(i, nd.out)
+                if nx is not None and nx.op == "relu":
+                    op.relu = True
+                    consumed.add(j)
+                    op.y = new_out(nd.out, shp)
+                    plan.append(op)
+                elif nx is not None and nx.op == "add":
+                    pending_bn[j] = op   # emitted when the add node is reached (its other operand is ready then)
+                else:
+                    op.y = new_out(nd.out, shp)
+                    plan.append(op)
+            elif nd.op == "add":
+                other = alias.get(tid(a["other"]), tid(a["other"]))
+                op = pending_bn.pop(i, None)
+                if op is None:
+                    raise NotImplementedError("add without a preceding BatchNorm is not used by any model in the zoo")
+                op.res = other
+                j, nx = next_same_slot(i, nd.out)
+                if nx is not None and nx.op == "relu":
+                    op.relu = True
+                    consumed.add(j)
+                op.y = new_out(nd.out, op.out_shape)
+                plan.append(op)
+            elif nd.op == "relu":
+                raise NotImplementedError("stand-alone ReLU (every ReLU in the zoo follows conv/bn/linear)")
+            elif nd.op == "maxpool":
+                h, w, c = shape[nd.inp]
+                op = _Op("maxpool", node=i, x=src, in_shape=(h, w, c), out_shape=(h // 2, w // 2, c))
+                op.y = new_out(nd.out, op.out_shape)
+                plan.append(op)
+            elif nd.op == "avgpool":
+                h, w, c = shape[nd.inp]
+                op = _Op("avgpool", node=i, x=src, in_shape=(h, w, c), out_shape=(1, 1, c))
+                op.y = new_out(nd.out, op.out_shape)
+                plan.append(op)
+            elif nd.op == "flatten":
+                shp = shape[nd.inp]
+                ver[nd.out] += 1
+                alias[tid(nd.out)] = src
+                shape[nd.out] = (int(math.prod(shp)),)
+                self.tshape[tid(nd.out)] = shape[nd.out]
+            elif nd.op == "dropout":
+                shp = shape[nd.inp]
+                op = _Op("dropout", node=i, attrs=a, x=src, in_shape=shp, out_shape=shp)
+                op.y = new_out(nd.out, shp)
+                plan.append(op)
+            elif nd.op == "linear":
+                op = _Op("linear", node=i, name=nd.name, attrs=a, x=src, in_shape=shape[nd.inp], out_shape=(a["cout"],))
+                j, nx = next_same_slot(i, nd.out)
+                if nx is not None and nx.op == "relu":
+                    op.relu = True
+                    consumed.add(j)
+                op.y = new_out(nd.out, op.out_shape)
+                plan.append(op)
+            else:
+                raise NotImplementedError(nd.op)
+        self.plan = plan
+        self.alias = alias
+        self.out_tid = alias.get(tid("x"), tid("x"))
+        self.in_tid = "x@0"
+        # static gradient-flow analysis: which tensors need grads, and which dgrad writes accumulate
+        written = set()
+        for op in reversed(plan):
+            op.need_dx = op.x != self.in_tid
+            if op.res is not None:
+                written.add(op.res)        # fused bn+add writes the residual gradient first (plain store)
+            if op.need_dx:
+                op.acc_dx = op.x in written
+                written.add(op.x)
+
+    def _numel(self, shp):
+        return int(math.prod(shp))
+
+    def _alloc(self):
+        B, dev = self.max_batch, self.device
+        self.act, self.grad = {}, {}
+        for op in self.plan:
+            self.act[op.y] = torch.empty((B, *op.out_shape), dtype=self.act_dtype, device=dev)
+        for op in self.plan:
+            for t in (op.x, op.res):
+                if t is not None and t != self.in_tid and t not in self.grad:
+                    self.grad[t] = torch.empty((B, *self.tshape[t]), dtype=self.act_dtype, device=dev)
+        self.grad[self.out_tid] = torch.empty((B, *self.tshape[self.out_tid]), dtype=self.act_dtype, device=dev)
+        self.logits = torch.empty((B, self.tshape[self.out_tid][-1]), dtype=torch.float32, device=dev)
+        for op in self.plan:
+            if op.kind == "bn" or (op.kind == "conv" and op.saved.get("want_stats")):
+                c = op.out_shape[-1]
+                op.saved["stats"] = torch.zeros(2, c, dtype=torch.float32, device=dev)     # sum, sum of squares
+                op.saved["mean_rstd"] = torch.zeros(2, c, dtype=torch.float32, device=dev)
+                op.saved["dsum"] = torch.zeros(2, c, dtype=torch.float32, device=dev)      # sum dy, sum dy*xhat
+            if op.kind == "maxpool":
+                op.saved["idx"] = torch.empty((B, *op.out_shape), dtype=torch.uint8, device=dev)
+            if op.kind == "dropout":
+                op.saved["mask"] = torch.empty((B, *op.out_shape), dtype=torch.uint8, device=dev)
+        self._bn_src = {}
+        for i, op in enumerate(self.plan):   # a BN op reads the statistics its producer conv accumulated
+            if op.kind == "bn":
+                prod = next((q for q in self.plan[:i] if q.y == op.x and q.kind == "conv"), None)
+                op.saved["producer"] = prod
+
+    # ------------------------------------------------------------------------------------------------------------
+    # parameter views
+    # ------------------------------------------------------------------------------------------------------------
+    def bind(self, w, wb, g):
+        """Point the net at flat fp32 params ``w``, their bf16 shadow ``wb`` and the flat fp32 gradient ``g``."""
+        self.w, self.wb, self.g = w, wb, g
+        lay = self.layout
+        self.pw = {p.name: lay.view(w, p) for p in lay.params + lay.buffers}
+        self.pwb = {p.name: lay.view(wb, p) for p in lay.params} if wb is not None else {}
+        self.pg = {p.name: lay.view(g, p) for p in lay.params} if g is not None else {}
+
+    def T(self, t, B):
+        return self.act[t][:B] if t != self.in_tid else self._x[:B]
+
+    def G(self, t, B):
+        return self.grad[t][:B]
+
+    # ------------------------------------------------------------------------------------------------------------
+    # forward
+    # ------------------------------------------------------------------------------------------------------------
+    def forward(self, x_nhwc, train: bool):
+        """``x_nhwc``: [B,H,W,C] bf16 (channels of the first conv, un-padded).  Returns fp32 logits [B,classes]."""
+        B = x_nhwc.shape[0]
+        self._x, self._B, self._train = x_nhwc, B, train
+        for op in self.plan:
+            getattr(self, "_fwd_" + op.kind)(op, B, train)
+        out = self.T(self.out_tid, B)
+        self.logits[:B].copy_(out.reshape(B, -1))
+        return self.logits[:B]
+
+    def backward(self, dlogits):
+        """``dlogits`` [B,classes] (already scaled by 1/B).  Fills the flat gradient buffer."""
+        B = dlogits.shape[0]
+        self.G(self.out_tid, B).copy_(dlogits.reshape(self.G(self.out_tid, B).shape))
+        for op in reversed(self.plan):
+            getattr(self, "_bwd_" + op.kind)(op, B)
+
+    # ---- conv ---------------------------------------------------------------------------------------------------
+    def _fwd_conv(self, op, B, train):
+        a = op.attrs
+        x, y = self.T(op.x, B), self.T(op.y, B)
+        bias = self.pw.get(op.name + ".bias")
+        stats = op.saved.get("stats") if (train and op.saved.get("want_stats")) else None
+        if self.impl["conv_fwd"] == "sm100" and ops.conv_supported(op.in_shape, a, "fwd"):
+            ops.conv2d_fwd_sm100(x, self.pwb[op.name + ".weight"], bias, y, a.get("stride", 1), a.get("pad", 0), op.relu, stats)
+            return
+        wt = self.pwb[op.name + ".weight"].permute(0, 3, 1, 2)
+        out = F.conv2d(x.permute(0, 3, 1, 2), wt, bias.to(self.act_dtype) if bias is not None else None, a.get("stride", 1), a.get("pad", 0))
+        if op.relu:
+            out = F.relu(out)
+        y.copy_(out.permute(0, 2, 3, 1))
+        if stats is not None:
+            yf = y.float().reshape(-1, y.shape[-1])
+            stats[0].copy_(yf.sum(0)); stats[1].copy_((yf * yf).sum(0))
+
+    def _bwd_conv(self, op, B):
+        a = op.attrs
+        x, y, dy = self.T(op.x, B), self.T(op.y, B), self.G(op.y, B)
+        if op.relu:  # dy <- dy * (y > 0), in place (y is the post-ReLU output)
+            ops.relu_bwd_(dy, y, self.impl["bn"])
+        name = op.name + ".weight"
+        gw, gb = self.pg[name], self.pg.get(op.name + ".bias")
+        s, p = a.get("stride", 1), a.get("pad", 0)
+        if self.impl["conv_wgrad"] == "sm100" and ops.conv_supported(op.in_shape, a, "wgrad"):
+            ops.conv2d_wgrad_sm100(x, dy, gw, gb, s, p)
+        else:
+            _, dw, db = torch.ops.aten.convolution_backward(
+                dy.permute(0, 3, 1, 2), x.permute(0, 3, 1, 2), self.pwb[name].permute(0, 3, 1, 2),
+                [a["cout"]] if gb is not None else None, [s, s], [p, p], [1, 1], False, [0, 0], 1, [False, True, gb is not None])
+            gw.copy_(dw.permute(0, 2, 3, 1))
+            if gb is not None:
+                gb.copy_(db)
+        if not op.need_dx:
+            return
+        dx = self.G(op.x, B)
+        if self.impl["conv_dgrad"] == "sm100" and ops.conv_supported(op.in_shape, a, "dgrad"):
+            ops.conv2d_dgrad_sm100(dy, self.pwb[name], dx, s, p, op.acc_dx)
+            return
+        di, _, _ = torch.ops.aten.convolution_backward(
+            dy.permute(0, 3, 1, 2), x.permute(0, 3, 1, 2), self.pwb[name].permute(0, 3, 1, 2), None, [s, s], [p, p], [1, 1],
+            False, [0, 0], 1, [True, False, False])
+        di = di.permute(0, 2, 3, 1)
+        if op.acc_dx:
+            dx.add_(di)
+        else:
+            dx.copy_(di)
+
+    # ---- batch norm (+ residual + relu) ------------------------------------------------------------------------------
+    def _fwd_bn(self, op, B, train):
+        a = op.attrs
+        x, y = self.T(op.x, B), self.T(op.y, B)
+        res = self.T(op.res, B) if op.res is not None else None
+        gamma, beta = self.pw[op.name + ".weight"], self.pw[op.name + ".bias"]
+        rm, rv = self.pw[op.name + ".running_mean"], self.pw[op.name + ".running_var"]
+        prod = op.saved["producer"]
+        stats = prod.saved["stats"] if (prod is not None and prod.saved.get("want_stats")) else None
+        count = x.numel() // x.shape[-1]
+        ops.bn_fwd(x, y, res, gamma, beta, rm, rv, stats, op.saved["mean_rstd"], count, a.get("eps", 1e-5),
+                   a.get("momentum", 0.1), train, op.relu, self.impl["bn"])
+
+    def _bwd_bn(self, op, B):
+        x, y, dy = self.T(op.x, B), self.T(op.y, B), self.G(op.y, B)
+        dres = self.G(op.res, B) if op.res is not None else None
+        dx = self.G(op.x, B)
+        gamma = self.pw[op.name + ".weight"]
+        ops.bn_bwd(dy, y, x, gamma, op.saved["mean_rstd"], op.saved["dsum"], dx, dres,
+                   self.pg[op.name + ".weight"], self.pg[op.name + ".bias"], op.relu, self.impl["bn"])
+
+    # ---- pooling ---------------------------------------------------------------------------------------------------
+    def _fwd_maxpool(self, op, B, train):
+        ops.maxpool2_fwd(self.T(op.x, B), self.T(op.y, B), op.saved["idx"][:B], self.impl["pool"])
+
+    def _bwd_maxpool(self, op, B):
+        ops.maxpool2_bwd(self.G(op.y, B), op.saved["idx"][:B], self.G(op.x, B), self.impl["pool"])
+
+    def _fwd_avgpool(self, op, B, train):
+        ops.avgpool_fwd(self.T(op.x, B), self.T(op.y, B), self.impl["pool"])
+
+    def _bwd_avgpool(self, op, B):
+        ops.avgpool_bwd(self.G(op.y, B), self.G(op.x, B), self.impl["pool"])
+
+    # ---- dropout ---------------------------------------------------------------------------------------------------
+    def _fwd_dropout(self, op, B, train):
+        x, y = self.T(op.x, B), self.T(op.y, B)
+        if not train:
+            y.copy_(x)
+            return
+        ops.dropout_fwd(x.reshape(B, -1), y.reshape(B, -1), op.saved["mask"][:B].reshape(B, -1), op.attrs["p"], self.seed,
+                        self.step_counter, op.node, self.impl["dropout"])
+
+    def _bwd_dropout(self, op, B):
+        ops.dropout_bwd(self.G(op.y, B).reshape(B, -1), op.saved["mask"][:B].reshape(B, -1), self.G(op.x, B).reshape(B, -1),
+                        op.attrs["p"], self.impl["dropout"])
+
+    # ---- linear -----------------------------------------------------------------------------------------------------
+    def _fwd_linear(self, op, B, train):
+        x, y = self.T(op.x, B).reshape(B, -1), self.T(op.y, B)
+        ops.linear_fwd(x, self.pwb[op.name + ".weight"], self.pw.get(op.name + ".bias"), y, op.relu, self.impl["linear"])
+
+    def _bwd_linear(self, op, B):
+        x, y, dy = self.T(op.x, B).reshape(B, -1), self.T(op.y, B), self.G(op.y, B)
+        if op.relu:
+            ops.relu_bwd_(dy, y, self.impl["bn"])
+        dx = self.G(op.x, B).reshape(B, -1) if op.need_dx else None
+        ops.linear_bwd(x, dy, self.pwb[op.name + ".weight"], dx, self.pg[op.name + ".weight"], self.pg.get(op.name + ".bias"),
+                       op.acc_dx, self.impl["linear"])
+
+
+class NativeTrainer:
+    """Trainer with the TorchTrainer interface whose forward/backward is ``NativeNet``."""
+    name = "native"
+
+    def __init__(self, layout, args, device, max_shard: int, impl="auto"):
+        self.layout, self.args = layout, args
+        self.device = torch.device(device)
+        assert self.device.type == "cuda", "the native trainer runs on sm_100a devices only"
+        n = layout.n_total
+        self.w = torch.zeros(n, dtype=torch.float32, device=device)
+        self.wb = torch.zeros(n, dtype=torch.bfloat16, device=device)
+        self.g = torch.zeros(n, dtype=torch.float32, device=device)
+        self.m = torch.zeros(n, dtype=torch.float32, device=device)
+        self.bs = args.bs
+        self.net = NativeNet(layout, device, self.bs, impl, seed=args.seed)
+        self.net.bind(self.w, self.wb, self.g)
+        self.opt = ops.FlatSGD(n, device, args.client_lr, args.client_moment, 10.0, args.clip)
+        self.loss_sum = torch.zeros(1, dtype=torch.float32, device=device)
+        self.use_graphs = not args.no_graphs
+        self.max_shard = max_shard
+        self.perm = torch.zeros(max(1, max_shard), dtype=torch.int64, device=device)
+        self.cursor = torch.zeros(1, dtype=torch.int32, device=device)
+        self.y = torch.zeros(self.bs, dtype=torch.int64, device=device)
+        C, H, W = layout.in_shape
+        self.x = torch.zeros(self.bs, H, W, C, dtype=ACT, device=device)
+        self._graphs = {}
+        self._eval_nets = {}
+
+    def _step(self, dataset, B, w0):
+        meta = dataset.meta
+        ops.gather_normalize(dataset.data, self.perm, meta.mean, meta.std, out=self.x[:B], nhwc=True, cursor=self.cursor,
+                             targets=dataset.targets, out_labels=self.y, batch=B)
+        ops.ext().advance_cursor(self.cursor, B)
+        logits = self.net.forward(self.x[:B], True)
+        _, dl = ops.softmax_xent(logits, self.y[:B], True, self.loss_sum)
+        self.net.backward(dl)
+        self.opt.step(self.w, self.g, self.m, w0=w0, w_bf16=self.wb)
+        self.net.step_counter += 1
+
+    def _get_graph(self, dataset, B, w0):
+        key = (B, dataset.data.data_ptr(), w0.data_ptr())
+        if key in self._graphs:
+            return self._graphs[key]
+        keep = (self.w.clone(), self.wb.clone(), self.m.clone(), self.cursor.clone(), self.loss_sum.clone(),
+                self.net.step_counter.clone())
+        s = torch.cuda.Stream(self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            for _ in range(3):
+                self.cursor.zero_()
+                self._step(dataset, B, w0)
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        self.cursor.zero_()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self._step(dataset, B, w0)
+        self.w.copy_(keep[0]); self.wb.copy_(keep[1]); self.m.copy_(keep[2]); self.cursor.copy_(keep[3])
+        self.loss_sum.copy_(keep[4]); self.net.step_counter.copy_(keep[5])
+        self._graphs[key] = graph
+        return graph
+
+    def train_agent(self, agent, w_global, out, rnd: int = 0):
+        args, bs = self.args, self.bs
+        dataset, n = agent.dataset, agent.n_data
+        self.loss_sum.zero_()
+        graphs = self.use_graphs and n <= self.max_shard
+        if graphs:
+            full = self._get_graph(dataset, bs, w_global) if n >= bs else None
+            tail = self._get_graph(dataset, n % bs, w_global) if n % bs else None
+        ops.round_init(w_global, self.w, self.wb, self.m)
+        steps = 0
+        for ep in range(args.local_ep):
+            idx = agent.epoch_indices(args.seed, rnd, ep)
+            self.perm[:n].copy_(idx)
+            self.cursor.zero_()
+            for _ in range(n // bs):
+                full.replay() if graphs else self._step(dataset, bs, w_global)
+            if n % bs:
+                tail.replay() if graphs else self._step(dataset, n % bs, w_global)
+            steps += (n + bs - 1) // bs
+        if out.data_ptr() != self.w.data_ptr():
+            out.copy_(self.w)
+        return {"loss_sum": self.loss_sum, "steps": steps}
+
+    def launches_per_step(self):
+        return ops.LAUNCH_COUNTER.per_step if hasattr(ops, "LAUNCH_COUNTER") else 0
+
+    @torch.no_grad()
+    def eval_forward(self, w):
+        """Eval-mode forward of parameters ``w`` through the native executor (running BN statistics, no dropout)."""
+        key = w.data_ptr()
+        if key not in self._eval_nets:
+            net = NativeNet(self.layout, self.device, self.bs, self.net.impl, seed=self.args.seed)
+            self._eval_nets = {key: (net, torch.zeros(self.layout.n_total, dtype=ACT, device=self.device))}
+        net, wb = self._eval_nets[key]
+        wb.copy_(w)
+        net.bind(w, wb, None)
+
+        def fwd(x_nchw):
+            x = x_nchw.permute(0, 2, 3, 1).to(ACT).contiguous()
+            return net.forward(x, False).clone()
+        return fwd

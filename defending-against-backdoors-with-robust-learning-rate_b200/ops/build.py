@@ -44,10 +44,11 @@ def _cutlass_include():
 
 
 def _hash(paths, extra=""):
-    h = hashlib.sha256(extra.encode())
-    for p in sorted(paths):
+    """Content hash that is independent of where the repo lives (the gpurun box unpacks it under a scratch path)."""
+    h = hashlib.sha256(" ".join(a for a in extra.split() if not a.startswith(("-I", "-L"))).encode())
+    for p in sorted(paths, key=os.path.basename):
         with open(p, "rb") as f:
-            h.update(p.encode()); h.update(f.read())
+            h.update(os.path.basename(p).encode()); h.update(f.read())
     return h.hexdigest()
 
 
