@@ -422,7 +422,7 @@ class NativeTrainer:
         torch.cuda.current_stream(self.device).wait_stream(s)
         self.cursor.zero_()
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        with torch.cuda.graph(graph, capture_error_mode="thread_local"):
             self._step(dataset, B, w0)
         self.w.copy_(keep[0]); self.wb.copy_(keep[1]); self.m.copy_(keep[2]); self.cursor.copy_(keep[3])
         self.loss_sum.copy_(keep[4]); self.net.step_counter.copy_(keep[5])

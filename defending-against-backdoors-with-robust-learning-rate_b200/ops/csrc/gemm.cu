@@ -1,0 +1,327 @@
+// tcgen05 / TMEM / TMA GEMM and implicit-GEMM convolution for sm_100a (forward and data-gradient of every conv /
+// linear layer of the model zoo; replaces the cuDNN / cuBLAS calls behind src/models.py:22-31,47-58 and autograd).
+//
+//   C[M, N] = A[M, K] * B[N, K]^T      bf16 operands (K-major, 128-byte swizzled tiles), fp32 accumulation in TMEM
+//
+// * plain mode: A is a row-major [M][K] matrix (linear layers).
+// * conv mode : A is never materialised.  The activation tensor is NHWC; for filter tap (dy,dx) the 128 x 64 A tile of
+//   k-block (tap, channel-block) is ONE 4-D TMA box {64 ch, TW, TH, TN} of the input at spatial offset (dy-pad, dx-pad);
+//   out-of-bounds coordinates are zero-filled by the TMA unit, which implements the padding.  Strided (2x) convolutions
+//   read a parity-split copy of the input ([4][N][H/2][W/2][C], see space_to_depth in norm.cu) through per-tap plane
+//   offsets, so they use the same kernel.  The data-gradient of a 3x3/s1 conv is the same kernel on dY with the
+//   tap-flipped, transposed filter.
+// * warp-specialised CTA (192 threads): warp 0 = TMA producer, warp 1 = single-thread tcgen05.mma issuer,
+//   warps 2-5 = epilogue (tcgen05.ld TMEM->registers, bias / ReLU / residual-accumulate, bf16 pack, staging through
+//   shared memory for fully coalesced 16-byte global stores, and per-channel sum / sum-of-squares reductions that feed
+//   BatchNorm -- fused here so the conv output is not re-read for statistics).
+// * 4-stage (BN=64) / 3-stage (BN=128) smem ring with full/empty mbarriers; tcgen05.commit releases stages; two CTAs
+//   are resident per SM (<= 113 KB smem, <= 128 TMEM columns each) so one CTA's epilogue overlaps the other's mainloop.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "gemm.h"
+#include "umma.cuh"
+
+namespace rlr {
+
+using namespace umma;
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kThreads = 192;
+constexpr int kEpiThreads = 128;
+
+template <int BN>
+struct TileCfg {
+    static constexpr int kStages = BN == 64 ? 4 : 3;
+    static constexpr int kABytes = BM * BK * 2;
+    static constexpr int kBBytes = BN * BK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kPitch = BN * 2 + 16;                    // staging row pitch (bytes), conflict-free 16 B stores
+    static constexpr int kStagingBytes = BM * kPitch;
+    static constexpr int kRingBytes = kStages * kStageBytes;
+    static_assert(kStagingBytes <= kRingBytes, "staging aliases the operand ring");
+    static constexpr int kSmemBytes = kRingBytes + 1024 /*align slack*/ + 1024 /*barriers, row index*/;
+};
+
+struct __align__(8) SharedTail {
+    uint64_t full[4];
+    uint64_t empty[4];
+    uint64_t tmem_full;
+    uint32_t tmem_base;
+    uint32_t pad;
+    int row_index[BM];   // global output row of each tile row, -1 = masked
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 2)
+umma_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvGemmParams p) {
+    using Cfg = TileCfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    SharedTail* tail = reinterpret_cast<SharedTail*>(smem + Cfg::kRingBytes);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile_m = blockIdx.x, tile_n = blockIdx.y;
+
+    // ---- tile origin -------------------------------------------------------------------------------------------------
+    int n0 = 0, h0 = 0, w0 = 0;
+    if (p.mode == 1) {
+        const int tw_i = tile_m % p.tiles_w;
+        const int th_i = (tile_m / p.tiles_w) % p.tiles_h;
+        const int tn_i = tile_m / (p.tiles_w * p.tiles_h);
+        w0 = tw_i * p.TW; h0 = th_i * p.TH; n0 = tn_i * p.TN;
+    }
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA);
+        prefetch_tmap(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&tail->full[s], 1); mbar_init(&tail->empty[s], 1); }
+        mbar_init(&tail->tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(&tail->tmem_base, BN);
+    if (warp >= 2) {   // each epilogue thread owns one tile row: resolve its global output row once
+        const int r = threadIdx.x - 64;
+        int gi;
+        if (p.mode == 1) {
+            const int tw = r % p.TW, th = (r / p.TW) % p.TH, tn = r / (p.TW * p.TH);
+            const int w = w0 + tw, h = h0 + th, n = n0 + tn;
+            gi = (w < p.Wo && h < p.Ho && n < p.NB) ? ((n * p.Ho + h) * p.Wo + w) : -1;
+        } else {
+            gi = tile_m * BM + r;
+            if (gi >= p.M) gi = -1;
+        }
+        tail->row_index[r] = gi;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_acc = tail->tmem_base;
+
+    if (warp == 0) {
+        // ================================ TMA producer =====================================================================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                mbar_wait(&tail->empty[stage], phase ^ 1);
+                uint8_t* sa = smem + stage * Cfg::kStageBytes;
+                uint8_t* sb = sa + Cfg::kABytes;
+                mbar_expect_tx(&tail->full[stage], Cfg::kStageBytes);
+                if (p.mode == 1) {
+                    const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
+                    tma_load_4d(&tmA, &tail->full[stage], sa, cb * BK, w0 + p.dw[tap], h0 + p.dh[tap], n0 + p.dn[tap]);
+                } else {
+                    tma_load_2d(&tmA, &tail->full[stage], sa, kb * BK, tile_m * BM);
+                }
+                tma_load_2d(&tmB, &tail->full[stage], sb, kb * BK, tile_n * BN);
+                if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer (one thread) ==============================================================
+        if (lane == 0) {
+            constexpr uint32_t idesc = idesc_bf16(BM, BN, 0, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                mbar_wait(&tail->full[stage], phase);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+                const uint32_t sb = sa + Cfg::kABytes;
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {
+                    const uint64_t da = smem_desc_sw128(sa + k * 32, 16, 1024);
+                    const uint64_t db = smem_desc_sw128(sb + k * 32, 16, 1024);
+                    umma_bf16(tmem_acc, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(&tail->empty[stage]);   // frees this smem stage once the MMAs above have read it
+                if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(&tail->tmem_full);          // accumulator complete
+        }
+    } else {
+        // ================================ epilogue (4 warps, 128 threads) =======================================================
+        const int et = threadIdx.x - 64;                 // 0..127
+        const int lane_base = (warp & 3) * 32;           // TMEM lanes this warp may access
+        const int row = lane_base + lane;                // tile row held by this thread
+        mbar_wait(&tail->tmem_full, 0);
+        tc_fence_after();
+        uint8_t* staging = smem;                         // operand ring is idle now: reuse it
+        const int col0 = tile_n * BN;
+#pragma unroll
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_acc + ((uint32_t)lane_base << 16) + c0, v);
+            uint32_t packed[16];
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+                float a = __uint_as_float(v[j]), b = __uint_as_float(v[j + 1]);
+                if (p.bias) { a += p.bias[col0 + c0 + j]; b += p.bias[col0 + c0 + j + 1]; }
+                if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+                packed[j >> 1] = pack_bf16x2(a, b);
+            }
+            uint4* dst = reinterpret_cast<uint4*>(staging + row * Cfg::kPitch + c0 * 2);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) dst[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+        }
+        tc_fence_before();
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // epilogue-only named barrier: staging tile complete
+        // ---- coalesced 16-byte stores (optionally accumulating into the existing output) ----
+        constexpr int kChunks = BN * 2 / 16;             // 16 B chunks per row
+        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+        for (int idx = et; idx < BM * kChunks; idx += kEpiThreads) {
+            const int r = idx / kChunks, ch = idx - r * kChunks;
+            const int gi = tail->row_index[r];
+            if (gi < 0) continue;
+            uint4 val = *reinterpret_cast<const uint4*>(staging + r * Cfg::kPitch + ch * 16);
+            uint4* gp = reinterpret_cast<uint4*>(out + (size_t)gi * p.ldc + col0 + ch * 8);
+            if (p.accumulate) {
+                const uint4 old = *gp;
+                const __nv_bfloat162* o2 = reinterpret_cast<const __nv_bfloat162*>(&old);
+                __nv_bfloat162* v2 = reinterpret_cast<__nv_bfloat162*>(&val);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float2 a = __bfloat1622float2(v2[q]), b = __bfloat1622float2(o2[q]);
+                    v2[q] = __floats2bfloat162_rn(a.x + b.x, a.y + b.y);
+                }
+            }
+            *gp = val;
+        }
+        // ---- per-channel statistics of the (bf16-rounded) output tile: sum and sum of squares -> BatchNorm ----
+        if (p.stats) {
+            const int c = et % BN, part = et / BN;       // BN=64: part 0 -> sums, part 1 -> squares; BN=128: both
+            float s1 = 0.f, s2 = 0.f;
+            const __nv_bfloat16* colp = reinterpret_cast<const __nv_bfloat16*>(staging) + c;
+            for (int r = 0; r < BM; ++r) {
+                if (tail->row_index[r] < 0) continue;
+                const float x = __bfloat162float(*(colp + r * (Cfg::kPitch / 2)));
+                s1 += x; s2 += x * x;
+            }
+            if (BN == 64) {
+                atomicAdd(p.stats + (part ? p.N : 0) + col0 + c, part ? s2 : s1);
+            } else {
+                atomicAdd(p.stats + col0 + c, s1);
+                atomicAdd(p.stats + p.N + col0 + c, s2);
+            }
+        }
+    }
+    // ---- teardown ----------------------------------------------------------------------------------------------------------
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_acc, BN);
+}
+
+// =====================================================================================================================
+// host side: tensor maps + launch
+// =====================================================================================================================
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || !f) return nullptr;
+        fn = reinterpret_cast<EncodeTiledFn>(f);
+    }
+    return fn;
+}
+
+// bf16 tensor of `rank` dims (innermost first), 128-byte swizzle, zero fill out of bounds.
+cudaError_t make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                           const uint32_t* box) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return cudaErrorNotSupported;
+    cuuint64_t gd[5], gs[4];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+template <int BN>
+static cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, int m_tiles, cudaStream_t st) {
+    using Cfg = TileCfg<BN>;
+    static bool configured = false;
+    if (!configured) {
+        RLR_CUDA_CHECK(cudaFuncSetAttribute(umma_conv_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        configured = true;
+    }
+    dim3 grid(m_tiles, p.N / BN);
+    umma_conv_gemm_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
+    return cudaGetLastError();
+}
+
+static int pick_bn(int N) { return (N % 128 == 0) ? 128 : 64; }
+
+// Plain GEMM: out[M][ldc] (bf16) = A[M][K] * B[N][K]^T (+bias)(relu).  K % 64 == 0, N % 64 == 0.
+cudaError_t launch_gemm_bf16(const void* A, const void* B, void* out, int M, int N, int K, int lda, int ldb, int ldc,
+                             const float* bias, int relu, int accumulate, float* stats, cudaStream_t st) {
+    if (K % BK || N % 64 || M <= 0) return cudaErrorInvalidValue;
+    const int bn = pick_bn(N);
+    CUtensorMap tmA, tmB;
+    {
+        const uint64_t d[2] = {(uint64_t)K, (uint64_t)M}, s[1] = {(uint64_t)lda * 2};
+        const uint32_t b[2] = {BK, BM};
+        RLR_CUDA_CHECK(make_tmap_bf16(&tmA, A, 2, d, s, b));
+    }
+    {
+        const uint64_t d[2] = {(uint64_t)K, (uint64_t)N}, s[1] = {(uint64_t)ldb * 2};
+        const uint32_t b[2] = {BK, (uint32_t)bn};
+        RLR_CUDA_CHECK(make_tmap_bf16(&tmB, B, 2, d, s, b));
+    }
+    ConvGemmParams p{};
+    p.M = M; p.N = N; p.num_kb = K / BK; p.mode = 0;
+    p.out = out; p.ldc = ldc; p.bias = bias; p.stats = stats; p.relu = relu; p.accumulate = accumulate;
+    const int m_tiles = (M + BM - 1) / BM;
+    return bn == 128 ? launch_bn<128>(tmA, tmB, p, m_tiles, st) : launch_bn<64>(tmA, tmB, p, m_tiles, st);
+}
+
+static int pow2_ceil(int x) { int p = 1; while (p < x) p <<= 1; return p; }
+
+// Implicit-GEMM convolution.  `x` is [planes*NB][Hin][Win][Cin] bf16 NHWC (planes = 1, or 4 parity planes for stride 2),
+// `w` is [Cout][ntaps*Cin] bf16 (tap-major K), out is [NB*Ho*Wo][ldc] bf16.  Taps are given as input offsets.
+cudaError_t launch_conv_bf16(const void* x, const void* w, void* out, int NB, int planes, int Hin, int Win, int Cin, int Ho, int Wo,
+                             int Cout, int ldc, int ntaps, const int* dh, const int* dw, const int* dplane, const float* bias,
+                             int relu, int accumulate, float* stats, cudaStream_t st) {
+    if (Cin % BK || Cout % 64 || ntaps < 1 || ntaps > 9) return cudaErrorInvalidValue;
+    const int bn = pick_bn(Cout);
+    ConvGemmParams p{};
+    // output tile: TW x TH x TN = 128 output pixels, TW/TH powers of two covering the image
+    int TW = pow2_ceil(Wo); if (TW > BM) TW = BM;
+    int TH = pow2_ceil(Ho); if (TW * TH > BM) TH = BM / TW;
+    int TN = BM / (TW * TH);
+    p.TW = TW; p.TH = TH; p.TN = TN;
+    p.tiles_w = (Wo + TW - 1) / TW; p.tiles_h = (Ho + TH - 1) / TH;
+    const int tiles_n = (NB + TN - 1) / TN;
+    const int m_tiles = p.tiles_w * p.tiles_h * tiles_n;
+    p.M = NB * Ho * Wo; p.N = Cout; p.mode = 1; p.cblocks = Cin / BK; p.num_kb = ntaps * p.cblocks; p.ntaps = ntaps;
+    p.Ho = Ho; p.Wo = Wo; p.NB = NB;
+    for (int t = 0; t < ntaps; ++t) { p.dh[t] = (int8_t)dh[t]; p.dw[t] = (int8_t)dw[t]; p.dn[t] = dplane[t] * NB; }
+    p.out = out; p.ldc = ldc; p.bias = bias; p.stats = stats; p.relu = relu; p.accumulate = accumulate;
+    CUtensorMap tmA, tmB;
+    {
+        const uint64_t d[4] = {(uint64_t)Cin, (uint64_t)Win, (uint64_t)Hin, (uint64_t)planes * NB};
+        const uint64_t s[3] = {(uint64_t)Cin * 2, (uint64_t)Win * Cin * 2, (uint64_t)Hin * Win * Cin * 2};
+        const uint32_t b[4] = {BK, (uint32_t)TW, (uint32_t)TH, (uint32_t)TN};
+        RLR_CUDA_CHECK(make_tmap_bf16(&tmA, x, 4, d, s, b));
+    }
+    {
+        const uint64_t K = (uint64_t)ntaps * Cin;
+        const uint64_t d[2] = {K, (uint64_t)Cout}, s[1] = {K * 2};
+        const uint32_t b[2] = {BK, (uint32_t)bn};
+        RLR_CUDA_CHECK(make_tmap_bf16(&tmB, w, 2, d, s, b));
+    }
+    return bn == 128 ? launch_bn<128>(tmA, tmB, p, m_tiles, st) : launch_bn<64>(tmA, tmB, p, m_tiles, st);
+}
+
+}  // namespace rlr

@@ -1,5 +1,67 @@
-// tcgen05 / TMA GEMM + implicit-GEMM convolution launchers (see gemm.cu).
+// tcgen05 / TMA GEMM + implicit-GEMM convolution launchers (gemm.cu, wgrad.cu) and the memory-bound layer kernels
+// (norm.cu).  Raw pointers + stream; bindings in gemm_binding.cpp.
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+
+namespace rlr {
+
+struct ConvGemmParams {
+    int M, N, num_kb;
+    int mode;                  // 0 plain [M][K] A operand, 1 implicit conv (4-D NHWC A operand)
+    int cblocks;               // Cin / 64
+    int TW, TH, TN;            // output tile = TW x TH x TN pixels (= 128)
+    int Ho, Wo, NB;
+    int tiles_w, tiles_h;
+    int ntaps;
+    int8_t dh[9], dw[9];       // per tap: input row / col offset relative to the output pixel (in plane coordinates)
+    int dn[9];                 // per tap: image offset (parity plane * NB) for strided convs
+    void* out;                 // bf16 [M][ldc]
+    int ldc;
+    const float* bias;         // [N] or null
+    float* stats;              // [2][N] (sum, sum of squares) or null
+    int relu, accumulate;
+};
+
+cudaError_t launch_gemm_bf16(const void* A, const void* B, void* out, int M, int N, int K, int lda, int ldb, int ldc,
+                             const float* bias, int relu, int accumulate, float* stats, cudaStream_t st);
+cudaError_t launch_conv_bf16(const void* x, const void* w, void* out, int NB, int planes, int Hin, int Win, int Cin, int Ho, int Wo,
+                             int Cout, int ldc, int ntaps, const int* dh, const int* dw, const int* dplane, const float* bias,
+                             int relu, int accumulate, float* stats, cudaStream_t st);
+
+// ---- norm.cu: NHWC bf16 layer kernels -----------------------------------------------------------------------------
+// per-channel sum / sum of squares of x[M][C]
+cudaError_t launch_channel_stats(const __nv_bfloat16* x, long long M, int C, float* stats /*[2][C], accumulates*/, int num_sms, cudaStream_t st);
+// finalize statistics: mean/rstd (+ running stats update with momentum, unbiased variance)
+cudaError_t launch_bn_finalize(const float* stats, float* mean_rstd, float* running_mean, float* running_var, int C, float count,
+                               float eps, float momentum, int train, cudaStream_t st);
+// y = act(gamma * (x - mean) * rstd + beta [+ res])
+cudaError_t launch_bn_apply(const __nv_bfloat16* x, const __nv_bfloat16* res, __nv_bfloat16* y, const float* gamma, const float* beta,
+                            const float* mean_rstd, long long M, int C, int relu, int num_sms, cudaStream_t st);
+// dsum[0][c] = sum dz, dsum[1][c] = sum dz * xhat   (dz = dy * (y > 0) if relu)
+cudaError_t launch_bn_bwd_reduce(const __nv_bfloat16* dy, const __nv_bfloat16* y, const __nv_bfloat16* x, const float* mean_rstd,
+                                 float* dsum /*accumulates*/, long long M, int C, int relu, int num_sms, cudaStream_t st);
+// dx = gamma * rstd * (dz - dsum0/M - xhat * dsum1/M); dres = dz; dgamma = dsum1, dbeta = dsum0
+cudaError_t launch_bn_bwd_apply(const __nv_bfloat16* dy, const __nv_bfloat16* y, const __nv_bfloat16* x, const float* gamma,
+                                const float* mean_rstd, const float* dsum, __nv_bfloat16* dx, __nv_bfloat16* dres, float* dgamma,
+                                float* dbeta, long long M, int C, int relu, int num_sms, cudaStream_t st);
+cudaError_t launch_relu_bwd(__nv_bfloat16* dy, const __nv_bfloat16* y, long long n, int num_sms, cudaStream_t st);
+cudaError_t launch_maxpool2_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, uint8_t* idx, int B, int H, int W, int C, cudaStream_t st);
+cudaError_t launch_maxpool2_bwd(const __nv_bfloat16* dy, const uint8_t* idx, __nv_bfloat16* dx, int B, int H, int W, int C, cudaStream_t st);
+cudaError_t launch_avgpool_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, int B, int HW, int C, cudaStream_t st);
+cudaError_t launch_avgpool_bwd(const __nv_bfloat16* dy, __nv_bfloat16* dx, int B, int HW, int C, cudaStream_t st);
+cudaError_t launch_dropout_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, uint8_t* mask, long long n, float p, uint64_t seed,
+                               const long long* step, uint64_t stream, cudaStream_t st);
+cudaError_t launch_dropout_bwd(const __nv_bfloat16* dy, const uint8_t* mask, __nv_bfloat16* dx, long long n, float p, cudaStream_t st);
+// x[NB][H][W][C] -> four parity planes [4][NB][H/2][W/2][C] (plane = (h&1)*2 + (w&1)); H, W even
+cudaError_t launch_space_to_depth(const __nv_bfloat16* x, __nv_bfloat16* y, int NB, int H, int W, int C, int num_sms, cudaStream_t st);
+// tap-flipped transposed filter for the data gradient: wt[ci][8-t][co] = w[co][t][ci]   (3x3) / wt[ci][co] = w[co][ci] (1x1)
+cudaError_t launch_filter_transpose(const __nv_bfloat16* w, __nv_bfloat16* wt, int Cout, int ntaps, int Cin, cudaStream_t st);
+// small dense layers on CUDA cores (heads with N=10): y = x W^T + b ; dx = dy W ; dW = dy^T x ; db = sum dy
+cudaError_t launch_linear_small_fwd(const __nv_bfloat16* x, const __nv_bfloat16* w, const float* bias, __nv_bfloat16* y, int B, int K,
+                                    int N, int relu, cudaStream_t st);
+cudaError_t launch_linear_small_bwd(const __nv_bfloat16* x, const __nv_bfloat16* dy, const __nv_bfloat16* w, __nv_bfloat16* dx,
+                                    float* dw, float* db, int B, int K, int N, int accumulate_dx, cudaStream_t st);
+
+}  // namespace rlr

@@ -1,3 +1,147 @@
+// Python bindings for the tcgen05 GEMM / implicit-GEMM conv kernels (gemm.cu) and the NHWC layer kernels (norm.cu).
 #include <torch/extension.h>
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <c10/cuda/CUDAStream.h>
+
+#include <vector>
+
 #include "gemm.h"
-void register_gemm_bindings(py::module_& m) { (void)m; }
+
+namespace {
+inline cudaStream_t cur_stream() { return c10::cuda::getCurrentCUDAStream().stream(); }
+inline int num_sms() { return at::cuda::getCurrentDeviceProperties()->multiProcessorCount; }
+inline void check(cudaError_t e, const char* what) { TORCH_CHECK(e == cudaSuccess, what, ": ", cudaGetErrorString(e)); }
+template <typename T>
+inline T* opt(const c10::optional<at::Tensor>& t) { return t.has_value() && t->defined() ? reinterpret_cast<T*>(t->data_ptr()) : nullptr; }
+inline const __nv_bfloat16* bf(const at::Tensor& t) {
+    TORCH_CHECK(t.is_cuda() && t.scalar_type() == at::kBFloat16 && t.is_contiguous(), "expected contiguous CUDA bf16 tensor");
+    return reinterpret_cast<const __nv_bfloat16*>(t.data_ptr());
+}
+inline __nv_bfloat16* bfm(at::Tensor& t) { return const_cast<__nv_bfloat16*>(bf(t)); }
+inline const __nv_bfloat16* bfo(const c10::optional<at::Tensor>& t) { return t.has_value() && t->defined() ? bf(*t) : nullptr; }
+inline float* f32(const at::Tensor& t) {
+    TORCH_CHECK(t.is_cuda() && t.scalar_type() == at::kFloat && t.is_contiguous(), "expected contiguous CUDA fp32 tensor");
+    return reinterpret_cast<float*>(t.data_ptr());
+}
+
+// out[M][N] = A[M][K] @ B[N][K]^T (+bias)(relu)
+void gemm_bf16(at::Tensor A, at::Tensor B, at::Tensor out, c10::optional<at::Tensor> bias, bool relu, bool accumulate,
+               c10::optional<at::Tensor> stats) {
+    c10::cuda::CUDAGuard g(A.device());
+    const int M = A.size(0), K = A.size(1), N = B.size(0);
+    TORCH_CHECK(B.size(1) == K && out.size(0) == M && out.size(1) == N);
+    check(rlr::launch_gemm_bf16(bf(A), bf(B), bfm(out), M, N, K, K, K, N, opt<const float>(bias), relu, accumulate, opt<float>(stats),
+                                cur_stream()), "gemm_bf16");
+}
+
+// x: [planes*NB, Hin, Win, Cin]; w: [Cout, ntaps*Cin]; out: [NB, Ho, Wo, Cout]
+void conv_bf16(at::Tensor x, at::Tensor w, at::Tensor out, int64_t NB, int64_t planes, std::vector<int64_t> dh, std::vector<int64_t> dw,
+               std::vector<int64_t> dplane, c10::optional<at::Tensor> bias, bool relu, bool accumulate, c10::optional<at::Tensor> stats) {
+    c10::cuda::CUDAGuard g(x.device());
+    TORCH_CHECK(x.dim() == 4 && out.dim() == 4 && w.dim() == 2);
+    const int Hin = x.size(1), Win = x.size(2), Cin = x.size(3), Ho = out.size(1), Wo = out.size(2), Cout = out.size(3);
+    const int T = (int)dh.size();
+    TORCH_CHECK(x.size(0) == planes * NB && out.size(0) == NB && w.size(0) == Cout && w.size(1) == (int64_t)T * Cin);
+    int a[9], b[9], c[9];
+    for (int t = 0; t < T; ++t) { a[t] = (int)dh[t]; b[t] = (int)dw[t]; c[t] = (int)dplane[t]; }
+    check(rlr::launch_conv_bf16(bf(x), bf(w), bfm(out), (int)NB, (int)planes, Hin, Win, Cin, Ho, Wo, Cout, Cout, T, a, b, c,
+                                opt<const float>(bias), relu, accumulate, opt<float>(stats), cur_stream()), "conv_bf16");
+}
+
+void channel_stats(at::Tensor x, at::Tensor stats) {
+    c10::cuda::CUDAGuard g(x.device());
+    const int C = x.size(-1);
+    check(rlr::launch_channel_stats(bf(x), x.numel() / C, C, f32(stats), num_sms(), cur_stream()), "channel_stats");
+}
+void bn_finalize(at::Tensor stats, at::Tensor mean_rstd, at::Tensor rm, at::Tensor rv, double count, double eps, double momentum, bool train) {
+    c10::cuda::CUDAGuard g(stats.device());
+    const int C = mean_rstd.size(-1);
+    check(rlr::launch_bn_finalize(f32(stats), f32(mean_rstd), (float*)rm.data_ptr(), (float*)rv.data_ptr(), C, (float)count, (float)eps,
+                                  (float)momentum, train, cur_stream()), "bn_finalize");
+}
+void bn_apply(at::Tensor x, c10::optional<at::Tensor> res, at::Tensor y, at::Tensor gamma, at::Tensor beta, at::Tensor mean_rstd, bool relu) {
+    c10::cuda::CUDAGuard g(x.device());
+    const int C = x.size(-1);
+    check(rlr::launch_bn_apply(bf(x), bfo(res), bfm(y), (const float*)gamma.data_ptr(), (const float*)beta.data_ptr(), f32(mean_rstd),
+                               x.numel() / C, C, relu, num_sms(), cur_stream()), "bn_apply");
+}
+void bn_bwd(at::Tensor dy, at::Tensor y, at::Tensor x, at::Tensor gamma, at::Tensor mean_rstd, at::Tensor dsum, at::Tensor dx,
+            c10::optional<at::Tensor> dres, at::Tensor dgamma, at::Tensor dbeta, bool relu) {
+    c10::cuda::CUDAGuard g(x.device());
+    const int C = x.size(-1);
+    const long long M = x.numel() / C;
+    check(cudaMemsetAsync(dsum.data_ptr(), 0, sizeof(float) * 2 * C, cur_stream()), "bn_bwd/memset");
+    check(rlr::launch_bn_bwd_reduce(bf(dy), bf(y), bf(x), f32(mean_rstd), f32(dsum), M, C, relu, num_sms(), cur_stream()), "bn_bwd_reduce");
+    check(rlr::launch_bn_bwd_apply(bf(dy), bf(y), bf(x), (const float*)gamma.data_ptr(), f32(mean_rstd), f32(dsum), bfm(dx),
+                                   const_cast<__nv_bfloat16*>(bfo(dres)), (float*)dgamma.data_ptr(), (float*)dbeta.data_ptr(), M, C, relu,
+                                   num_sms(), cur_stream()), "bn_bwd_apply");
+}
+void relu_bwd(at::Tensor dy, at::Tensor y) {
+    c10::cuda::CUDAGuard g(dy.device());
+    check(rlr::launch_relu_bwd(bfm(dy), bf(y), dy.numel(), num_sms(), cur_stream()), "relu_bwd");
+}
+void maxpool2_fwd(at::Tensor x, at::Tensor y, at::Tensor idx) {
+    c10::cuda::CUDAGuard g(x.device());
+    check(rlr::launch_maxpool2_fwd(bf(x), bfm(y), (uint8_t*)idx.data_ptr(), x.size(0), x.size(1), x.size(2), x.size(3), cur_stream()), "maxpool2_fwd");
+}
+void maxpool2_bwd(at::Tensor dy, at::Tensor idx, at::Tensor dx) {
+    c10::cuda::CUDAGuard g(dx.device());
+    check(rlr::launch_maxpool2_bwd(bf(dy), (const uint8_t*)idx.data_ptr(), bfm(dx), dx.size(0), dx.size(1), dx.size(2), dx.size(3), cur_stream()), "maxpool2_bwd");
+}
+void avgpool_fwd(at::Tensor x, at::Tensor y) {
+    c10::cuda::CUDAGuard g(x.device());
+    check(rlr::launch_avgpool_fwd(bf(x), bfm(y), x.size(0), x.size(1) * x.size(2), x.size(3), cur_stream()), "avgpool_fwd");
+}
+void avgpool_bwd(at::Tensor dy, at::Tensor dx) {
+    c10::cuda::CUDAGuard g(dx.device());
+    check(rlr::launch_avgpool_bwd(bf(dy), bfm(dx), dx.size(0), dx.size(1) * dx.size(2), dx.size(3), cur_stream()), "avgpool_bwd");
+}
+void dropout_fwd(at::Tensor x, at::Tensor y, at::Tensor mask, double p, int64_t seed, at::Tensor step, int64_t stream) {
+    c10::cuda::CUDAGuard g(x.device());
+    check(rlr::launch_dropout_fwd(bf(x), bfm(y), (uint8_t*)mask.data_ptr(), x.numel(), (float)p, (uint64_t)seed,
+                                  (const long long*)step.data_ptr(), (uint64_t)stream, cur_stream()), "dropout_fwd");
+}
+void dropout_bwd(at::Tensor dy, at::Tensor mask, at::Tensor dx, double p) {
+    c10::cuda::CUDAGuard g(dx.device());
+    check(rlr::launch_dropout_bwd(bf(dy), (const uint8_t*)mask.data_ptr(), bfm(dx), dx.numel(), (float)p, cur_stream()), "dropout_bwd");
+}
+void space_to_depth(at::Tensor x, at::Tensor y) {
+    c10::cuda::CUDAGuard g(x.device());
+    check(rlr::launch_space_to_depth(bf(x), bfm(y), x.size(0), x.size(1), x.size(2), x.size(3), num_sms(), cur_stream()), "space_to_depth");
+}
+void filter_transpose(at::Tensor w, at::Tensor wt, int64_t Cout, int64_t ntaps, int64_t Cin) {
+    c10::cuda::CUDAGuard g(w.device());
+    check(rlr::launch_filter_transpose(bf(w), bfm(wt), Cout, ntaps, Cin, cur_stream()), "filter_transpose");
+}
+void linear_small_fwd(at::Tensor x, at::Tensor w, c10::optional<at::Tensor> bias, at::Tensor y, bool relu) {
+    c10::cuda::CUDAGuard g(x.device());
+    check(rlr::launch_linear_small_fwd(bf(x), bf(w), opt<const float>(bias), bfm(y), x.size(0), x.size(1), w.size(0), relu, cur_stream()), "linear_small_fwd");
+}
+void linear_small_bwd(at::Tensor x, at::Tensor dy, at::Tensor w, c10::optional<at::Tensor> dx, at::Tensor dw, c10::optional<at::Tensor> db,
+                      bool accumulate_dx) {
+    c10::cuda::CUDAGuard g(x.device());
+    check(rlr::launch_linear_small_bwd(bf(x), bf(dy), bf(w), const_cast<__nv_bfloat16*>(bfo(dx)), (float*)dw.data_ptr(), opt<float>(db),
+                                       x.size(0), x.size(1), w.size(0), accumulate_dx, cur_stream()), "linear_small_bwd");
+}
+}  // namespace
+
+void register_gemm_bindings(py::module_& m) {
+    m.def("gemm_bf16", &gemm_bf16);
+    m.def("conv_bf16", &conv_bf16);
+    m.def("channel_stats", &channel_stats);
+    m.def("bn_finalize", &bn_finalize);
+    m.def("bn_apply", &bn_apply);
+    m.def("bn_bwd", &bn_bwd);
+    m.def("relu_bwd", &relu_bwd);
+    m.def("maxpool2_fwd", &maxpool2_fwd);
+    m.def("maxpool2_bwd", &maxpool2_bwd);
+    m.def("avgpool_fwd", &avgpool_fwd);
+    m.def("avgpool_bwd", &avgpool_bwd);
+    m.def("dropout_fwd", &dropout_fwd);
+    m.def("dropout_bwd", &dropout_bwd);
+    m.def("space_to_depth", &space_to_depth);
+    m.def("filter_transpose", &filter_transpose);
+    m.def("linear_small_fwd", &linear_small_fwd);
+    m.def("linear_small_bwd", &linear_small_bwd);
+}

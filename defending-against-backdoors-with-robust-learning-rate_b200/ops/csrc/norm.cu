@@ -1,0 +1,485 @@
+// Memory-bound layer kernels over NHWC bf16 activations (one 16-byte vector = 8 channels per thread):
+// BatchNorm (training statistics, fused normalise + residual add + ReLU, two-pass backward), ReLU backward, 2x2
+// max-pool, global average pool, dropout (Philox), space-to-depth for strided convs, filter transpose for dgrad, and
+// the tiny classifier heads.  They replace the ATen elementwise / cuDNN-BN calls behind autograd in the reference's
+// local step (src/agent.py:46-48) and are what the tcgen05 conv kernels hand their outputs to.
+#include "common.cuh"
+#include "gemm.h"
+
+namespace rlr {
+
+struct bf8 { float v[8]; };
+__device__ __forceinline__ bf8 load8(const __nv_bfloat16* p) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+    bf8 r;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); r.v[2 * i] = f.x; r.v[2 * i + 1] = f.y; }
+    return r;
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const bf8& r) {
+    uint4 u;
+    u.x = pack_bf16x2(r.v[0], r.v[1]); u.y = pack_bf16x2(r.v[2], r.v[3]);
+    u.z = pack_bf16x2(r.v[4], r.v[5]); u.w = pack_bf16x2(r.v[6], r.v[7]);
+    *reinterpret_cast<uint4*>(p) = u;
+}
+static inline int rows_grid(long long M, int rows_per_block, int num_sms, int per_sm) {
+    long long want = (M + rows_per_block - 1) / rows_per_block;
+    long long cap = (long long)num_sms * per_sm;
+    return (int)(want < 1 ? 1 : (want > cap ? cap : want));
+}
+static inline bool chan_ok(int C) { return C >= 8 && C <= 2048 && (C % 8) == 0 && (256 % (C / 8)) == 0; }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// per-channel reductions:  out[0][c] += sum_r a(r,c),  out[1][c] += sum_r b(r,c)
+// MODE 0: a = x, b = x^2 (forward statistics)     MODE 1: a = dz, b = dz * xhat (backward)
+// ---------------------------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256) channel_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                                                               const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean_rstd,
+                                                               float* out, long long M, int C, int relu) {
+    extern __shared__ float sh[];   // [2][C]
+    const int tpr = C / 8, rpi = 256 / tpr;
+    const int cg = threadIdx.x % tpr, ry = threadIdx.x / tpr;
+    for (int i = threadIdx.x; i < 2 * C; i += 256) sh[i] = 0.f;
+    __syncthreads();
+    float a[8], b[8], mu[8], rs[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a[i] = 0.f; b[i] = 0.f; mu[i] = 0.f; rs[i] = 1.f; }
+    if (MODE == 1) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { mu[i] = mean_rstd[cg * 8 + i]; rs[i] = mean_rstd[C + cg * 8 + i]; }
+    }
+    for (long long r = (long long)blockIdx.x * rpi + ry; r < M; r += (long long)gridDim.x * rpi) {
+        const size_t off = (size_t)r * C + cg * 8;
+        const bf8 xv = load8(x + off);
+        if (MODE == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { a[i] += xv.v[i]; b[i] += xv.v[i] * xv.v[i]; }
+        } else {
+            bf8 dz = load8(dy + off);
+            if (relu) {
+                const bf8 yv = load8(y + off);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) dz.v[i] = yv.v[i] > 0.f ? dz.v[i] : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { a[i] += dz.v[i]; b[i] += dz.v[i] * (xv.v[i] - mu[i]) * rs[i]; }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { atomicAdd(&sh[cg * 8 + i], a[i]); atomicAdd(&sh[C + cg * 8 + i], b[i]); }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += 256) atomicAdd(out + i, sh[i]);
+}
+
+cudaError_t launch_channel_stats(const __nv_bfloat16* x, long long M, int C, float* stats, int num_sms, cudaStream_t st) {
+    if (!chan_ok(C)) return cudaErrorInvalidValue;
+    const int rpi = 256 / (C / 8);
+    channel_reduce_kernel<0><<<rows_grid(M, rpi * 8, num_sms, 4), 256, 2 * C * sizeof(float), st>>>(x, nullptr, nullptr, nullptr, stats, M, C, 0);
+    return cudaGetLastError();
+}
+cudaError_t launch_bn_bwd_reduce(const __nv_bfloat16* dy, const __nv_bfloat16* y, const __nv_bfloat16* x, const float* mean_rstd,
+                                 float* dsum, long long M, int C, int relu, int num_sms, cudaStream_t st) {
+    if (!chan_ok(C)) return cudaErrorInvalidValue;
+    const int rpi = 256 / (C / 8);
+    channel_reduce_kernel<1><<<rows_grid(M, rpi * 8, num_sms, 4), 256, 2 * C * sizeof(float), st>>>(x, dy, y, mean_rstd, dsum, M, C, relu);
+    return cudaGetLastError();
+}
+
+__global__ void bn_finalize_kernel(const float* __restrict__ stats, float* __restrict__ mean_rstd, float* running_mean,
+                                   float* running_var, int C, float count, float eps, float momentum, int train) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    if (train) {
+        const float mean = stats[c] / count;
+        const float var = fmaxf(stats[C + c] / count - mean * mean, 0.f);
+        mean_rstd[c] = mean;
+        mean_rstd[C + c] = rsqrtf(var + eps);
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+        const float unbiased = count > 1.f ? var * count / (count - 1.f) : var;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+    } else {
+        mean_rstd[c] = running_mean[c];
+        mean_rstd[C + c] = rsqrtf(running_var[c] + eps);
+    }
+}
+cudaError_t launch_bn_finalize(const float* stats, float* mean_rstd, float* running_mean, float* running_var, int C, float count,
+                               float eps, float momentum, int train, cudaStream_t st) {
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(stats, mean_rstd, running_mean, running_var, C, count, eps, momentum, train);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
+                                                         __nv_bfloat16* __restrict__ y, const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, const float* __restrict__ mean_rstd,
+                                                         long long M, int C, int relu) {
+    const int tpr = C / 8, rpi = 256 / tpr;
+    const int cg = threadIdx.x % tpr, ry = threadIdx.x / tpr;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = cg * 8 + i;
+        sc[i] = gamma[c] * mean_rstd[C + c];
+        sh[i] = beta[c] - mean_rstd[c] * sc[i];
+    }
+    for (long long r = (long long)blockIdx.x * rpi + ry; r < M; r += (long long)gridDim.x * rpi) {
+        const size_t off = (size_t)r * C + cg * 8;
+        bf8 v = load8(x + off);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v.v[i] = v.v[i] * sc[i] + sh[i];
+        if (res) {
+            const bf8 rv = load8(res + off);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v.v[i] += rv.v[i];
+        }
+        if (relu) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v.v[i] = fmaxf(v.v[i], 0.f);
+        }
+        store8(y + off, v);
+    }
+}
+cudaError_t launch_bn_apply(const __nv_bfloat16* x, const __nv_bfloat16* res, __nv_bfloat16* y, const float* gamma, const float* beta,
+                            const float* mean_rstd, long long M, int C, int relu, int num_sms, cudaStream_t st) {
+    if (!chan_ok(C)) return cudaErrorInvalidValue;
+    const int rpi = 256 / (C / 8);
+    bn_apply_kernel<<<rows_grid(M, rpi * 4, num_sms, 8), 256, 0, st>>>(x, res, y, gamma, beta, mean_rstd, M, C, relu);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
+                                                             const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+                                                             const float* __restrict__ mean_rstd, const float* __restrict__ dsum,
+                                                             __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dres,
+                                                             float* dgamma, float* dbeta, long long M, int C, int relu) {
+    const int tpr = C / 8, rpi = 256 / tpr;
+    const int cg = threadIdx.x % tpr, ry = threadIdx.x / tpr;
+    float mu[8], rs[8], g[8], k1[8], k2[8];
+    const float invM = 1.0f / (float)M;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = cg * 8 + i;
+        mu[i] = mean_rstd[c]; rs[i] = mean_rstd[C + c]; g[i] = gamma[c] * rs[i];
+        k1[i] = dsum[c] * invM; k2[i] = dsum[C + c] * invM;
+    }
+    if (blockIdx.x == 0 && ry == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { dbeta[cg * 8 + i] = dsum[cg * 8 + i]; dgamma[cg * 8 + i] = dsum[C + cg * 8 + i]; }
+    }
+    for (long long r = (long long)blockIdx.x * rpi + ry; r < M; r += (long long)gridDim.x * rpi) {
+        const size_t off = (size_t)r * C + cg * 8;
+        bf8 dz = load8(dy + off);
+        if (relu) {
+            const bf8 yv = load8(y + off);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dz.v[i] = yv.v[i] > 0.f ? dz.v[i] : 0.f;
+        }
+        if (dres) store8(dres + off, dz);
+        const bf8 xv = load8(x + off);
+        bf8 o;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o.v[i] = g[i] * (dz.v[i] - k1[i] - (xv.v[i] - mu[i]) * rs[i] * k2[i]);
+        store8(dx + off, o);
+    }
+}
+cudaError_t launch_bn_bwd_apply(const __nv_bfloat16* dy, const __nv_bfloat16* y, const __nv_bfloat16* x, const float* gamma,
+                                const float* mean_rstd, const float* dsum, __nv_bfloat16* dx, __nv_bfloat16* dres, float* dgamma,
+                                float* dbeta, long long M, int C, int relu, int num_sms, cudaStream_t st) {
+    if (!chan_ok(C)) return cudaErrorInvalidValue;
+    const int rpi = 256 / (C / 8);
+    bn_bwd_apply_kernel<<<rows_grid(M, rpi * 4, num_sms, 8), 256, 0, st>>>(dy, y, x, gamma, mean_rstd, dsum, dx, dres, dgamma, dbeta, M, C, relu);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) relu_bwd_kernel(__nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y, long long n8) {
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n8; q += (long long)gridDim.x * blockDim.x) {
+        bf8 d = load8(dy + 8 * q);
+        const bf8 yv = load8(y + 8 * q);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d.v[i] = yv.v[i] > 0.f ? d.v[i] : 0.f;
+        store8(dy + 8 * q, d);
+    }
+}
+cudaError_t launch_relu_bwd(__nv_bfloat16* dy, const __nv_bfloat16* y, long long n, int num_sms, cudaStream_t st) {
+    if (n % 8) return cudaErrorInvalidValue;
+    relu_bwd_kernel<<<rows_grid(n / 8, 256, num_sms, 8), 256, 0, st>>>(dy, y, n / 8);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// 2x2 / stride-2 max-pool (floor mode, like nn.MaxPool2d(2,2)); idx = 2*dy+dx of the first maximum
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) maxpool2_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                             uint8_t* __restrict__ idx, int B, int H, int W, int C) {
+    const int Ho = H / 2, Wo = W / 2, cg_n = C / 8;
+    const long long total = (long long)B * Ho * Wo * cg_n;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int cg = (int)(t % cg_n);
+        long long r = t / cg_n;
+        const int wo = (int)(r % Wo); r /= Wo;
+        const int ho = (int)(r % Ho);
+        const int b = (int)(r / Ho);
+        const __nv_bfloat16* base = x + (((size_t)b * H + 2 * ho) * W + 2 * wo) * C + cg * 8;
+        bf8 best = load8(base);
+        uint8_t bi[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int k = 1; k < 4; ++k) {
+            const bf8 v = load8(base + ((size_t)(k >> 1) * W + (k & 1)) * C);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) if (v.v[i] > best.v[i]) { best.v[i] = v.v[i]; bi[i] = (uint8_t)k; }
+        }
+        const size_t o = (((size_t)b * Ho + ho) * Wo + wo) * C + cg * 8;
+        store8(y + o, best);
+        uint2 pk;
+        pk.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
+        pk.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
+        *reinterpret_cast<uint2*>(idx + o) = pk;
+    }
+}
+__global__ void __launch_bounds__(256) maxpool2_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx,
+                                                             __nv_bfloat16* __restrict__ dx, int B, int H, int W, int C) {
+    const int Ho = H / 2, Wo = W / 2, cg_n = C / 8;
+    const long long total = (long long)B * H * W * cg_n;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int cg = (int)(t % cg_n);
+        long long r = t / cg_n;
+        const int w = (int)(r % W); r /= W;
+        const int h = (int)(r % H);
+        const int b = (int)(r / H);
+        bf8 o;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o.v[i] = 0.f;
+        const int ho = h >> 1, wo = w >> 1;
+        if (ho < Ho && wo < Wo) {
+            const size_t src = (((size_t)b * Ho + ho) * Wo + wo) * C + cg * 8;
+            const bf8 g = load8(dy + src);
+            const uint2 pk = *reinterpret_cast<const uint2*>(idx + src);
+            const int me = (h & 1) * 2 + (w & 1);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int k = ((i < 4 ? pk.x : pk.y) >> (8 * (i & 3))) & 0xff;
+                o.v[i] = (k == me) ? g.v[i] : 0.f;
+            }
+        }
+        store8(dx + (((size_t)b * H + h) * W + w) * C + cg * 8, o);
+    }
+}
+cudaError_t launch_maxpool2_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, uint8_t* idx, int B, int H, int W, int C, cudaStream_t st) {
+    if (C % 8) return cudaErrorInvalidValue;
+    const long long total = (long long)B * (H / 2) * (W / 2) * (C / 8);
+    maxpool2_fwd_kernel<<<rows_grid(total, 256, 148, 8), 256, 0, st>>>(x, y, idx, B, H, W, C);
+    return cudaGetLastError();
+}
+cudaError_t launch_maxpool2_bwd(const __nv_bfloat16* dy, const uint8_t* idx, __nv_bfloat16* dx, int B, int H, int W, int C, cudaStream_t st) {
+    if (C % 8) return cudaErrorInvalidValue;
+    const long long total = (long long)B * H * W * (C / 8);
+    maxpool2_bwd_kernel<<<rows_grid(total, 256, 148, 8), 256, 0, st>>>(dy, idx, dx, B, H, W, C);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void avgpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int HW, int C) {
+    const int cg_n = C / 8;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= B * cg_n) return;
+    const int b = t / cg_n, cg = t % cg_n;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int p = 0; p < HW; ++p) {
+        const bf8 v = load8(x + ((size_t)b * HW + p) * C + cg * 8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += v.v[i];
+    }
+    bf8 o;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o.v[i] = acc[i] / (float)HW;
+    store8(y + (size_t)b * C + cg * 8, o);
+}
+__global__ void avgpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx, int B, int HW, int C) {
+    const int cg_n = C / 8;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)B * HW * cg_n) return;
+    const int cg = (int)(t % cg_n);
+    const long long bp = t / cg_n;
+    const int b = (int)(bp / HW);
+    bf8 g = load8(dy + (size_t)b * C + cg * 8);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g.v[i] /= (float)HW;
+    store8(dx + (size_t)bp * C + cg * 8, g);
+}
+cudaError_t launch_avgpool_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, int B, int HW, int C, cudaStream_t st) {
+    if (C % 8) return cudaErrorInvalidValue;
+    avgpool_fwd_kernel<<<(B * (C / 8) + 127) / 128, 128, 0, st>>>(x, y, B, HW, C);
+    return cudaGetLastError();
+}
+cudaError_t launch_avgpool_bwd(const __nv_bfloat16* dy, __nv_bfloat16* dx, int B, int HW, int C, cudaStream_t st) {
+    if (C % 8) return cudaErrorInvalidValue;
+    const long long total = (long long)B * HW * (C / 8);
+    avgpool_bwd_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(dy, dx, B, HW, C);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// dropout: keep-mask from Philox4x32-10 keyed by (seed; element/8, step ^ stream); 16 random bits per element
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dropout_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                            uint8_t* __restrict__ mask, long long n8, float p, uint64_t seed,
+                                                            const long long* __restrict__ step, uint64_t stream) {
+    const Philox ph(seed);
+    const uint64_t str = ((uint64_t)(*step) << 20) ^ stream;
+    const uint32_t thr = (uint32_t)(p * 65536.0f);
+    const float scale = 1.0f / (1.0f - p);
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n8; q += (long long)gridDim.x * blockDim.x) {
+        const uint4 u = ph((uint64_t)q, str);
+        const uint32_t r[4] = {u.x, u.y, u.z, u.w};
+        bf8 v = load8(x + 8 * q);
+        uint8_t m[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint32_t bits = (r[i >> 1] >> (16 * (i & 1))) & 0xffffu;
+            m[i] = bits >= thr;
+            v.v[i] = m[i] ? v.v[i] * scale : 0.f;
+        }
+        store8(y + 8 * q, v);
+        uint2 pk;
+        pk.x = m[0] | (m[1] << 8) | (m[2] << 16) | (m[3] << 24);
+        pk.y = m[4] | (m[5] << 8) | (m[6] << 16) | (m[7] << 24);
+        *reinterpret_cast<uint2*>(mask + 8 * q) = pk;
+    }
+}
+__global__ void __launch_bounds__(256) dropout_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ mask,
+                                                            __nv_bfloat16* __restrict__ dx, long long n8, float scale) {
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n8; q += (long long)gridDim.x * blockDim.x) {
+        bf8 g = load8(dy + 8 * q);
+        const uint2 pk = *reinterpret_cast<const uint2*>(mask + 8 * q);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int k = ((i < 4 ? pk.x : pk.y) >> (8 * (i & 3))) & 0xff;
+            g.v[i] = k ? g.v[i] * scale : 0.f;
+        }
+        store8(dx + 8 * q, g);
+    }
+}
+cudaError_t launch_dropout_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, uint8_t* mask, long long n, float p, uint64_t seed,
+                               const long long* step, uint64_t stream, cudaStream_t st) {
+    if (n % 8) return cudaErrorInvalidValue;
+    dropout_fwd_kernel<<<rows_grid(n / 8, 256, 148, 8), 256, 0, st>>>(x, y, mask, n / 8, p, seed, step, stream);
+    return cudaGetLastError();
+}
+cudaError_t launch_dropout_bwd(const __nv_bfloat16* dy, const uint8_t* mask, __nv_bfloat16* dx, long long n, float p, cudaStream_t st) {
+    if (n % 8) return cudaErrorInvalidValue;
+    dropout_bwd_kernel<<<rows_grid(n / 8, 256, 148, 8), 256, 0, st>>>(dy, mask, dx, n / 8, 1.0f / (1.0f - p));
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// space-to-depth: x[NB][H][W][C] -> y[4][NB][H/2][W/2][C], plane = (h&1)*2 + (w&1)
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) space_to_depth_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                               int NB, int H, int W, int C) {
+    const int cg_n = C / 8, H2 = H / 2, W2 = W / 2;
+    const long long total = (long long)NB * H * W * cg_n;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int cg = (int)(t % cg_n);
+        long long r = t / cg_n;
+        const int w = (int)(r % W); r /= W;
+        const int h = (int)(r % H);
+        const int n = (int)(r / H);
+        const int plane = (h & 1) * 2 + (w & 1);
+        const uint4 v = *reinterpret_cast<const uint4*>(x + (((size_t)n * H + h) * W + w) * C + cg * 8);
+        *reinterpret_cast<uint4*>(y + ((((size_t)plane * NB + n) * H2 + (h >> 1)) * W2 + (w >> 1)) * C + cg * 8) = v;
+    }
+}
+cudaError_t launch_space_to_depth(const __nv_bfloat16* x, __nv_bfloat16* y, int NB, int H, int W, int C, int num_sms, cudaStream_t st) {
+    if (C % 8 || H % 2 || W % 2) return cudaErrorInvalidValue;
+    const long long total = (long long)NB * H * W * (C / 8);
+    space_to_depth_kernel<<<rows_grid(total, 256, num_sms, 8), 256, 0, st>>>(x, y, NB, H, W, C);
+    return cudaGetLastError();
+}
+
+// wt[ci][T-1-t][co] = w[co][t][ci]
+__global__ void filter_transpose_kernel(const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ wt, int Cout, int T, int Cin) {
+    const long long total = (long long)Cout * T * Cin;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int co = (int)(i % Cout);
+        const long long r = i / Cout;
+        const int tt = (int)(r % T);
+        const int ci = (int)(r / T);
+        wt[i] = w[((size_t)co * T + (T - 1 - tt)) * Cin + ci];   // writes coalesced over co
+    }
+}
+cudaError_t launch_filter_transpose(const __nv_bfloat16* w, __nv_bfloat16* wt, int Cout, int ntaps, int Cin, cudaStream_t st) {
+    const long long total = (long long)Cout * ntaps * Cin;
+    filter_transpose_kernel<<<(int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256), 256, 0, st>>>(w, wt, Cout, ntaps, Cin);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// small dense layers (classifier heads, N <= 32): CUDA cores, fp32 accumulation
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) linear_small_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+                                                                 const float* __restrict__ bias, __nv_bfloat16* __restrict__ y,
+                                                                 int B, int K, int N, int relu) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= B) return;
+    float acc[32];
+#pragma unroll
+    for (int n = 0; n < 32; ++n) acc[n] = 0.f;
+    for (int k = lane; k < K; k += 32) {
+        const float xv = __bfloat162float(x[(size_t)warp * K + k]);
+#pragma unroll
+        for (int n = 0; n < 32; ++n) if (n < N) acc[n] += xv * __bfloat162float(w[(size_t)n * K + k]);
+    }
+#pragma unroll
+    for (int n = 0; n < 32; ++n) {
+        if (n < N) {
+            float v = warp_sum(acc[n]);
+            if (lane == 0) {
+                v += bias ? bias[n] : 0.f;
+                if (relu) v = fmaxf(v, 0.f);
+                y[(size_t)warp * N + n] = __float2bfloat16(v);
+            }
+        }
+    }
+}
+cudaError_t launch_linear_small_fwd(const __nv_bfloat16* x, const __nv_bfloat16* w, const float* bias, __nv_bfloat16* y, int B, int K,
+                                    int N, int relu, cudaStream_t st) {
+    if (N > 32) return cudaErrorInvalidValue;
+    linear_small_fwd_kernel<<<(B * 32 + 127) / 128, 128, 0, st>>>(x, w, bias, y, B, K, N, relu);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) linear_small_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                                                                 const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ dx,
+                                                                 float* __restrict__ dw, float* __restrict__ db, int B, int K, int N,
+                                                                 int accumulate_dx) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n_dx = dx ? (long long)B * K : 0, n_dw = (long long)N * K;
+    if (t < n_dx) {                                   // dx[b][k] = sum_n dy[b][n] w[n][k]
+        const int b = (int)(t / K), k = (int)(t % K);
+        float acc = 0.f;
+        for (int n = 0; n < N; ++n) acc += __bfloat162float(dy[(size_t)b * N + n]) * __bfloat162float(w[(size_t)n * K + k]);
+        if (accumulate_dx) acc += __bfloat162float(dx[t]);
+        dx[t] = __float2bfloat16(acc);
+    } else if (t < n_dx + n_dw) {                     // dw[n][k] = sum_b dy[b][n] x[b][k]
+        const long long u = t - n_dx;
+        const int n = (int)(u / K), k = (int)(u % K);
+        float acc = 0.f;
+        for (int b = 0; b < B; ++b) acc += __bfloat162float(dy[(size_t)b * N + n]) * __bfloat162float(x[(size_t)b * K + k]);
+        dw[u] = acc;
+    } else if (db && t < n_dx + n_dw + N) {           // db[n] = sum_b dy[b][n]
+        const int n = (int)(t - n_dx - n_dw);
+        float acc = 0.f;
+        for (int b = 0; b < B; ++b) acc += __bfloat162float(dy[(size_t)b * N + n]);
+        db[n] = acc;
+    }
+}
+cudaError_t launch_linear_small_bwd(const __nv_bfloat16* x, const __nv_bfloat16* dy, const __nv_bfloat16* w, __nv_bfloat16* dx,
+                                    float* dw, float* db, int B, int K, int N, int accumulate_dx, cudaStream_t st) {
+    const long long total = (dx ? (long long)B * K : 0) + (long long)N * K + N;
+    linear_small_bwd_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(x, dy, w, dx, dw, db, B, K, N, accumulate_dx);
+    return cudaGetLastError();
+}
+
+}  // namespace rlr

@@ -1,0 +1,239 @@
+"""Layer primitives of the native executor (models/native.py), each with an ``sm100`` back-end (hand-written kernels
+of ops/csrc: gemm.cu = tcgen05/TMEM/TMA implicit-GEMM convolution + GEMM, norm.cu = NHWC bf16 layer kernels) and an
+``aten`` back-end (the same math through PyTorch library calls on the same buffers: CPU path + in-place oracle)."""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+_scratch = {}
+
+
+def _ext():
+    from . import ext
+    return ext()
+
+
+def scratch(tag, shape, dtype, device):
+    """Persistent scratch tensor (stable address: safe to bake into CUDA graphs)."""
+    key = (tag, tuple(shape), dtype, str(device))
+    t = _scratch.get(key)
+    if t is None:
+        t = _scratch[key] = torch.zeros(shape, dtype=dtype, device=device)
+    return t
+
+
+# =====================================================================================================================
+# convolution
+# =====================================================================================================================
+def conv_supported(in_shape, a, kind):
+    """Can the tcgen05 implicit-GEMM kernel run this conv?  ``in_shape`` = (H, W, Cin)."""
+    h, w, cin = in_shape
+    k, s, p, cout = a["k"], a.get("stride", 1), a.get("pad", 0), a["cout"]
+    if k not in (1, 3) or s not in (1, 2) or cout % 64:
+        return False
+    if kind == "fwd":
+        return (s == 1 or (h % 2 == 0 and w % 2 == 0)) and (cin % 64 == 0 or cin < 64)
+    if kind == "dgrad":
+        return s == 1 and cin % 64 == 0
+    return False
+
+
+def _taps(k, stride, pad):
+    dh, dw, pl = [], [], []
+    for dy in range(k):
+        for dx in range(k):
+            oy, ox = dy - pad, dx - pad
+            if stride == 1:
+                dh.append(oy); dw.append(ox); pl.append(0)
+            else:  # input index 2*o + off  ->  parity plane (off mod 2), shifted by floor(off / 2)
+                dh.append(oy // 2); dw.append(ox // 2); pl.append((oy % 2) * 2 + (ox % 2))
+    return dh, dw, pl
+
+
+def conv2d_fwd_sm100(x, w, bias, y, stride, pad, relu, stats, tag="fwd"):
+    """y[B,Ho,Wo,Cout] = conv(x[B,H,W,Cin], w[Cout,k,k,Cin]) (+bias)(ReLU); ``stats`` [2,Cout] gets per-channel sum / sum^2."""
+    e = _ext()
+    B, H, W, Cin = x.shape
+    Cout, k = w.shape[0], w.shape[1]
+    if Cin % 64:
+        cp = (Cin + 63) // 64 * 64
+        xp = scratch(("xpad", tag), (B, H, W, cp), x.dtype, x.device)
+        xp[..., :Cin].copy_(x)
+        wp = scratch(("wpad", tag, w.data_ptr()), (Cout, k, k, cp), w.dtype, w.device)
+        wp[..., :Cin].copy_(w)
+        x, w, Cin = xp, wp, cp
+    planes = 1
+    if stride == 2:
+        x4 = scratch(("s2d", tag), (4 * B, H // 2, W // 2, Cin), x.dtype, x.device)
+        e.space_to_depth(x, x4)
+        x, planes = x4, 4
+    dh, dw, pl = _taps(k, stride, pad)
+    if stats is not None:
+        stats.zero_()
+    e.conv_bf16(x, w.reshape(Cout, k * k * Cin), y, B, planes, dh, dw, pl, bias, bool(relu), False, stats)
+    return y
+
+
+def conv2d_dgrad_sm100(dy, w, dx, stride, pad, accumulate):
+    """dx[B,H,W,Cin] (+)= conv_transpose(dy[B,Ho,Wo,Cout], w[Cout,k,k,Cin]) for stride 1: a convolution of dy with
+    the tap-flipped, transposed filter and padding k-1-pad."""
+    assert stride == 1
+    e = _ext()
+    Cout, k, _, Cin = w.shape
+    B = dy.shape[0]
+    wt = scratch(("wt", w.data_ptr()), (Cin, k * k * Cout), w.dtype, w.device)
+    e.filter_transpose(w, wt, Cout, k * k, Cin)
+    dh, dw, pl = _taps(k, 1, k - 1 - pad)
+    e.conv_bf16(dy, wt, dx, B, 1, dh, dw, pl, None, False, bool(accumulate), None)
+    return dx
+
+
+# =====================================================================================================================
+# batch norm (+ residual + relu)
+# =====================================================================================================================
+def bn_fwd(x, y, res, gamma, beta, rm, rv, stats, mean_rstd, count, eps, momentum, train, relu, impl):
+    C = x.shape[-1]
+    if impl == "sm100":
+        e = _ext()
+        if train and stats is None:
+            stats = scratch(("bnstats", mean_rstd.data_ptr()), (2, C), torch.float32, x.device)
+            stats.zero_()
+            e.channel_stats(x, stats)
+        e.bn_finalize(stats if stats is not None else mean_rstd, mean_rstd, rm, rv, float(count), float(eps), float(momentum), bool(train))
+        e.bn_apply(x, res, y, gamma, beta, mean_rstd, bool(relu))
+        return
+    xf = x.float().reshape(-1, C)
+    if train:
+        if stats is not None:
+            mean = stats[0] / count
+            var = (stats[1] / count - mean * mean).clamp_min(0)
+        else:
+            mean = xf.mean(0)
+            var = xf.var(0, unbiased=False)
+        rm.mul_(1 - momentum).add_(momentum * mean)
+        rv.mul_(1 - momentum).add_(momentum * var * (count / max(1, count - 1)))
+        mean_rstd[0].copy_(mean); mean_rstd[1].copy_(torch.rsqrt(var + eps))
+    else:
+        mean_rstd[0].copy_(rm); mean_rstd[1].copy_(torch.rsqrt(rv + eps))
+    out = (xf - mean_rstd[0]) * (mean_rstd[1] * gamma) + beta
+    if res is not None:
+        out = out + res.float().reshape(-1, C)
+    if relu:
+        out = out.clamp_min(0)
+    y.copy_(out.reshape(y.shape))
+
+
+def bn_bwd(dy, y, x, gamma, mean_rstd, dsum, dx, dres, dgamma, dbeta, relu, impl):
+    C = x.shape[-1]
+    if impl == "sm100":
+        _ext().bn_bwd(dy, y, x, gamma, mean_rstd, dsum, dx, dres, dgamma, dbeta, bool(relu))
+        return
+    dz = dy.float().reshape(-1, C)
+    if relu:
+        dz = dz * (y.float().reshape(-1, C) > 0)
+    if dres is not None:
+        dres.copy_(dz.reshape(dres.shape))
+    xhat = (x.float().reshape(-1, C) - mean_rstd[0]) * mean_rstd[1]
+    s0, s1 = dz.sum(0), (dz * xhat).sum(0)
+    M = dz.shape[0]
+    dbeta.copy_(s0); dgamma.copy_(s1)
+    dx.copy_((gamma * mean_rstd[1] * (dz - s0 / M - xhat * s1 / M)).reshape(dx.shape))
+
+
+def relu_bwd_(dy, y, impl):
+    if impl == "sm100" and dy.numel() % 8 == 0:
+        _ext().relu_bwd(dy, y)
+    else:
+        dy.mul_(y > 0)
+
+
+# =====================================================================================================================
+# pooling / dropout
+# =====================================================================================================================
+def maxpool2_fwd(x, y, idx, impl):
+    if impl == "sm100" and x.shape[-1] % 8 == 0:
+        _ext().maxpool2_fwd(x, y, idx)
+        return
+    B, H, W, C = x.shape
+    Ho, Wo = H // 2, W // 2
+    win = x[:, :Ho * 2, :Wo * 2].reshape(B, Ho, 2, Wo, 2, C).permute(0, 1, 3, 5, 2, 4).reshape(B, Ho, Wo, C, 4)
+    v, i = win.float().max(-1)
+    y.copy_(v); idx.copy_(i)
+
+
+def maxpool2_bwd(dy, idx, dx, impl):
+    if impl == "sm100" and dx.shape[-1] % 8 == 0:
+        _ext().maxpool2_bwd(dy, idx, dx)
+        return
+    B, H, W, C = dx.shape
+    Ho, Wo = H // 2, W // 2
+    dx.zero_()
+    oh = F.one_hot(idx.long(), 4).to(dy.dtype) * dy.unsqueeze(-1)                   # [B,Ho,Wo,C,4]
+    dx[:, :Ho * 2, :Wo * 2].copy_(oh.reshape(B, Ho, Wo, C, 2, 2).permute(0, 1, 4, 2, 5, 3).reshape(B, Ho * 2, Wo * 2, C))
+
+
+def avgpool_fwd(x, y, impl):
+    if impl == "sm100":
+        _ext().avgpool_fwd(x, y)
+    else:
+        y.copy_(x.float().mean((1, 2), keepdim=True))
+
+
+def avgpool_bwd(dy, dx, impl):
+    if impl == "sm100":
+        _ext().avgpool_bwd(dy, dx)
+    else:
+        dx.copy_((dy.float() / (dx.shape[1] * dx.shape[2])).expand_as(dx))
+
+
+def dropout_fwd(x, y, mask, p, seed, step, stream, impl):
+    if impl == "sm100" and x.numel() % 8 == 0:
+        _ext().dropout_fwd(x, y, mask, float(p), int(seed), step, int(stream))
+        return
+    keep = torch.rand(x.shape, device=x.device) >= p
+    mask.copy_(keep)
+    y.copy_(x * keep / (1 - p))
+
+
+def dropout_bwd(dy, mask, dx, p, impl):
+    if impl == "sm100" and dx.numel() % 8 == 0:
+        _ext().dropout_bwd(dy, mask, dx, float(p))
+    else:
+        dx.copy_(dy * mask / (1 - p))
+
+
+# =====================================================================================================================
+# linear
+# =====================================================================================================================
+def linear_fwd(x, w, bias, y, relu, impl):
+    """y[B,N] = x[B,K] w[N,K]^T + b (ReLU).  N <= 32: CUDA-core head kernel; otherwise the tcgen05 GEMM."""
+    N, K = w.shape
+    if impl == "sm100":
+        if N <= 32:
+            _ext().linear_small_fwd(x.contiguous(), w, bias, y, bool(relu))
+            return
+        if K % 64 == 0 and N % 64 == 0:
+            _ext().gemm_bf16(x.contiguous(), w, y, bias, bool(relu), False, None)
+            return
+    out = F.linear(x, w.to(x.dtype), bias.to(x.dtype) if bias is not None else None)
+    if relu:
+        out = F.relu(out)
+    y.copy_(out)
+
+
+def linear_bwd(x, dy, w, dx, dw, db, acc_dx, impl):
+    N, K = w.shape
+    if impl == "sm100" and N <= 32:
+        _ext().linear_small_bwd(x.contiguous(), dy.contiguous(), w, dx, dw, db, bool(acc_dx))
+        return
+    dyf = dy.to(x.dtype)
+    dw.copy_(dyf.t() @ x)
+    if db is not None:
+        db.copy_(dyf.float().sum(0))
+    if dx is not None:
+        d = dyf @ w.to(x.dtype)
+        if acc_dx:
+            dx.add_(d)
+        else:
+            dx.copy_(d)

@@ -79,7 +79,7 @@ class TorchTrainer:
         torch.cuda.current_stream(self.device).wait_stream(s)
         self.cursor.zero_()
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        with torch.cuda.graph(graph, capture_error_mode="thread_local"):
             self._graph_body(dataset, B, w0)
         self.w.copy_(keep[0]); self.m.copy_(keep[1]); self.cursor.copy_(keep[2]); self.loss_sum.copy_(keep[3])
         self._graphs[key] = graph

@@ -54,7 +54,7 @@ def _agg_worker(rank, world, port, outdir, provider):
         tot = fa.flipped.clone()
         dist.all_reduce(tot)
         results[f"{mode}-{theta}"] = dict(err=float((got - ref).abs().max()), flipped=int(tot.item()), flipped_ref=nflip,
-                                          shadow_err=float((fa.w_bf16.float().cpu() - ref.bfloat16().float()).abs().max()))
+                                          shadow_err=float((fa.w_bf16.float().cpu() - got.bfloat16().float()).abs().max()))
         dist.barrier()
     torch.save(results, os.path.join(outdir, f"agg{rank}.pt"))
     fa.close()

@@ -1,0 +1,188 @@
+"""GPU numerics of the tcgen05 GEMM / implicit-GEMM convolution kernels (gemm.cu), the NHWC layer kernels (norm.cu)
+and the native executor against plain PyTorch fp32 references of the same ops."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import rlr_b200  # noqa: F401
+from rlr_b200 import ops
+from rlr_b200.models import get_layout
+from rlr_b200.models.native import NativeNet
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+BF = torch.bfloat16
+
+
+def _rel(a, b):
+    return float((a.float() - b.float()).abs().max() / (b.float().abs().max() + 1e-6))
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (256, 128, 256), (300, 64, 128), (1000, 192, 576), (4096, 256, 1024), (77, 512, 4608)])
+def test_gemm_bf16(M, N, K):
+    torch.manual_seed(M + N + K)
+    A = (torch.randn(M, K, device=DEV) * 0.5).to(BF)
+    Bm = (torch.randn(N, K, device=DEV) * 0.5).to(BF)
+    bias = torch.randn(N, device=DEV)
+    out = torch.empty(M, N, device=DEV, dtype=BF)
+    stats = torch.zeros(2, N, device=DEV)
+    ops.ext().gemm_bf16(A, Bm, out, bias, True, False, stats)
+    ref = F.relu(A.float() @ Bm.float().t() + bias)
+    assert _rel(out, ref) < 1e-2
+    torch.testing.assert_close(stats[0], out.float().sum(0), rtol=2e-3, atol=2e-2 * M ** 0.5)
+    torch.testing.assert_close(stats[1], (out.float() ** 2).sum(0), rtol=2e-3, atol=1e-1 * M ** 0.5)
+    out2 = out.clone()
+    ops.ext().gemm_bf16(A, Bm, out2, None, False, True, None)     # accumulate into existing output
+    ref2 = out.float() + A.float() @ Bm.float().t()
+    assert _rel(out2, ref2) < 2e-2
+
+
+CONV_CASES = [  # B, H, W, Cin, Cout, k, stride, pad
+    (256, 32, 32, 64, 64, 3, 1, 1), (80, 32, 32, 64, 64, 3, 1, 1), (64, 16, 16, 128, 128, 3, 1, 1), (64, 8, 8, 256, 256, 3, 1, 1),
+    (80, 4, 4, 512, 512, 3, 1, 1), (37, 2, 2, 512, 512, 3, 1, 1), (32, 32, 32, 3, 64, 3, 1, 1), (32, 32, 32, 64, 128, 3, 2, 1),
+    (32, 32, 32, 64, 128, 1, 2, 0), (40, 8, 8, 256, 512, 3, 2, 1), (40, 8, 8, 256, 512, 1, 2, 0), (16, 15, 15, 64, 128, 3, 1, 0),
+    (16, 26, 26, 64, 64, 3, 1, 0), (8, 30, 30, 3, 64, 3, 1, 0),
+]
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,s,p", CONV_CASES)
+def test_conv_fwd(B, H, W, Cin, Cout, k, s, p):
+    torch.manual_seed(B + H + Cin)
+    x = (torch.randn(B, H, W, Cin, device=DEV)).to(BF)
+    w = (torch.randn(Cout, k, k, Cin, device=DEV) / (k * k * Cin) ** 0.5).to(BF)
+    bias = torch.randn(Cout, device=DEV) * 0.1
+    Ho, Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    assert ops.conv_supported((H, W, Cin), dict(k=k, stride=s, pad=p, cout=Cout), "fwd")
+    y = torch.full((B, Ho, Wo, Cout), 7.0, device=DEV, dtype=BF)
+    stats = torch.zeros(2, Cout, device=DEV)
+    ops.conv2d_fwd_sm100(x, w, bias, y, s, p, True, stats, tag=("t", B, H, Cin, k, s))
+    ref = F.relu(F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), bias, s, p)).permute(0, 2, 3, 1)
+    assert _rel(y, ref) < 1e-2
+    torch.testing.assert_close(stats[0], y.float().sum((0, 1, 2)), rtol=2e-3, atol=0.5)
+    torch.testing.assert_close(stats[1], (y.float() ** 2).sum((0, 1, 2)), rtol=2e-3, atol=0.5)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,p,acc", [(64, 32, 32, 64, 64, 3, 1, False), (80, 16, 16, 128, 128, 3, 1, True),
+                                                     (48, 8, 8, 256, 256, 3, 1, True), (80, 4, 4, 512, 512, 3, 1, False),
+                                                     (16, 15, 15, 64, 128, 3, 0, False), (32, 8, 8, 128, 64, 1, 0, False)])
+def test_conv_dgrad(B, H, W, Cin, Cout, k, p, acc):
+    torch.manual_seed(B + H)
+    Ho, Wo = H + 2 * p - k + 1, W + 2 * p - k + 1
+    dy = torch.randn(B, Ho, Wo, Cout, device=DEV).to(BF)
+    w = (torch.randn(Cout, k, k, Cin, device=DEV) / (k * k * Cout) ** 0.5).to(BF)
+    dx = torch.randn(B, H, W, Cin, device=DEV).to(BF)
+    base = dx.clone()
+    ops.conv2d_dgrad_sm100(dy, w, dx, 1, p, acc)
+    ref = torch.ops.aten.convolution_backward(dy.float().permute(0, 3, 1, 2), torch.zeros(B, Cin, H, W, device=DEV),
+                                              w.float().permute(0, 3, 1, 2), None, [1, 1], [p, p], [1, 1], False, [0, 0], 1,
+                                              [True, False, False])[0].permute(0, 2, 3, 1)
+    if acc:
+        ref = ref + base.float()
+    assert _rel(dx, ref) < 1.5e-2
+
+
+@pytest.mark.parametrize("C,M,relu,res", [(64, 5000, True, True), (128, 777, True, False), (512, 4096, False, False), (256, 100, True, True)])
+def test_bn_kernels(C, M, relu, res):
+    torch.manual_seed(C + M)
+    x = (torch.randn(M, C, device=DEV) * 2 + 0.5).to(BF).view(M // 1 if False else M, 1, 1, C)
+    r = torch.randn_like(x) if res else None
+    gamma, beta = torch.rand(C, device=DEV) + 0.5, torch.randn(C, device=DEV) * 0.1
+    out = {}
+    for impl in ("aten", "sm100"):
+        rm, rv = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+        y = torch.empty_like(x); mr = torch.zeros(2, C, device=DEV)
+        ops.bn_fwd(x, y, r, gamma, beta, rm, rv, None, mr, M, 1e-5, 0.1, True, relu, impl)
+        dy = torch.randn(M, 1, 1, C, device=DEV, generator=torch.Generator(DEV).manual_seed(1)).to(BF)
+        dx, dres = torch.empty_like(x), (torch.empty_like(x) if res else None)
+        dg, db, ds = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV), torch.zeros(2, C, device=DEV)
+        ops.bn_bwd(dy, y, x, gamma, mr, ds, dx, dres, dg, db, relu, impl)
+        ye = torch.empty_like(x)
+        ops.bn_fwd(x, ye, r, gamma, beta, rm, rv, None, torch.zeros(2, C, device=DEV), M, 1e-5, 0.1, False, relu, impl)
+        out[impl] = dict(y=y, rm=rm, rv=rv, dx=dx, dres=dres, dg=dg, db=db, ye=ye)
+    a, b = out["aten"], out["sm100"]
+    for k in ("y", "dx", "ye"):
+        assert _rel(b[k], a[k]) < 2e-2, k
+    for k in ("rm", "rv", "dg", "db"):
+        torch.testing.assert_close(b[k], a[k], rtol=2e-2, atol=2e-2 * max(1.0, float(a[k].abs().max())))
+    if res:
+        assert _rel(b["dres"], a["dres"]) < 1e-2
+
+
+def test_pool_dropout_s2d_transpose_linear_small():
+    torch.manual_seed(3)
+    e = ops.ext()
+    x = torch.randn(9, 13, 13, 64, device=DEV).to(BF)
+    for impl in ("aten", "sm100"):
+        y = torch.empty(9, 6, 6, 64, device=DEV, dtype=BF); idx = torch.empty(9, 6, 6, 64, device=DEV, dtype=torch.uint8)
+        ops.maxpool2_fwd(x, y, idx, impl)
+        dx = torch.empty_like(x)
+        ops.maxpool2_bwd(y, idx, dx, impl)
+        if impl == "aten":
+            ry, rdx = y.clone(), dx.clone()
+    ref = F.max_pool2d(x.float().permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1)
+    assert torch.equal(y.float(), ref) and torch.equal(ry, y) and torch.equal(rdx, dx)
+    a = torch.randn(7, 4, 4, 512, device=DEV).to(BF)
+    p = torch.empty(7, 1, 1, 512, device=DEV, dtype=BF); ops.avgpool_fwd(a, p, "sm100")
+    assert _rel(p, a.float().mean((1, 2), keepdim=True)) < 1e-2
+    da = torch.empty_like(a); ops.avgpool_bwd(p, da, "sm100")
+    assert _rel(da, (p.float() / 16).expand_as(a)) < 1e-2
+    # dropout: mask statistics, fwd/bwd consistency, fresh masks per step
+    n = 1 << 20
+    xd = torch.ones(4, n // 4, device=DEV, dtype=BF); yd = torch.empty_like(xd); m = torch.empty(4, n // 4, device=DEV, dtype=torch.uint8)
+    step = torch.zeros(1, dtype=torch.int64, device=DEV)
+    ops.dropout_fwd(xd, yd, m, 0.5, 11, step, 5, "sm100")
+    keep = m.float().mean().item()
+    assert abs(keep - 0.5) < 5e-3 and torch.equal(yd.float(), m.float() * 2)
+    dxd = torch.empty_like(xd); ops.dropout_bwd(xd, m, dxd, 0.5, "sm100")
+    assert torch.equal(dxd, yd)
+    m2 = torch.empty_like(m); step += 1
+    ops.dropout_fwd(xd, yd, m2, 0.5, 11, step, 5, "sm100")
+    assert abs((m2 == m).float().mean().item() - 0.5) < 5e-3
+    # space to depth
+    s = torch.randn(3, 8, 6, 64, device=DEV).to(BF); s4 = torch.empty(12, 4, 3, 64, device=DEV, dtype=BF)
+    e.space_to_depth(s, s4)
+    for ph in range(2):
+        for pw in range(2):
+            assert torch.equal(s4[(ph * 2 + pw) * 3:(ph * 2 + pw + 1) * 3], s[:, ph::2, pw::2])
+    # filter transpose
+    w = torch.randn(128, 3, 3, 64, device=DEV).to(BF); wt = torch.empty(64, 9 * 128, device=DEV, dtype=BF)
+    e.filter_transpose(w, wt, 128, 9, 64)
+    assert torch.equal(wt.view(64, 3, 3, 128), w.flip(1, 2).permute(3, 1, 2, 0))
+    # small linear head
+    xx = torch.randn(50, 512, device=DEV).to(BF); ww = (torch.randn(10, 512, device=DEV) * 0.05).to(BF); bb = torch.randn(10, device=DEV)
+    yy = torch.empty(50, 10, device=DEV, dtype=BF); ops.linear_fwd(xx, ww, bb, yy, False, "sm100")
+    assert _rel(yy, xx.float() @ ww.float().t() + bb) < 1e-2
+    dyy = torch.randn(50, 10, device=DEV).to(BF)
+    dxx = torch.empty_like(xx); dww = torch.empty(10, 512, device=DEV); dbb = torch.empty(10, device=DEV)
+    ops.linear_bwd(xx, dyy, ww, dxx, dww, dbb, False, "sm100")
+    assert _rel(dxx, dyy.float() @ ww.float()) < 1e-2 and _rel(dww, dyy.float().t() @ xx.float()) < 1e-3
+    torch.testing.assert_close(dbb, dyy.float().sum(0), rtol=1e-3, atol=1e-3)
+
+
+@pytest.mark.parametrize("model,B", [("resnet18", 64), ("vgg11", 48), ("cnn_cifar", 32), ("cnn_mnist", 32)])
+def test_native_net_sm100_matches_aten_backend(model, B):
+    """Whole forward/backward: kernels (sm100) vs library calls (aten) through the same plan and buffers."""
+    torch.manual_seed(0)
+    lay = get_layout(model)
+    for nd in lay.nodes:
+        if nd.op == "dropout":
+            nd.attrs["p"] = 0.0   # masks come from different RNGs in the two back-ends
+    w = lay.init_(torch.zeros(lay.n_total, device=DEV), 1)
+    C, H, W = lay.in_shape
+    x = torch.randn(B, H, W, C, device=DEV).to(BF)
+    y = torch.randint(0, 10, (B,), device=DEV)
+    res = {}
+    for impl in ("aten", "sm100"):
+        net = NativeNet(lay, DEV, B, impl=impl)
+        wi, g = w.clone(), torch.zeros_like(w)
+        net.bind(wi, wi.to(BF), g)
+        logits = net.forward(x, True).clone()
+        _, dl = ops.softmax_xent(logits, y)
+        net.backward(dl)
+        res[impl] = (logits, g[: lay.n_vote].clone(), wi[lay.n_vote:].clone())
+    (la, ga, sa), (ls, gs, ss) = res["aten"], res["sm100"]
+    assert _rel(ls, la) < 5e-2
+    cos = F.cosine_similarity(gs.double(), ga.double(), dim=0).item()
+    assert cos > 0.99, cos
+    if sa.numel():
+        torch.testing.assert_close(ss, sa, rtol=5e-2, atol=5e-2)
