@@ -264,7 +264,7 @@ class NativeNet:
         bias = self.pw.get(op.name + ".bias")
         stats = op.saved.get("stats") if (train and op.saved.get("want_stats")) else None
         if self.impl["conv_fwd"] == "sm100" and ops.conv_supported(op.in_shape, a, "fwd"):
-            ops.conv2d_fwd_sm100(x, self.pwb[op.name + ".weight"], bias, y, a.get("stride", 1), a.get("pad", 0), op.relu, stats)
+            ops.conv2d_fwd_sm100(x, self.pwb[op.name + ".weight"], bias, y, a.get("stride", 1), a.get("pad", 0), op.relu, stats, tag=(id(self), op.name))
             return
         wt = self.pwb[op.name + ".weight"].permute(0, 3, 1, 2)
         out = F.conv2d(x.permute(0, 3, 1, 2), wt, bias.to(self.act_dtype) if bias is not None else None, a.get("stride", 1), a.get("pad", 0))
@@ -284,7 +284,7 @@ class NativeNet:
         gw, gb = self.pg[name], self.pg.get(op.name + ".bias")
         s, p = a.get("stride", 1), a.get("pad", 0)
         if self.impl["conv_wgrad"] == "sm100" and ops.conv_supported(op.in_shape, a, "wgrad"):
-            ops.conv2d_wgrad_sm100(x, dy, gw, gb, s, p)
+            ops.conv2d_wgrad_sm100(x, dy, gw, gb, s, p, tag=(id(self), op.name))
         else:
             _, dw, db = torch.ops.aten.convolution_backward(
                 dy.permute(0, 3, 1, 2), x.permute(0, 3, 1, 2), self.pwb[name].permute(0, 3, 1, 2),
@@ -345,7 +345,7 @@ class NativeNet:
     def _fwd_dropout(self, op, B, train):
         x, y = self.T(op.x, B), self.T(op.y, B)
         if not train:
-            y.copy_(x)
+            y.copy_(x.reshape(y.shape))
             return
         ops.dropout_fwd(x.reshape(B, -1), y.reshape(B, -1), op.saved["mask"][:B].reshape(B, -1), op.attrs["p"], self.seed,
                         self.step_counter, op.node, self.impl["dropout"])
@@ -418,7 +418,9 @@ class NativeTrainer:
         with torch.cuda.stream(s):
             for _ in range(3):
                 self.cursor.zero_()
+                c0 = ops.launch_calls()
                 self._step(dataset, B, w0)
+                self._launches = ops.launch_calls() - c0
         torch.cuda.current_stream(self.device).wait_stream(s)
         self.cursor.zero_()
         graph = torch.cuda.CUDAGraph()
@@ -453,7 +455,9 @@ class NativeTrainer:
         return {"loss_sum": self.loss_sum, "steps": steps}
 
     def launches_per_step(self):
-        return ops.LAUNCH_COUNTER.per_step if hasattr(ops, "LAUNCH_COUNTER") else 0
+        """Calls into our extension per local step (every call launches at least one of our kernels), measured during
+        the eager warm-up step that precedes graph capture."""
+        return getattr(self, "_launches", 0)
 
     @torch.no_grad()
     def eval_forward(self, w):

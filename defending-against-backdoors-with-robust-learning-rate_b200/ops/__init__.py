@@ -26,6 +26,34 @@ _lock = threading.Lock()
 MODE_IDS = {"avg": 0, "comed": 1, "sign": 2}
 
 
+class _Counter:
+    """Counts calls into the native extension (each call launches >= 1 of our kernels); used for ``gpu_launches``."""
+    calls = 0
+
+
+class _CountingExt:
+    def __init__(self, mod):
+        self._mod = mod
+        self._cache = {}
+
+    def __getattr__(self, name):
+        fn = self._cache.get(name)
+        if fn is None:
+            real = getattr(self._mod, name)
+            if not callable(real):
+                return real
+
+            def fn(*a, _real=real, **k):
+                _Counter.calls += 1
+                return _real(*a, **k)
+            self._cache[name] = fn
+        return fn
+
+
+def launch_calls() -> int:
+    return _Counter.calls
+
+
 def native_available() -> bool:
     """True if the compiled extension can be imported (it may still be unusable without a GPU)."""
     try:
@@ -53,7 +81,7 @@ def ext():
         except Exception as e:  # noqa: BLE001
             _ext_err = e
             raise
-        _ext = mod
+        _ext = _CountingExt(mod)
     return _ext
 
 
@@ -318,5 +346,5 @@ def eval_metrics(logits, labels, loss_sum, confusion):
     confusion.view(-1).index_add_(0, labels * C + pred, torch.ones_like(labels))
 
 
-from .nn import (avgpool_bwd, avgpool_fwd, bn_bwd, bn_fwd, conv2d_dgrad_sm100, conv2d_fwd_sm100, conv_supported,  # noqa: E402,F401
+from .nn import (avgpool_bwd, avgpool_fwd, bn_bwd, bn_fwd, conv2d_dgrad_sm100, conv2d_fwd_sm100, conv2d_wgrad_sm100, conv_supported,  # noqa: E402,F401
                  dropout_bwd, dropout_fwd, linear_bwd, linear_fwd, maxpool2_bwd, maxpool2_fwd, relu_bwd_, scratch)

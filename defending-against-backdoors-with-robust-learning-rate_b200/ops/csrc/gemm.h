@@ -30,6 +30,12 @@ cudaError_t launch_conv_bf16(const void* x, const void* w, void* out, int NB, in
                              int Cout, int ldc, int ntaps, const int* dh, const int* dw, const int* dplane, const float* bias,
                              int relu, int accumulate, float* stats, cudaStream_t st);
 
+// ---- wgrad.cu: MN-major tcgen05 weight gradients (fp32, accumulated with red.add) -----------------------------------
+cudaError_t launch_conv_wgrad_bf16(const void* dy, const void* x, float* dW, int NB, int planes, int Hin, int Win, int Cin, int Cin_valid,
+                                   int Ho, int Wo, int Cout, int ntaps, const int* dh, const int* dw, const int* dplane, int num_sms,
+                                   cudaStream_t st);
+cudaError_t launch_linear_wgrad_bf16(const void* dy, const void* x, float* dW, int B, int N, int K, int num_sms, cudaStream_t st);
+
 // ---- norm.cu: NHWC bf16 layer kernels -----------------------------------------------------------------------------
 // per-channel sum / sum of squares of x[M][C]
 cudaError_t launch_channel_stats(const __nv_bfloat16* x, long long M, int C, float* stats /*[2][C], accumulates*/, int num_sms, cudaStream_t st);

@@ -49,6 +49,27 @@ void conv_bf16(at::Tensor x, at::Tensor w, at::Tensor out, int64_t NB, int64_t p
                                 opt<const float>(bias), relu, accumulate, opt<float>(stats), cur_stream()), "conv_bf16");
 }
 
+// dW[Cout][T][Cin_valid] (fp32, pre-zeroed) += wgrad(dy[NB,Ho,Wo,Cout], x[planes*NB,Hin,Win,Cin])
+void conv_wgrad_bf16(at::Tensor dy, at::Tensor x, at::Tensor dW, int64_t NB, int64_t planes, int64_t cin_valid, std::vector<int64_t> dh,
+                     std::vector<int64_t> dw, std::vector<int64_t> dplane) {
+    c10::cuda::CUDAGuard g(x.device());
+    TORCH_CHECK(x.dim() == 4 && dy.dim() == 4);
+    const int Hin = x.size(1), Win = x.size(2), Cin = x.size(3), Ho = dy.size(1), Wo = dy.size(2), Cout = dy.size(3);
+    const int T = (int)dh.size();
+    TORCH_CHECK(x.size(0) == planes * NB && dy.size(0) == NB && dW.numel() == (int64_t)Cout * T * cin_valid);
+    TORCH_CHECK(Cout == 64 || Cout % 128 == 0, "wgrad: Cout must be 64 or a multiple of 128");
+    int a[9], b[9], c[9];
+    for (int t = 0; t < T; ++t) { a[t] = (int)dh[t]; b[t] = (int)dw[t]; c[t] = (int)dplane[t]; }
+    check(rlr::launch_conv_wgrad_bf16(bf(dy), bf(x), f32(dW), (int)NB, (int)planes, Hin, Win, Cin, (int)cin_valid, Ho, Wo, Cout, T, a, b, c,
+                                      num_sms(), cur_stream()), "conv_wgrad_bf16");
+}
+void linear_wgrad_bf16(at::Tensor dy, at::Tensor x, at::Tensor dW) {
+    c10::cuda::CUDAGuard g(x.device());
+    const int B = x.size(0), K = x.size(1), N = dy.size(1);
+    TORCH_CHECK(dy.size(0) == B && dW.numel() == (int64_t)N * K && (N == 64 || N % 128 == 0));
+    check(rlr::launch_linear_wgrad_bf16(bf(dy), bf(x), f32(dW), B, N, K, num_sms(), cur_stream()), "linear_wgrad_bf16");
+}
+
 void channel_stats(at::Tensor x, at::Tensor stats) {
     c10::cuda::CUDAGuard g(x.device());
     const int C = x.size(-1);
@@ -129,6 +150,8 @@ void linear_small_bwd(at::Tensor x, at::Tensor dy, at::Tensor w, c10::optional<a
 void register_gemm_bindings(py::module_& m) {
     m.def("gemm_bf16", &gemm_bf16);
     m.def("conv_bf16", &conv_bf16);
+    m.def("conv_wgrad_bf16", &conv_wgrad_bf16);
+    m.def("linear_wgrad_bf16", &linear_wgrad_bf16);
     m.def("channel_stats", &channel_stats);
     m.def("bn_finalize", &bn_finalize);
     m.def("bn_apply", &bn_apply);

@@ -36,6 +36,8 @@ def conv_supported(in_shape, a, kind):
         return (s == 1 or (h % 2 == 0 and w % 2 == 0)) and (cin % 64 == 0 or cin < 64)
     if kind == "dgrad":
         return s == 1 and cin % 64 == 0
+    if kind == "wgrad":
+        return (s == 1 or (h % 2 == 0 and w % 2 == 0)) and (cin % 64 == 0 or cin < 64) and (cout == 64 or cout % 128 == 0)
     return False
 
 
@@ -87,6 +89,31 @@ def conv2d_dgrad_sm100(dy, w, dx, stride, pad, accumulate):
     dh, dw, pl = _taps(k, 1, k - 1 - pad)
     e.conv_bf16(dy, wt, dx, B, 1, dh, dw, pl, None, False, bool(accumulate), None)
     return dx
+
+
+def conv2d_wgrad_sm100(x, dy, gw, gb, stride, pad, tag="fwd"):
+    """gw[Cout,k,k,Cin] (fp32) = sum over pixels of dy (x) x  (+ gb = sum dy).  Reuses the channel-padded / parity-split
+    copies of ``x`` that ``conv2d_fwd_sm100`` left in the scratch buffers of the same ``tag``."""
+    e = _ext()
+    B, H, W, Cin = x.shape
+    Cout, k = gw.shape[0], gw.shape[1]
+    cin_valid = Cin
+    if Cin % 64:
+        cp = (Cin + 63) // 64 * 64
+        x = scratch(("xpad", tag), (B, H, W, cp), x.dtype, x.device)      # filled by the forward pass
+        Cin = cp
+    planes = 1
+    if stride == 2:
+        x = scratch(("s2d", tag), (4 * B, H // 2, W // 2, Cin), x.dtype, x.device)  # filled by the forward pass
+        planes = 4
+    dh, dw, pl = _taps(k, stride, pad)
+    gw.zero_()
+    e.conv_wgrad_bf16(dy, x, gw, B, planes, cin_valid, dh, dw, pl)
+    if gb is not None:
+        st = scratch(("dbias", tag), (2, Cout), torch.float32, dy.device)
+        st.zero_()
+        e.channel_stats(dy, st)
+        gb.copy_(st[0])
 
 
 # =====================================================================================================================
@@ -228,7 +255,11 @@ def linear_bwd(x, dy, w, dx, dw, db, acc_dx, impl):
         _ext().linear_small_bwd(x.contiguous(), dy.contiguous(), w, dx, dw, db, bool(acc_dx))
         return
     dyf = dy.to(x.dtype)
-    dw.copy_(dyf.t() @ x)
+    if impl == "sm100" and K % 64 == 0 and (N == 64 or N % 128 == 0):
+        dw.zero_()
+        _ext().linear_wgrad_bf16(dy.contiguous(), x.contiguous(), dw)
+    else:
+        dw.copy_(dyf.t() @ x)
     if db is not None:
         db.copy_(dyf.float().sum(0))
     if dx is not None:

@@ -81,6 +81,42 @@ def test_conv_dgrad(B, H, W, Cin, Cout, k, p, acc):
     assert _rel(dx, ref) < 1.5e-2
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,s,p", [(64, 32, 32, 64, 64, 3, 1, 1), (80, 16, 16, 128, 128, 3, 1, 1), (48, 8, 8, 256, 256, 3, 1, 1),
+                                                   (80, 4, 4, 512, 512, 3, 1, 1), (32, 32, 32, 3, 64, 3, 1, 1), (32, 32, 32, 64, 128, 3, 2, 1),
+                                                   (32, 32, 32, 64, 128, 1, 2, 0), (40, 8, 8, 256, 512, 3, 2, 1), (16, 15, 15, 64, 128, 3, 1, 0),
+                                                   (24, 2, 2, 512, 512, 3, 1, 1)])
+def test_conv_wgrad(B, H, W, Cin, Cout, k, s, p):
+    torch.manual_seed(B + H + Cin)
+    Ho, Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    x = torch.randn(B, H, W, Cin, device=DEV).to(BF)
+    w = (torch.randn(Cout, k, k, Cin, device=DEV) / (k * k * Cin) ** 0.5).to(BF)
+    dy = torch.randn(B, Ho, Wo, Cout, device=DEV).to(BF)
+    assert ops.conv_supported((H, W, Cin), dict(k=k, stride=s, pad=p, cout=Cout), "wgrad")
+    tag = ("wg", B, H, Cin, k, s)
+    y = torch.empty(B, Ho, Wo, Cout, device=DEV, dtype=BF)
+    ops.conv2d_fwd_sm100(x, w, None, y, s, p, False, None, tag=tag)      # fills the padded / parity-split scratch copies
+    gw = torch.full((Cout, k, k, Cin), 3.0, device=DEV)
+    gb = torch.zeros(Cout, device=DEV)
+    ops.conv2d_wgrad_sm100(x, dy, gw, gb, s, p, tag=tag)
+    _, dw, db = torch.ops.aten.convolution_backward(dy.float().permute(0, 3, 1, 2), x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2),
+                                                    [Cout], [s, s], [p, p], [1, 1], False, [0, 0], 1, [False, True, True])
+    assert _rel(gw, dw.permute(0, 2, 3, 1)) < 1e-2
+    assert _rel(gb, db) < 1e-2
+
+
+def test_linear_wgrad_and_gemm_linear():
+    torch.manual_seed(5)
+    for B, K, N in [(256, 9216, 128), (100, 1024, 128), (256, 128, 256)]:
+        x = torch.randn(B, K, device=DEV).to(BF); dy = torch.randn(B, N, device=DEV).to(BF)
+        w = (torch.randn(N, K, device=DEV) / K ** 0.5).to(BF); b = torch.randn(N, device=DEV)
+        dw = torch.empty(N, K, device=DEV); db = torch.empty(N, device=DEV); dx = torch.empty(B, K, device=DEV, dtype=BF)
+        ops.linear_bwd(x, dy, w, dx, dw, db, False, "sm100")
+        assert _rel(dw, dy.float().t() @ x.float()) < 1e-2 and _rel(dx, dy.float() @ w.float()) < 2e-2
+        y = torch.empty(B, N, device=DEV, dtype=BF)
+        ops.linear_fwd(x, w, b, y, True, "sm100")
+        assert _rel(y, F.relu(x.float() @ w.float().t() + b)) < 1e-2
+
+
 @pytest.mark.parametrize("C,M,relu,res", [(64, 5000, True, True), (128, 777, True, False), (512, 4096, False, False), (256, 100, True, True)])
 def test_bn_kernels(C, M, relu, res):
     torch.manual_seed(C + M)
@@ -181,8 +217,32 @@ def test_native_net_sm100_matches_aten_backend(model, B):
         net.backward(dl)
         res[impl] = (logits, g[: lay.n_vote].clone(), wi[lay.n_vote:].clone())
     (la, ga, sa), (ls, gs, ss) = res["aten"], res["sm100"]
+    print(model, "logit rel", _rel(ls, la), "grad cos", F.cosine_similarity(gs.double(), ga.double(), dim=0).item())
+    worst = sorted(((F.cosine_similarity(lay.view(gs, p).double().flatten(), lay.view(ga, p).double().flatten(), dim=0).item(), p.name)
+                    for p in lay.params))[:6]
+    print("   worst per-parameter gradient cosines:", worst)
     assert _rel(ls, la) < 5e-2
     cos = F.cosine_similarity(gs.double(), ga.double(), dim=0).item()
     assert cos > 0.99, cos
     if sa.numel():
         torch.testing.assert_close(ss, sa, rtol=5e-2, atol=5e-2)
+
+
+@pytest.mark.parametrize("model", ["resnet18", "cnn_cifar"])
+def test_native_trainer_learns_like_torch_trainer(model):
+    """A few federated rounds on separable synthetic data: the sm_100a trainer must learn (and roughly track the torch
+    trainer); also exercises CUDA-graph capture of the native step, the ragged last batch and evaluation."""
+    from rlr_b200.engine import FLEngine
+    from rlr_b200.options import make_args
+    accs = {}
+    for trainer in ("native", "torch"):
+        args = make_args(data="cifar10", model=model, num_agents=2, local_ep=2, bs=64, synthetic=1000, synthetic_val=200, log_dir="",
+                         device=DEV, trainer=trainer, seed=2)
+        eng = FLEngine(args, verbose=False)
+        for r in range(1, 4):
+            eng.run_round(r)
+        accs[trainer] = eng.evaluate(3)["val_acc"]
+        assert eng.trainer.name == trainer
+        eng.close()
+    print(model, accs)
+    assert accs["native"] > 0.5 and accs["native"] > accs["torch"] - 0.25
