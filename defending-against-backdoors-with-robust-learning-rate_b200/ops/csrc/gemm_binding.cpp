@@ -131,6 +131,18 @@ void space_to_depth(at::Tensor x, at::Tensor y) {
     c10::cuda::CUDAGuard g(x.device());
     check(rlr::launch_space_to_depth(bf(x), bfm(y), x.size(0), x.size(1), x.size(2), x.size(3), num_sms(), cur_stream()), "space_to_depth");
 }
+void depth_to_space(at::Tensor x4, at::Tensor y, bool accumulate, int64_t plane_mask) {
+    c10::cuda::CUDAGuard g(y.device());
+    check(rlr::launch_depth_to_space(bf(x4), bfm(y), y.size(0), y.size(1), y.size(2), y.size(3), accumulate, (int)plane_mask, num_sms(),
+                                     cur_stream()), "depth_to_space");
+}
+void filter_gather_transpose(at::Tensor w, at::Tensor wt, int64_t Cout, int64_t T, int64_t Cin, std::vector<int64_t> taps) {
+    c10::cuda::CUDAGuard g(w.device());
+    int t[9];
+    TORCH_CHECK(taps.size() >= 1 && taps.size() <= 9);
+    for (size_t i = 0; i < taps.size(); ++i) t[i] = (int)taps[i];
+    check(rlr::launch_filter_gather_transpose(bf(w), bfm(wt), Cout, T, Cin, (int)taps.size(), t, cur_stream()), "filter_gather_transpose");
+}
 void filter_transpose(at::Tensor w, at::Tensor wt, int64_t Cout, int64_t ntaps, int64_t Cin) {
     c10::cuda::CUDAGuard g(w.device());
     check(rlr::launch_filter_transpose(bf(w), bfm(wt), Cout, ntaps, Cin, cur_stream()), "filter_transpose");
@@ -165,6 +177,8 @@ void register_gemm_bindings(py::module_& m) {
     m.def("dropout_bwd", &dropout_bwd);
     m.def("space_to_depth", &space_to_depth);
     m.def("filter_transpose", &filter_transpose);
+    m.def("depth_to_space", &depth_to_space);
+    m.def("filter_gather_transpose", &filter_gather_transpose);
     m.def("linear_small_fwd", &linear_small_fwd);
     m.def("linear_small_bwd", &linear_small_bwd);
 }

@@ -398,6 +398,67 @@ cudaError_t launch_space_to_depth(const __nv_bfloat16* x, __nv_bfloat16* y, int 
     return cudaGetLastError();
 }
 
+// inverse of space_to_depth with optional accumulation; planes missing from `plane_mask` count as zero
+__global__ void __launch_bounds__(256) depth_to_space_kernel(const __nv_bfloat16* __restrict__ x4, __nv_bfloat16* __restrict__ y, int NB,
+                                                               int H, int W, int C, int accumulate, int plane_mask) {
+    const int cg_n = C / 8, H2 = H / 2, W2 = W / 2;
+    const long long total = (long long)NB * H * W * cg_n;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int cg = (int)(t % cg_n);
+        long long r = t / cg_n;
+        const int w = (int)(r % W); r /= W;
+        const int h = (int)(r % H);
+        const int n = (int)(r / H);
+        const int plane = (h & 1) * 2 + (w & 1);
+        __nv_bfloat16* dst = y + (((size_t)n * H + h) * W + w) * C + cg * 8;
+        bf8 v;
+        if ((plane_mask >> plane) & 1) {
+            v = load8(x4 + ((((size_t)plane * NB + n) * H2 + (h >> 1)) * W2 + (w >> 1)) * C + cg * 8);
+        } else {
+            if (accumulate) continue;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v.v[i] = 0.f;
+        }
+        if (accumulate) {
+            const bf8 o = load8(dst);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v.v[i] += o.v[i];
+        }
+        store8(dst, v);
+    }
+}
+cudaError_t launch_depth_to_space(const __nv_bfloat16* x4, __nv_bfloat16* y, int NB, int H, int W, int C, int accumulate, int plane_mask,
+                                  int num_sms, cudaStream_t st) {
+    if (C % 8 || H % 2 || W % 2) return cudaErrorInvalidValue;
+    const long long total = (long long)NB * H * W * (C / 8);
+    depth_to_space_kernel<<<rows_grid(total, 256, num_sms, 8), 256, 0, st>>>(x4, y, NB, H, W, C, accumulate, plane_mask);
+    return cudaGetLastError();
+}
+
+// wt[ci][s][co] = w[co][taps[s]][ci]   (sub-filter of a strided conv's data gradient, one per input parity plane)
+struct TapList { int n; int t[9]; };
+__global__ void filter_gather_transpose_kernel(const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ wt, int Cout, int T,
+                                               int Cin, TapList taps) {
+    const long long total = (long long)Cout * taps.n * Cin;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int co = (int)(i % Cout);
+        const long long r = i / Cout;
+        const int s = (int)(r % taps.n);
+        const int ci = (int)(r / taps.n);
+        wt[i] = w[((size_t)co * T + taps.t[s]) * Cin + ci];
+    }
+}
+cudaError_t launch_filter_gather_transpose(const __nv_bfloat16* w, __nv_bfloat16* wt, int Cout, int T, int Cin, int nsub, const int* taps,
+                                           cudaStream_t st) {
+    if (nsub < 1 || nsub > 9) return cudaErrorInvalidValue;
+    TapList tl; tl.n = nsub;
+    for (int i = 0; i < nsub; ++i) tl.t[i] = taps[i];
+    const long long total = (long long)Cout * nsub * Cin;
+    const long long blocks = (total + 255) / 256;
+    filter_gather_transpose_kernel<<<(int)(blocks > 148 * 16 ? 148 * 16 : blocks), 256, 0, st>>>(w, wt, Cout, T, Cin, tl);
+    return cudaGetLastError();
+}
+
 // wt[ci][T-1-t][co] = w[co][t][ci]
 __global__ void filter_transpose_kernel(const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ wt, int Cout, int T, int Cin) {
     const long long total = (long long)Cout * T * Cin;

@@ -35,7 +35,7 @@ def conv_supported(in_shape, a, kind):
     if kind == "fwd":
         return (s == 1 or (h % 2 == 0 and w % 2 == 0)) and (cin % 64 == 0 or cin < 64)
     if kind == "dgrad":
-        return s == 1 and cin % 64 == 0
+        return cin % 64 == 0 and (s == 1 or (h % 2 == 0 and w % 2 == 0))
     if kind == "wgrad":
         return (s == 1 or (h % 2 == 0 and w % 2 == 0)) and (cin % 64 == 0 or cin < 64) and (cout == 64 or cout % 128 == 0)
     return False
@@ -80,14 +80,42 @@ def conv2d_fwd_sm100(x, w, bias, y, stride, pad, relu, stats, tag="fwd"):
 def conv2d_dgrad_sm100(dy, w, dx, stride, pad, accumulate):
     """dx[B,H,W,Cin] (+)= conv_transpose(dy[B,Ho,Wo,Cout], w[Cout,k,k,Cin]) for stride 1: a convolution of dy with
     the tap-flipped, transposed filter and padding k-1-pad."""
-    assert stride == 1
     e = _ext()
     Cout, k, _, Cin = w.shape
     B = dy.shape[0]
+    if stride == 2:
+        return _conv2d_dgrad_s2(e, dy, w, dx, pad, accumulate)
     wt = scratch(("wt", w.data_ptr()), (Cin, k * k * Cout), w.dtype, w.device)
     e.filter_transpose(w, wt, Cout, k * k, Cin)
     dh, dw, pl = _taps(k, 1, k - 1 - pad)
     e.conv_bf16(dy, wt, dx, B, 1, dh, dw, pl, None, False, bool(accumulate), None)
+    return dx
+
+
+def _conv2d_dgrad_s2(e, dy, w, dx, pad, accumulate):
+    """Stride-2 data gradient by input parity: input pixel (2a+pi, 2b+pj) only receives the taps with
+    (pi + pad - dy) and (pj + pad - dx) even, from output pixel (a + (pi+pad-dy)/2, b + (pj+pad-dx)/2).  Each parity
+    plane is therefore a small stride-1 convolution of dY with a sub-filter (1/2/2/4 taps for 3x3, pad 1); the four
+    planes are computed by the tcgen05 conv kernel into a parity-split buffer and interleaved by depth_to_space."""
+    Cout, k, _, Cin = w.shape
+    B, Ho, Wo, _ = dy.shape
+    dx4 = scratch(("dx4", w.data_ptr()), (4 * B, Ho, Wo, Cin), dy.dtype, dy.device)
+    mask = 0
+    for pi in range(2):
+        for pj in range(2):
+            taps, dh, dw = [], [], []
+            for fy in range(k):
+                for fx in range(k):
+                    if (pi + pad - fy) % 2 == 0 and (pj + pad - fx) % 2 == 0:
+                        taps.append(fy * k + fx); dh.append((pi + pad - fy) // 2); dw.append((pj + pad - fx) // 2)
+            if not taps:
+                continue
+            plane = pi * 2 + pj
+            mask |= 1 << plane
+            wt = scratch(("wt_s2", w.data_ptr(), plane), (Cin, len(taps) * Cout), w.dtype, w.device)
+            e.filter_gather_transpose(w, wt, Cout, k * k, Cin, taps)
+            e.conv_bf16(dy, wt, dx4[plane * B:(plane + 1) * B], B, 1, dh, dw, [0] * len(taps), None, False, False, None)
+    e.depth_to_space(dx4, dx, bool(accumulate), mask)
     return dx
 
 

@@ -1,0 +1,44 @@
+"""Launch the hot kernels on representative shapes (for `ncu --set full -k regex:...`)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from rlr_b200 import ops  # noqa: E402
+
+DEV, BF = "cuda:0", torch.bfloat16
+torch.manual_seed(0)
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+
+
+def conv_case(B, H, C, Cout, tag):
+    x = torch.randn(B, H, H, C, device=DEV).to(BF)
+    w = (torch.randn(Cout, 3, 3, C, device=DEV) * 0.05).to(BF)
+    y = torch.empty(B, H, H, Cout, device=DEV, dtype=BF)
+    stats = torch.zeros(2, Cout, device=DEV)
+    dy = torch.randn(B, H, H, Cout, device=DEV).to(BF)
+    gw = torch.zeros(Cout, 3, 3, C, device=DEV)
+    dx = torch.empty_like(x)
+    for _ in range(2):
+        if which in ("all", "fwd"):
+            ops.conv2d_fwd_sm100(x, w, None, y, 1, 1, False, stats, tag=tag)
+        if which in ("all", "wgrad"):
+            ops.conv2d_wgrad_sm100(x, dy, gw, None, 1, 1, tag=tag)
+        if which in ("all", "dgrad"):
+            ops.conv2d_dgrad_sm100(dy, w, dx, 1, 1, False)
+    torch.cuda.synchronize()
+
+
+conv_case(256, 32, 64, 64, "l1")
+conv_case(256, 8, 256, 256, "l3")
+if which in ("all", "agg"):
+    n = 11190272
+    g = torch.randn(n, device=DEV)
+    ws = [g + 0.01 * torch.randn(n, device=DEV) for _ in range(8)]
+    out = torch.empty_like(g); sh = torch.empty(n, device=DEV, dtype=BF)
+    for mode in ("avg", "comed"):
+        for _ in range(2):
+            ops.fused_aggregate(g, ws, [1.0] * 8, mode, 4, 1.0, n_vote=n - 12288, out=out, out_bf16=sh)
+    torch.cuda.synchronize()
+print("ok")

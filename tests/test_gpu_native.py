@@ -65,20 +65,27 @@ def test_conv_fwd(B, H, W, Cin, Cout, k, s, p):
 @pytest.mark.parametrize("B,H,W,Cin,Cout,k,p,acc", [(64, 32, 32, 64, 64, 3, 1, False), (80, 16, 16, 128, 128, 3, 1, True),
                                                      (48, 8, 8, 256, 256, 3, 1, True), (80, 4, 4, 512, 512, 3, 1, False),
                                                      (16, 15, 15, 64, 128, 3, 0, False), (32, 8, 8, 128, 64, 1, 0, False)])
-def test_conv_dgrad(B, H, W, Cin, Cout, k, p, acc):
+def test_conv_dgrad(B, H, W, Cin, Cout, k, p, acc, s=1):
     torch.manual_seed(B + H)
-    Ho, Wo = H + 2 * p - k + 1, W + 2 * p - k + 1
+    Ho, Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
     dy = torch.randn(B, Ho, Wo, Cout, device=DEV).to(BF)
     w = (torch.randn(Cout, k, k, Cin, device=DEV) / (k * k * Cout) ** 0.5).to(BF)
     dx = torch.randn(B, H, W, Cin, device=DEV).to(BF)
     base = dx.clone()
-    ops.conv2d_dgrad_sm100(dy, w, dx, 1, p, acc)
+    ops.conv2d_dgrad_sm100(dy, w, dx, s, p, acc)
     ref = torch.ops.aten.convolution_backward(dy.float().permute(0, 3, 1, 2), torch.zeros(B, Cin, H, W, device=DEV),
-                                              w.float().permute(0, 3, 1, 2), None, [1, 1], [p, p], [1, 1], False, [0, 0], 1,
+                                              w.float().permute(0, 3, 1, 2), None, [s, s], [p, p], [1, 1], False, [0, 0], 1,
                                               [True, False, False])[0].permute(0, 2, 3, 1)
     if acc:
         ref = ref + base.float()
     assert _rel(dx, ref) < 1.5e-2
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,p,acc", [(32, 32, 32, 64, 128, 3, 1, False), (40, 16, 16, 128, 256, 3, 1, True),
+                                                     (24, 8, 8, 256, 512, 3, 1, False), (32, 32, 32, 64, 128, 1, 0, True),
+                                                     (24, 8, 8, 256, 512, 1, 0, False)])
+def test_conv_dgrad_stride2(B, H, W, Cin, Cout, k, p, acc):
+    test_conv_dgrad(B, H, W, Cin, Cout, k, p, acc, s=2)
 
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout,k,s,p", [(64, 32, 32, 64, 64, 3, 1, 1), (80, 16, 16, 128, 128, 3, 1, 1), (48, 8, 8, 256, 256, 3, 1, 1),
