@@ -204,12 +204,19 @@ class NativeNet:
                     self.grad[t] = torch.empty((B, *self.tshape[t]), dtype=self.act_dtype, device=dev)
         self.grad[self.out_tid] = torch.empty((B, *self.tshape[self.out_tid]), dtype=self.act_dtype, device=dev)
         self.logits = torch.empty((B, self.tshape[self.out_tid][-1]), dtype=torch.float32, device=dev)
+        # all per-channel accumulators live in two arenas so one memset per pass re-arms every layer's atomics
+        need = [op for op in self.plan if op.kind == "bn" or (op.kind == "conv" and op.saved.get("want_stats"))]
+        tot = sum(2 * op.out_shape[-1] for op in need)
+        self.stats_arena = torch.zeros(max(1, tot), dtype=torch.float32, device=dev)   # forward: sum, sum of squares
+        self.dsum_arena = torch.zeros(max(1, tot), dtype=torch.float32, device=dev)    # backward: sum dy, sum dy*xhat
+        off = 0
+        for op in need:
+            c = op.out_shape[-1]
+            op.saved["stats"] = self.stats_arena[off:off + 2 * c].view(2, c)
+            op.saved["dsum"] = self.dsum_arena[off:off + 2 * c].view(2, c)
+            op.saved["mean_rstd"] = torch.zeros(2, c, dtype=torch.float32, device=dev)
+            off += 2 * c
         for op in self.plan:
-            if op.kind == "bn" or (op.kind == "conv" and op.saved.get("want_stats")):
-                c = op.out_shape[-1]
-                op.saved["stats"] = torch.zeros(2, c, dtype=torch.float32, device=dev)     # sum, sum of squares
-                op.saved["mean_rstd"] = torch.zeros(2, c, dtype=torch.float32, device=dev)
-                op.saved["dsum"] = torch.zeros(2, c, dtype=torch.float32, device=dev)      # sum dy, sum dy*xhat
             if op.kind == "maxpool":
                 op.saved["idx"] = torch.empty((B, *op.out_shape), dtype=torch.uint8, device=dev)
             if op.kind == "dropout":
@@ -244,6 +251,8 @@ class NativeNet:
         """``x_nhwc``: [B,H,W,C] bf16 (channels of the first conv, un-padded).  Returns fp32 logits [B,classes]."""
         B = x_nhwc.shape[0]
         self._x, self._B, self._train = x_nhwc, B, train
+        if train:
+            self.stats_arena.zero_()
         for op in self.plan:
             getattr(self, "_fwd_" + op.kind)(op, B, train)
         out = self.T(self.out_tid, B)
@@ -254,6 +263,8 @@ class NativeNet:
         """``dlogits`` [B,classes] (already scaled by 1/B).  Fills the flat gradient buffer."""
         B = dlogits.shape[0]
         self.G(self.out_tid, B).copy_(dlogits.reshape(self.G(self.out_tid, B).shape))
+        self.g.zero_()           # tcgen05 weight gradients are split-K reductions (red.add) into the flat buffer
+        self.dsum_arena.zero_()
         for op in reversed(self.plan):
             getattr(self, "_bwd_" + op.kind)(op, B)
 
@@ -264,7 +275,7 @@ class NativeNet:
         bias = self.pw.get(op.name + ".bias")
         stats = op.saved.get("stats") if (train and op.saved.get("want_stats")) else None
         if self.impl["conv_fwd"] == "sm100" and ops.conv_supported(op.in_shape, a, "fwd"):
-            ops.conv2d_fwd_sm100(x, self.pwb[op.name + ".weight"], bias, y, a.get("stride", 1), a.get("pad", 0), op.relu, stats, tag=(id(self), op.name))
+            ops.conv2d_fwd_sm100(x, self.pwb[op.name + ".weight"], bias, y, a.get("stride", 1), a.get("pad", 0), op.relu, stats, tag=(id(self), op.name), zero_stats=False)
             return
         wt = self.pwb[op.name + ".weight"].permute(0, 3, 1, 2)
         out = F.conv2d(x.permute(0, 3, 1, 2), wt, bias.to(self.act_dtype) if bias is not None else None, a.get("stride", 1), a.get("pad", 0))
@@ -284,7 +295,7 @@ class NativeNet:
         gw, gb = self.pg[name], self.pg.get(op.name + ".bias")
         s, p = a.get("stride", 1), a.get("pad", 0)
         if self.impl["conv_wgrad"] == "sm100" and ops.conv_supported(op.in_shape, a, "wgrad"):
-            ops.conv2d_wgrad_sm100(x, dy, gw, gb, s, p, tag=(id(self), op.name))
+            ops.conv2d_wgrad_sm100(x, dy, gw, gb, s, p, tag=(id(self), op.name), zero=False)
         else:
             _, dw, db = torch.ops.aten.convolution_backward(
                 dy.permute(0, 3, 1, 2), x.permute(0, 3, 1, 2), self.pwb[name].permute(0, 3, 1, 2),
@@ -326,7 +337,7 @@ class NativeNet:
         dx = self.G(op.x, B)
         gamma = self.pw[op.name + ".weight"]
         ops.bn_bwd(dy, y, x, gamma, op.saved["mean_rstd"], op.saved["dsum"], dx, dres,
-                   self.pg[op.name + ".weight"], self.pg[op.name + ".bias"], op.relu, self.impl["bn"])
+                   self.pg[op.name + ".weight"], self.pg[op.name + ".bias"], op.relu, self.impl["bn"], zero_dsum=False)
 
     # ---- pooling ---------------------------------------------------------------------------------------------------
     def _fwd_maxpool(self, op, B, train):
@@ -365,7 +376,7 @@ class NativeNet:
             ops.relu_bwd_(dy, y, self.impl["bn"])
         dx = self.G(op.x, B).reshape(B, -1) if op.need_dx else None
         ops.linear_bwd(x, dy, self.pwb[op.name + ".weight"], dx, self.pg[op.name + ".weight"], self.pg.get(op.name + ".bias"),
-                       op.acc_dx, self.impl["linear"])
+                       op.acc_dx, self.impl["linear"], zero=False)
 
 
 class NativeTrainer:

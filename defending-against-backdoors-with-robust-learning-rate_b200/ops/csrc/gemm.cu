@@ -40,7 +40,7 @@ struct TileCfg {
     static constexpr int kPitch = BN * 2 + 16;                    // staging row pitch (bytes), conflict-free 16 B stores
     static constexpr int kStagingBytes = BM * kPitch;
     static constexpr int kRingBytes = kStages * kStageBytes;
-    static_assert(kStagingBytes <= kRingBytes, "staging aliases the operand ring");
+    static_assert(kStagingBytes + 2 * BN * 4 <= kRingBytes, "staging aliases the operand ring");
     static constexpr int kSmemBytes = kRingBytes + 1024 /*align slack*/ + 1024 /*barriers, row index*/;
 };
 
@@ -192,21 +192,28 @@ umma_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             *gp = val;
         }
         // ---- per-channel statistics of the (bf16-rounded) output tile: sum and sum of squares -> BatchNorm ----
+        // 128 threads = (BN/2 column pairs) x (256/BN row slices); partials meet in shared memory, one global atomic
+        // per column and statistic per tile.
         if (p.stats) {
-            const int c = et % BN, part = et / BN;       // BN=64: part 0 -> sums, part 1 -> squares; BN=128: both
-            float s1 = 0.f, s2 = 0.f;
-            const __nv_bfloat16* colp = reinterpret_cast<const __nv_bfloat16*>(staging) + c;
-            for (int r = 0; r < BM; ++r) {
+            float* red = reinterpret_cast<float*>(staging + Cfg::kStagingBytes);   // [2][BN], behind the staging tile
+            for (int i = et; i < 2 * BN; i += kEpiThreads) red[i] = 0.f;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            constexpr int kPairs = BN / 2, kSlices = kEpiThreads / kPairs, kRows = BM / kSlices;
+            const int cp = et % kPairs, sl = et / kPairs;
+            float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+            const uint8_t* colp = staging + cp * 4;
+#pragma unroll 4
+            for (int r = sl * kRows; r < (sl + 1) * kRows; ++r) {
                 if (tail->row_index[r] < 0) continue;
-                const float x = __bfloat162float(*(colp + r * (Cfg::kPitch / 2)));
-                s1 += x; s2 += x * x;
+                const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(colp + r * Cfg::kPitch);
+                const float2 x = __bfloat1622float2(h);
+                s1a += x.x; s1b += x.y; s2a += x.x * x.x; s2b += x.y * x.y;
             }
-            if (BN == 64) {
-                atomicAdd(p.stats + (part ? p.N : 0) + col0 + c, part ? s2 : s1);
-            } else {
-                atomicAdd(p.stats + col0 + c, s1);
-                atomicAdd(p.stats + p.N + col0 + c, s2);
-            }
+            atomicAdd(&red[2 * cp], s1a); atomicAdd(&red[2 * cp + 1], s1b);
+            atomicAdd(&red[BN + 2 * cp], s2a); atomicAdd(&red[BN + 2 * cp + 1], s2b);
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int i = et; i < 2 * BN; i += kEpiThreads)
+                atomicAdd(p.stats + (i < BN ? 0 : p.N) + col0 + (i % BN), red[i]);
         }
     }
     // ---- teardown ----------------------------------------------------------------------------------------------------------

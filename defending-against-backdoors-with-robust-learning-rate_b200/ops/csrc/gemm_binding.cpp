@@ -88,11 +88,11 @@ void bn_apply(at::Tensor x, c10::optional<at::Tensor> res, at::Tensor y, at::Ten
                                x.numel() / C, C, relu, num_sms(), cur_stream()), "bn_apply");
 }
 void bn_bwd(at::Tensor dy, at::Tensor y, at::Tensor x, at::Tensor gamma, at::Tensor mean_rstd, at::Tensor dsum, at::Tensor dx,
-            c10::optional<at::Tensor> dres, at::Tensor dgamma, at::Tensor dbeta, bool relu) {
+            c10::optional<at::Tensor> dres, at::Tensor dgamma, at::Tensor dbeta, bool relu, bool zero_dsum) {
     c10::cuda::CUDAGuard g(x.device());
     const int C = x.size(-1);
     const long long M = x.numel() / C;
-    check(cudaMemsetAsync(dsum.data_ptr(), 0, sizeof(float) * 2 * C, cur_stream()), "bn_bwd/memset");
+    if (zero_dsum) check(cudaMemsetAsync(dsum.data_ptr(), 0, sizeof(float) * 2 * C, cur_stream()), "bn_bwd/memset");
     check(rlr::launch_bn_bwd_reduce(bf(dy), bf(y), bf(x), f32(mean_rstd), f32(dsum), M, C, relu, num_sms(), cur_stream()), "bn_bwd_reduce");
     check(rlr::launch_bn_bwd_apply(bf(dy), bf(y), bf(x), (const float*)gamma.data_ptr(), f32(mean_rstd), f32(dsum), bfm(dx),
                                    const_cast<__nv_bfloat16*>(bfo(dres)), (float*)dgamma.data_ptr(), (float*)dbeta.data_ptr(), M, C, relu,

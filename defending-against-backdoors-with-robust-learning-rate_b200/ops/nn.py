@@ -53,7 +53,7 @@ def _taps(k, stride, pad):
     return dh, dw, pl
 
 
-def conv2d_fwd_sm100(x, w, bias, y, stride, pad, relu, stats, tag="fwd"):
+def conv2d_fwd_sm100(x, w, bias, y, stride, pad, relu, stats, tag="fwd", zero_stats=True):
     """y[B,Ho,Wo,Cout] = conv(x[B,H,W,Cin], w[Cout,k,k,Cin]) (+bias)(ReLU); ``stats`` [2,Cout] gets per-channel sum / sum^2."""
     e = _ext()
     B, H, W, Cin = x.shape
@@ -71,7 +71,7 @@ def conv2d_fwd_sm100(x, w, bias, y, stride, pad, relu, stats, tag="fwd"):
         e.space_to_depth(x, x4)
         x, planes = x4, 4
     dh, dw, pl = _taps(k, stride, pad)
-    if stats is not None:
+    if stats is not None and zero_stats:
         stats.zero_()
     e.conv_bf16(x, w.reshape(Cout, k * k * Cin), y, B, planes, dh, dw, pl, bias, bool(relu), False, stats)
     return y
@@ -119,7 +119,7 @@ def _conv2d_dgrad_s2(e, dy, w, dx, pad, accumulate):
     return dx
 
 
-def conv2d_wgrad_sm100(x, dy, gw, gb, stride, pad, tag="fwd"):
+def conv2d_wgrad_sm100(x, dy, gw, gb, stride, pad, tag="fwd", zero=True):
     """gw[Cout,k,k,Cin] (fp32) = sum over pixels of dy (x) x  (+ gb = sum dy).  Reuses the channel-padded / parity-split
     copies of ``x`` that ``conv2d_fwd_sm100`` left in the scratch buffers of the same ``tag``."""
     e = _ext()
@@ -135,7 +135,8 @@ def conv2d_wgrad_sm100(x, dy, gw, gb, stride, pad, tag="fwd"):
         x = scratch(("s2d", tag), (4 * B, H // 2, W // 2, Cin), x.dtype, x.device)  # filled by the forward pass
         planes = 4
     dh, dw, pl = _taps(k, stride, pad)
-    gw.zero_()
+    if zero:
+        gw.zero_()
     e.conv_wgrad_bf16(dy, x, gw, B, planes, cin_valid, dh, dw, pl)
     if gb is not None:
         st = scratch(("dbias", tag), (2, Cout), torch.float32, dy.device)
@@ -179,10 +180,10 @@ def bn_fwd(x, y, res, gamma, beta, rm, rv, stats, mean_rstd, count, eps, momentu
     y.copy_(out.reshape(y.shape))
 
 
-def bn_bwd(dy, y, x, gamma, mean_rstd, dsum, dx, dres, dgamma, dbeta, relu, impl):
+def bn_bwd(dy, y, x, gamma, mean_rstd, dsum, dx, dres, dgamma, dbeta, relu, impl, zero_dsum=True):
     C = x.shape[-1]
     if impl == "sm100":
-        _ext().bn_bwd(dy, y, x, gamma, mean_rstd, dsum, dx, dres, dgamma, dbeta, bool(relu))
+        _ext().bn_bwd(dy, y, x, gamma, mean_rstd, dsum, dx, dres, dgamma, dbeta, bool(relu), bool(zero_dsum))
         return
     dz = dy.float().reshape(-1, C)
     if relu:
@@ -277,14 +278,15 @@ def linear_fwd(x, w, bias, y, relu, impl):
     y.copy_(out)
 
 
-def linear_bwd(x, dy, w, dx, dw, db, acc_dx, impl):
+def linear_bwd(x, dy, w, dx, dw, db, acc_dx, impl, zero=True):
     N, K = w.shape
     if impl == "sm100" and N <= 32:
         _ext().linear_small_bwd(x.contiguous(), dy.contiguous(), w, dx, dw, db, bool(acc_dx))
         return
     dyf = dy.to(x.dtype)
     if impl == "sm100" and K % 64 == 0 and (N == 64 or N % 128 == 0):
-        dw.zero_()
+        if zero:
+            dw.zero_()
         _ext().linear_wgrad_bf16(dy.contiguous(), x.contiguous(), dw)
     else:
         dw.copy_(dyf.t() @ x)
