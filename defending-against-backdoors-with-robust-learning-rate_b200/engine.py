@@ -105,20 +105,27 @@ class FLEngine:
 
     # ---- end-to-end input streaming (bench "e2e"): shards come from pinned host memory every round ----------
     def enable_input_streaming(self):
-        """Keep a pinned host copy of every agent's shard; ``run_round(stream_inputs=True)`` then re-uploads the
-        shards this rank trains each round (what a deployment feeding fresh client data would do)."""
+        """End-to-end mode: every agent's shard gets a compact device buffer plus a pinned host copy, and
+        ``run_round(stream_inputs=True)`` re-uploads (one contiguous H2D copy, no scatter, no allocation) the shards this
+        rank trains each round -- what a deployment that receives fresh client data every round does.  Returns the total
+        bytes of all shards."""
+        from .data import DeviceDataset
         self._stream_src = {}
-        pin = (lambda t: t.cpu().pin_memory()) if self.ctx.device.type == "cuda" else (lambda t: t.cpu().clone())
+        cuda = self.ctx.device.type == "cuda"
+        pin = (lambda t: t.cpu().pin_memory()) if cuda else (lambda t: t.cpu().clone())
+        total = 0
         for a in self.agents:
-            self._stream_src[a.id] = (pin(a.dataset.data[a.idxs]), pin(a.dataset.targets[a.idxs]))
-        return sum(x.numel() * x.element_size() + y.numel() * y.element_size() for x, y in self._stream_src.values())
+            x, y = a.dataset.data[a.idxs].contiguous(), a.dataset.targets[a.idxs].contiguous()
+            self._stream_src[a.id] = (pin(x), pin(y))
+            a.dataset = DeviceDataset(a.dataset.name, x, y)        # compact shard; indices become local
+            a.idxs = torch.arange(a.n_data, device=self.ctx.device)
+            total += x.numel() * x.element_size() + y.numel() * y.element_size()
+        return total
 
     def _upload_shard(self, agent):
         x, y = self._stream_src[agent.id]
-        dx = x.to(self.ctx.device, non_blocking=True)
-        dy = y.to(self.ctx.device, non_blocking=True)
-        agent.dataset.data.index_copy_(0, agent.idxs, dx)
-        agent.dataset.targets.index_copy_(0, agent.idxs, dy)
+        agent.dataset.data.copy_(x, non_blocking=True)
+        agent.dataset.targets.copy_(y, non_blocking=True)
         return x.numel() * x.element_size() + y.numel() * y.element_size()
 
     # ---- one federated round (src/federated.py:66-74) --------------------------------------------------------

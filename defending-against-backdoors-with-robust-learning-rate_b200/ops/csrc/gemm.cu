@@ -160,7 +160,7 @@ umma_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
                 float a = __uint_as_float(v[j]), b = __uint_as_float(v[j + 1]);
-                if (p.bias) { a += p.bias[col0 + c0 + j]; b += p.bias[col0 + c0 + j + 1]; }
+                if (p.bias && col0 + c0 + j < p.N) { a += p.bias[col0 + c0 + j]; b += p.bias[col0 + c0 + j + 1]; }
                 if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
                 packed[j >> 1] = pack_bf16x2(a, b);
             }
@@ -176,7 +176,7 @@ umma_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         for (int idx = et; idx < BM * kChunks; idx += kEpiThreads) {
             const int r = idx / kChunks, ch = idx - r * kChunks;
             const int gi = tail->row_index[r];
-            if (gi < 0) continue;
+            if (gi < 0 || col0 + ch * 8 >= p.N) continue;     // masked row / column chunk beyond Cout
             uint4 val = *reinterpret_cast<const uint4*>(staging + r * Cfg::kPitch + ch * 16);
             uint4* gp = reinterpret_cast<uint4*>(out + (size_t)gi * p.ldc + col0 + ch * 8);
             if (p.accumulate) {
@@ -213,7 +213,7 @@ umma_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             atomicAdd(&red[BN + 2 * cp], s2a); atomicAdd(&red[BN + 2 * cp + 1], s2b);
             asm volatile("bar.sync 1, 128;" ::: "memory");
             for (int i = et; i < 2 * BN; i += kEpiThreads)
-                atomicAdd(p.stats + (i < BN ? 0 : p.N) + col0 + (i % BN), red[i]);
+                if (col0 + (i % BN) < p.N) atomicAdd(p.stats + (i < BN ? 0 : p.N) + col0 + (i % BN), red[i]);
         }
     }
     // ---- teardown ----------------------------------------------------------------------------------------------------------
@@ -263,7 +263,7 @@ static cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, con
         RLR_CUDA_CHECK(cudaFuncSetAttribute(umma_conv_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         configured = true;
     }
-    dim3 grid(m_tiles, p.N / BN);
+    dim3 grid(m_tiles, (p.N + BN - 1) / BN);
     umma_conv_gemm_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
     return cudaGetLastError();
 }
@@ -273,7 +273,7 @@ static int pick_bn(int N) { return (N % 128 == 0) ? 128 : 64; }
 // Plain GEMM: out[M][ldc] (bf16) = A[M][K] * B[N][K]^T (+bias)(relu).  K % 64 == 0, N % 64 == 0.
 cudaError_t launch_gemm_bf16(const void* A, const void* B, void* out, int M, int N, int K, int lda, int ldb, int ldc,
                              const float* bias, int relu, int accumulate, float* stats, cudaStream_t st) {
-    if (K % BK || N % 64 || M <= 0) return cudaErrorInvalidValue;
+    if (K % BK || N % 8 || M <= 0) return cudaErrorInvalidValue;
     const int bn = pick_bn(N);
     CUtensorMap tmA, tmB;
     {
@@ -300,7 +300,7 @@ static int pow2_ceil(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 cudaError_t launch_conv_bf16(const void* x, const void* w, void* out, int NB, int planes, int Hin, int Win, int Cin, int Ho, int Wo,
                              int Cout, int ldc, int ntaps, const int* dh, const int* dw, const int* dplane, const float* bias,
                              int relu, int accumulate, float* stats, cudaStream_t st) {
-    if (Cin % BK || Cout % 64 || ntaps < 1 || ntaps > 9) return cudaErrorInvalidValue;
+    if (Cin % BK || Cout % 8 || ntaps < 1 || ntaps > 9) return cudaErrorInvalidValue;
     const int bn = pick_bn(Cout);
     ConvGemmParams p{};
     // output tile: TW x TH x TN = 128 output pixels, TW/TH powers of two covering the image

@@ -49,6 +49,16 @@ void conv_bf16(at::Tensor x, at::Tensor w, at::Tensor out, int64_t NB, int64_t p
                                 opt<const float>(bias), relu, accumulate, opt<float>(stats), cur_stream()), "conv_bf16");
 }
 
+// x: [NB,H,W,64]; w: [Cout, 9*64]; out: [NB,H,W,Cout]   (3x3, stride 1, pad 1)
+void conv3x3_halo_bf16(at::Tensor x, at::Tensor w, at::Tensor out, c10::optional<at::Tensor> bias, bool relu, bool accumulate,
+                       c10::optional<at::Tensor> stats, int64_t bo_mode) {
+    c10::cuda::CUDAGuard g(x.device());
+    TORCH_CHECK(x.dim() == 4 && x.size(3) == 64 && out.dim() == 4 && w.dim() == 2 && w.size(1) == 9 * 64 && w.size(0) == out.size(3));
+    TORCH_CHECK(out.size(0) == x.size(0) && out.size(1) == x.size(1) && out.size(2) == x.size(2));
+    check(rlr::launch_conv3x3_halo_bf16(bf(x), bf(w), bfm(out), x.size(0), x.size(1), x.size(2), out.size(3), opt<const float>(bias), relu,
+                                        accumulate, opt<float>(stats), (int)bo_mode, num_sms(), cur_stream()), "conv3x3_halo_bf16");
+}
+
 // dW[Cout][T][Cin_valid] (fp32, pre-zeroed) += wgrad(dy[NB,Ho,Wo,Cout], x[planes*NB,Hin,Win,Cin])
 void conv_wgrad_bf16(at::Tensor dy, at::Tensor x, at::Tensor dW, int64_t NB, int64_t planes, int64_t cin_valid, std::vector<int64_t> dh,
                      std::vector<int64_t> dw, std::vector<int64_t> dplane) {
@@ -57,7 +67,7 @@ void conv_wgrad_bf16(at::Tensor dy, at::Tensor x, at::Tensor dW, int64_t NB, int
     const int Hin = x.size(1), Win = x.size(2), Cin = x.size(3), Ho = dy.size(1), Wo = dy.size(2), Cout = dy.size(3);
     const int T = (int)dh.size();
     TORCH_CHECK(x.size(0) == planes * NB && dy.size(0) == NB && dW.numel() == (int64_t)Cout * T * cin_valid);
-    TORCH_CHECK(Cout == 64 || Cout % 128 == 0, "wgrad: Cout must be 64 or a multiple of 128");
+    TORCH_CHECK((Cout <= 64 && Cout % 8 == 0) || Cout % 128 == 0, "wgrad: Cout must be <= 64 or a multiple of 128");
     int a[9], b[9], c[9];
     for (int t = 0; t < T; ++t) { a[t] = (int)dh[t]; b[t] = (int)dw[t]; c[t] = (int)dplane[t]; }
     check(rlr::launch_conv_wgrad_bf16(bf(dy), bf(x), f32(dW), (int)NB, (int)planes, Hin, Win, Cin, (int)cin_valid, Ho, Wo, Cout, T, a, b, c,
@@ -66,7 +76,7 @@ void conv_wgrad_bf16(at::Tensor dy, at::Tensor x, at::Tensor dW, int64_t NB, int
 void linear_wgrad_bf16(at::Tensor dy, at::Tensor x, at::Tensor dW) {
     c10::cuda::CUDAGuard g(x.device());
     const int B = x.size(0), K = x.size(1), N = dy.size(1);
-    TORCH_CHECK(dy.size(0) == B && dW.numel() == (int64_t)N * K && (N == 64 || N % 128 == 0));
+    TORCH_CHECK(dy.size(0) == B && dW.numel() == (int64_t)N * K && ((N <= 64 && N % 8 == 0) || N % 128 == 0));
     check(rlr::launch_linear_wgrad_bf16(bf(dy), bf(x), f32(dW), B, N, K, num_sms(), cur_stream()), "linear_wgrad_bf16");
 }
 
@@ -162,6 +172,7 @@ void linear_small_bwd(at::Tensor x, at::Tensor dy, at::Tensor w, c10::optional<a
 void register_gemm_bindings(py::module_& m) {
     m.def("gemm_bf16", &gemm_bf16);
     m.def("conv_bf16", &conv_bf16);
+    m.def("conv3x3_halo_bf16", &conv3x3_halo_bf16);
     m.def("conv_wgrad_bf16", &conv_wgrad_bf16);
     m.def("linear_wgrad_bf16", &linear_wgrad_bf16);
     m.def("channel_stats", &channel_stats);

@@ -203,7 +203,7 @@ static int pow2_ceil_(int x) { int q = 1; while (q < x) q <<= 1; return q; }
 cudaError_t launch_conv_wgrad_bf16(const void* dy, const void* x, float* dW, int NB, int planes, int Hin, int Win, int Cin, int Cin_valid,
                                    int Ho, int Wo, int Cout, int ntaps, const int* dh, const int* dw, const int* dplane, int num_sms,
                                    cudaStream_t st) {
-    if (Cin % 64 || Cout % 64 || (ntaps != 1 && ntaps != 9)) return cudaErrorInvalidValue;
+    if (Cin % 64 || Cout % 8 || (ntaps != 1 && ntaps != 9)) return cudaErrorInvalidValue;
     WgradParams p{};
     int TW = pow2_ceil_(Wo); if (TW > 64) TW = 64;
     int TH = pow2_ceil_(Ho); if (TW * TH > 64) TH = 64 / TW;
@@ -236,7 +236,7 @@ cudaError_t launch_conv_wgrad_bf16(const void* dy, const void* x, float* dW, int
 
 // dW[N][K] += dy[B][N]^T x[B][K]     (N, K multiples of 64)
 cudaError_t launch_linear_wgrad_bf16(const void* dy, const void* x, float* dW, int B, int N, int K, int num_sms, cudaStream_t st) {
-    if (N % 64 || K % 64) return cudaErrorInvalidValue;
+    if (N % 8 || K % 64) return cudaErrorInvalidValue;
     WgradParams p{};
     p.mode = 0; p.num_kb = (B + WG_BK - 1) / WG_BK; p.T = 1; p.ntaps_cta = 1;
     const bool wide = K % 128 == 0;

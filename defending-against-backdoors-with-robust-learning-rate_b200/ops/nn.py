@@ -30,14 +30,15 @@ def conv_supported(in_shape, a, kind):
     """Can the tcgen05 implicit-GEMM kernel run this conv?  ``in_shape`` = (H, W, Cin)."""
     h, w, cin = in_shape
     k, s, p, cout = a["k"], a.get("stride", 1), a.get("pad", 0), a["cout"]
-    if k not in (1, 3) or s not in (1, 2) or cout % 64:
+    if k not in (1, 3) or s not in (1, 2) or cout % 8:
         return False
+    even = s == 1 or (h % 2 == 0 and w % 2 == 0)
     if kind == "fwd":
-        return (s == 1 or (h % 2 == 0 and w % 2 == 0)) and (cin % 64 == 0 or cin < 64)
-    if kind == "dgrad":
-        return cin % 64 == 0 and (s == 1 or (h % 2 == 0 and w % 2 == 0))
+        return even and (cin % 64 == 0 or cin < 64)
+    if kind == "dgrad":      # reduction over Cout (padded to 64 by the TMA zero fill is NOT available here: K must be exact)
+        return even and cin % 8 == 0 and cout % 64 == 0
     if kind == "wgrad":
-        return (s == 1 or (h % 2 == 0 and w % 2 == 0)) and (cin % 64 == 0 or cin < 64) and (cout == 64 or cout % 128 == 0)
+        return even and (cin % 64 == 0 or cin < 64) and (cout <= 64 or cout % 128 == 0)
     return False
 
 
@@ -284,15 +285,27 @@ def linear_bwd(x, dy, w, dx, dw, db, acc_dx, impl, zero=True):
         _ext().linear_small_bwd(x.contiguous(), dy.contiguous(), w, dx, dw, db, bool(acc_dx))
         return
     dyf = dy.to(x.dtype)
-    if impl == "sm100" and K % 64 == 0 and (N == 64 or N % 128 == 0):
+    sm = impl == "sm100" and K % 64 == 0 and N % 64 == 0
+    if sm and (N <= 64 or N % 128 == 0):
         if zero:
             dw.zero_()
         _ext().linear_wgrad_bf16(dy.contiguous(), x.contiguous(), dw)
     else:
         dw.copy_(dyf.t() @ x)
     if db is not None:
-        db.copy_(dyf.float().sum(0))
+        if sm and N % 8 == 0 and 256 % (N // 8) == 0:
+            st = scratch(("dbias_lin", w.data_ptr()), (2, N), torch.float32, dy.device)
+            st.zero_()
+            _ext().channel_stats(dy.contiguous(), st)
+            db.copy_(st[0])
+        else:
+            db.copy_(dyf.float().sum(0))
     if dx is not None:
+        if sm:   # dx = dy @ W  ==  GEMM with the transposed weight as the K-major B operand
+            wt = scratch(("wt_lin", w.data_ptr()), (K, N), w.dtype, w.device)
+            _ext().filter_transpose(w, wt, N, 1, K)
+            _ext().gemm_bf16(dy.contiguous(), wt, dx, None, False, bool(acc_dx), None)
+            return
         d = dyf @ w.to(x.dtype)
         if acc_dx:
             dx.add_(d)

@@ -124,6 +124,7 @@ def test_input_streaming_roundtrip():
     eng = _engine(num_agents=2)
     nbytes = eng.enable_input_streaming()
     assert nbytes == 1200 * (28 * 28 + 8)
-    before = eng.train_dataset.data.clone()
+    before = [a.dataset.data.clone() for a in eng.agents]
     info = eng.run_round(1, stream_inputs=True)
-    assert info["h2d_bytes"] == nbytes and torch.equal(before, eng.train_dataset.data)
+    assert info["h2d_bytes"] == nbytes and all(torch.equal(b, a.dataset.data) for a, b in zip(eng.agents, before))
+    assert all(len(a.dataset) == a.n_data for a in eng.agents)

@@ -41,7 +41,7 @@ CONV_CASES = [  # B, H, W, Cin, Cout, k, stride, pad
     (256, 32, 32, 64, 64, 3, 1, 1), (80, 32, 32, 64, 64, 3, 1, 1), (64, 16, 16, 128, 128, 3, 1, 1), (64, 8, 8, 256, 256, 3, 1, 1),
     (80, 4, 4, 512, 512, 3, 1, 1), (37, 2, 2, 512, 512, 3, 1, 1), (32, 32, 32, 3, 64, 3, 1, 1), (32, 32, 32, 64, 128, 3, 2, 1),
     (32, 32, 32, 64, 128, 1, 2, 0), (40, 8, 8, 256, 512, 3, 2, 1), (40, 8, 8, 256, 512, 1, 2, 0), (16, 15, 15, 64, 128, 3, 1, 0),
-    (16, 26, 26, 64, 64, 3, 1, 0), (8, 30, 30, 3, 64, 3, 1, 0),
+    (16, 26, 26, 64, 64, 3, 1, 0), (8, 30, 30, 3, 64, 3, 1, 0), (32, 28, 28, 1, 32, 3, 1, 0), (32, 26, 26, 32, 64, 3, 1, 0),
 ]
 
 
@@ -64,7 +64,8 @@ def test_conv_fwd(B, H, W, Cin, Cout, k, s, p):
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout,k,p,acc", [(64, 32, 32, 64, 64, 3, 1, False), (80, 16, 16, 128, 128, 3, 1, True),
                                                      (48, 8, 8, 256, 256, 3, 1, True), (80, 4, 4, 512, 512, 3, 1, False),
-                                                     (16, 15, 15, 64, 128, 3, 0, False), (32, 8, 8, 128, 64, 1, 0, False)])
+                                                     (16, 15, 15, 64, 128, 3, 0, False), (32, 8, 8, 128, 64, 1, 0, False),
+                                                     (32, 26, 26, 32, 64, 3, 0, False)])
 def test_conv_dgrad(B, H, W, Cin, Cout, k, p, acc, s=1):
     torch.manual_seed(B + H)
     Ho, Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
@@ -91,7 +92,7 @@ def test_conv_dgrad_stride2(B, H, W, Cin, Cout, k, p, acc):
 @pytest.mark.parametrize("B,H,W,Cin,Cout,k,s,p", [(64, 32, 32, 64, 64, 3, 1, 1), (80, 16, 16, 128, 128, 3, 1, 1), (48, 8, 8, 256, 256, 3, 1, 1),
                                                    (80, 4, 4, 512, 512, 3, 1, 1), (32, 32, 32, 3, 64, 3, 1, 1), (32, 32, 32, 64, 128, 3, 2, 1),
                                                    (32, 32, 32, 64, 128, 1, 2, 0), (40, 8, 8, 256, 512, 3, 2, 1), (16, 15, 15, 64, 128, 3, 1, 0),
-                                                   (24, 2, 2, 512, 512, 3, 1, 1)])
+                                                   (24, 2, 2, 512, 512, 3, 1, 1), (32, 28, 28, 1, 32, 3, 1, 0), (32, 26, 26, 32, 64, 3, 1, 0)])
 def test_conv_wgrad(B, H, W, Cin, Cout, k, s, p):
     torch.manual_seed(B + H + Cin)
     Ho, Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
@@ -253,3 +254,29 @@ def test_native_trainer_learns_like_torch_trainer(model):
         eng.close()
     print(model, accs)
     assert accs["native"] > 0.5 and accs["native"] > accs["torch"] - 0.25
+
+
+@pytest.mark.parametrize("B,H,W,Cout,acc", [(64, 32, 32, 64, False), (37, 16, 16, 64, True), (8, 32, 32, 128, False), (5, 16, 8, 32, False)])
+def test_conv3x3_halo_kernel(B, H, W, Cout, acc):
+    """Persistent halo-reuse conv (conv_halo.cu): A operands are shifted views into one smem halo tile (descriptor start not
+    aligned to the swizzle atom -> base-offset field)."""
+    torch.manual_seed(B + H)
+    x = torch.randn(B, H, W, 64, device=DEV).to(BF)
+    w = (torch.randn(Cout, 3, 3, 64, device=DEV) / 24).to(BF)
+    bias = torch.randn(Cout, device=DEV) * 0.1
+    base = torch.randn(B, H, W, Cout, device=DEV).to(BF)
+    ref = F.relu(F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), bias, 1, 1)).permute(0, 2, 3, 1)
+    if acc:
+        ref = ref + base.float()
+    errs = {}
+    for bo in (1, 0):
+        y = base.clone() if acc else torch.full_like(base, 5.0)
+        stats = torch.zeros(2, Cout, device=DEV)
+        ops.ext().conv3x3_halo_bf16(x, w.reshape(Cout, 576), y, bias, True, acc, stats, bo)
+        torch.cuda.synchronize()
+        errs[bo] = _rel(y, ref)
+        if bo == 1:
+            s_ok = acc or torch.allclose(stats[0], y.float().sum((0, 1, 2)), rtol=2e-3, atol=0.5)
+    print("halo conv rel err by base-offset mode:", errs)
+    assert errs[1] < 1e-2, errs
+    assert s_ok

@@ -1,0 +1,59 @@
+"""The native executor's plan (fusion, hand-derived backward, residual gradient accumulation) against PyTorch autograd, run on
+CPU in fp32 through the `aten` back-end.  The sm_100a kernels behind the same plan are checked in tests/test_gpu_native.py."""
+import pytest
+import torch
+
+from rlr_b200 import ops
+from rlr_b200.models import GraphNet, get_layout
+from rlr_b200.models.native import NativeNet
+
+
+@pytest.mark.parametrize("name,tol", [("cnn_mnist", 1e-5), ("cnn_cifar", 1e-5), ("vgg11", 1e-4), ("resnet18", 3e-2)])
+def test_plan_matches_autograd(name, tol):
+    torch.manual_seed(0)
+    lay = get_layout(name)
+    for nd in lay.nodes:
+        if nd.op == "dropout":
+            nd.attrs["p"] = 0.0
+    w = lay.init_(torch.zeros(lay.n_total), 1)
+    g_ref, g_nat = torch.zeros(lay.n_total), torch.zeros(lay.n_total)
+    ref = GraphNet(lay, w.clone(), g_ref)
+    ref.train()
+    nat = NativeNet(lay, "cpu", 8, impl="aten", act_dtype=torch.float32)
+    w2 = w.clone()
+    nat.bind(w2, w2, g_nat)
+    C, H, W = lay.in_shape
+    x, y = torch.randn(6, C, H, W), torch.randint(0, 10, (6,))
+    logits_ref = ref(x)
+    torch.nn.functional.cross_entropy(logits_ref, y).backward()
+    logits = nat.forward(x.permute(0, 2, 3, 1).contiguous(), True)
+    _, dl = ops.softmax_xent(logits, y)
+    nat.backward(dl)
+    nv = lay.n_vote
+    torch.testing.assert_close(logits, logits_ref.detach(), atol=1e-4, rtol=1e-4)
+    # ResNet: BatchNorm backward on 6 samples is ill-conditioned (near-zero channel variances) -> looser bound
+    assert float((g_nat[:nv] - g_ref[:nv]).abs().max()) <= tol * max(1.0, float(g_ref[:nv].abs().max()))
+    torch.testing.assert_close(w2[nv:], ref.w[nv:], atol=1e-4, rtol=1e-4)          # BN running statistics
+
+
+def test_plan_fusion_shapes_resnet():
+    lay = get_layout("resnet18")
+    nat = NativeNet(lay, "cpu", 2, impl="aten", act_dtype=torch.float32)
+    kinds = [op.kind for op in nat.plan]
+    assert kinds.count("conv") == 20 and kinds.count("bn") == 20 and kinds.count("linear") == 1
+    fused_add = [op for op in nat.plan if op.kind == "bn" and op.res is not None]
+    assert len(fused_add) == 8 and all(op.relu for op in fused_add)      # one bn+add+relu per BasicBlock
+    assert sum(op.acc_dx for op in nat.plan if op.kind == "conv") == 8   # conv1 of every block accumulates into the skip grad
+    assert all(op.saved["want_stats"] for op in nat.plan if op.kind == "conv")
+
+
+def test_eval_mode_uses_running_stats_and_no_dropout():
+    lay = get_layout("cnn_cifar")
+    w = lay.init_(torch.zeros(lay.n_total), 3)
+    nat = NativeNet(lay, "cpu", 4, impl="aten", act_dtype=torch.float32)
+    nat.bind(w, w, None)
+    x = torch.randn(4, 32, 32, 3)
+    a, b = nat.forward(x, False).clone(), nat.forward(x, False).clone()
+    ref = GraphNet(lay, w.clone(), None).eval()
+    torch.testing.assert_close(a, b)
+    torch.testing.assert_close(a, ref(x.permute(0, 3, 1, 2)).detach(), atol=1e-4, rtol=1e-4)
