@@ -206,13 +206,14 @@ class NativeNet:
         self.logits = torch.empty((B, self.tshape[self.out_tid][-1]), dtype=torch.float32, device=dev)
         # all per-channel accumulators live in two arenas so one memset per pass re-arms every layer's atomics
         need = [op for op in self.plan if op.kind == "bn" or (op.kind == "conv" and op.saved.get("want_stats"))]
+        S = ops.STAT_SLOTS
         tot = sum(2 * op.out_shape[-1] for op in need)
-        self.stats_arena = torch.zeros(max(1, tot), dtype=torch.float32, device=dev)   # forward: sum, sum of squares
-        self.dsum_arena = torch.zeros(max(1, tot), dtype=torch.float32, device=dev)    # backward: sum dy, sum dy*xhat
+        self.stats_arena = torch.zeros(max(1, tot * S), dtype=torch.float32, device=dev)   # forward: [slots][sum, sum^2][C] per op
+        self.dsum_arena = torch.zeros(max(1, tot), dtype=torch.float32, device=dev)        # backward: sum dy, sum dy*xhat
         off = 0
         for op in need:
             c = op.out_shape[-1]
-            op.saved["stats"] = self.stats_arena[off:off + 2 * c].view(2, c)
+            op.saved["stats"] = self.stats_arena[off * S:(off + 2 * c) * S].view(S, 2, c)
             op.saved["dsum"] = self.dsum_arena[off:off + 2 * c].view(2, c)
             op.saved["mean_rstd"] = torch.zeros(2, c, dtype=torch.float32, device=dev)
             off += 2 * c
@@ -284,7 +285,7 @@ class NativeNet:
         y.copy_(out.permute(0, 2, 3, 1))
         if stats is not None:
             yf = y.float().reshape(-1, y.shape[-1])
-            stats[0].copy_(yf.sum(0)); stats[1].copy_((yf * yf).sum(0))
+            stats[0, 0].copy_(yf.sum(0)); stats[0, 1].copy_((yf * yf).sum(0))   # slot 0; the others stay zero
 
     def _bwd_conv(self, op, B):
         a = op.attrs

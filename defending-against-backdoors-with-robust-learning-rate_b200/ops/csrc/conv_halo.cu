@@ -5,8 +5,11 @@
 // Here an output tile is 16 rows x 8 columns of one image and its whole receptive field -- 18 x 10 pixels x 64 channels,
 // stored with a 16-pixel row pitch = 36 KB -- is loaded ONCE by a single 4-D TMA box (zero fill at the borders = padding).
 // The A operand of tap (dy,dx) is then just a *view* into that halo: 16 groups (image rows) of 8 pixel-rows, group stride
-// SBO = 16 px * 128 B = 2048 B, start address offset by (dy*16 + dx) * 128 B; because that start is not aligned to the
-// 1024-byte swizzle atom, the descriptor's base-offset field carries (address >> 7) & 7 = dx.  All 9 x 64 x 64 filter taps
+// SBO = 16 px * 128 B = 2048 B, start address offset by (dy*16 + dx) * 128 B.  That start is not aligned to the 1024-byte
+// swizzle atom; measured on B200 (tests/test_gpu_native.py::test_conv3x3_halo_kernel): the tensor core applies the 128-byte
+// swizzle as a function of the ABSOLUTE shared-memory address bits, exactly like the TMA unit that wrote the tile, so the
+// shifted view is read correctly with the descriptor's base-offset field left at 0 (setting it to (addr>>7)&7 is wrong).
+// All 9 x 64 x 64 filter taps
 // (72 KB) stay resident in shared memory for the lifetime of the persistent CTA, so per output tile the kernel moves 36 KB
 // instead of 216 KB and becomes tensor/epilogue bound.  Accumulators are double-buffered in TMEM (2 x 64 columns) so the
 // epilogue of tile i (bias / ReLU / residual-accumulate / bf16 / coalesced stores / BatchNorm statistics) overlaps the
@@ -43,7 +46,7 @@ struct HaloParams {
     const float* bias;
     float* stats;
     int relu, accumulate;
-    int bo_mode;                  // 1: descriptor base offset = (addr >> 7) & 7 (documented); 0: leave it at zero (experiment)
+    int bo_mode;                  // 0 (correct on B200): base-offset field 0;  1: (addr >> 7) & 7 -- kept for the experiment
 };
 
 struct __align__(8) HaloShared {
@@ -145,9 +148,22 @@ umma_conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
         __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
         int acc = 0;
         uint32_t acc_phase = 0;
+        if (p.stats) red[et] = 0.f;                                 // per-CTA statistics, flushed once at the end
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             const int n = tile / tiles_per_img, r = tile - n * tiles_per_img;
             const int h0 = (r / p.tiles_w) * HL_TH, w0 = (r % p.tiles_w) * HL_TW;
+            // residual-accumulate operand: issue all loads BEFORE waiting for the accumulator so their latency overlaps the MMAs
+            uint4 oldv[8];
+            if (p.accumulate) {
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int idx = et + it * 128, rr = idx >> 3, ch = idx & 7;
+                    const int h = h0 + (rr >> 3), w = w0 + (rr & 7);
+                    oldv[it] = make_uint4(0, 0, 0, 0);
+                    if (col0 + ch * 8 < p.N && h < p.H && w < p.W)
+                        oldv[it] = *reinterpret_cast<const uint4*>(out + (((size_t)n * p.H + h) * p.W + w) * p.ldc + col0 + ch * 8);
+                }
+            }
             mbar_wait(&sh->acc_full[acc], acc_phase);
             tc_fence_after();
 #pragma unroll
@@ -168,10 +184,11 @@ umma_conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
             }
             tc_fence_before();
             mbar_arrive(&sh->acc_empty[acc]);                        // 128 arrivals release the accumulator to the MMA warp
-            if (p.stats) { for (int i = et; i < 128; i += 128) red[i] = 0.f; }
             asm volatile("bar.sync 1, 128;" ::: "memory");
             // coalesced stores: tile row rr = g*8 + px  ->  image pixel (h0+g, w0+px)
-            for (int idx = et; idx < 128 * 8; idx += 128) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int idx = et + it * 128;
                 const int rr = idx >> 3, ch = idx & 7;
                 if (col0 + ch * 8 >= p.N) continue;
                 const int h = h0 + (rr >> 3), w = w0 + (rr & 7);
@@ -180,8 +197,7 @@ umma_conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
                 uint4 val = *reinterpret_cast<const uint4*>(s_stage + rr * HL_PITCH_OUT + ch * 16);
                 uint4* gp = reinterpret_cast<uint4*>(out + gi * p.ldc + col0 + ch * 8);
                 if (p.accumulate) {
-                    const uint4 old = *gp;
-                    const __nv_bfloat162* o2 = reinterpret_cast<const __nv_bfloat162*>(&old);
+                    const __nv_bfloat162* o2 = reinterpret_cast<const __nv_bfloat162*>(&oldv[it]);
                     __nv_bfloat162* v2 = reinterpret_cast<__nv_bfloat162*>(&val);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
@@ -202,13 +218,15 @@ umma_conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
                 }
                 atomicAdd(&red[2 * cp], s1a); atomicAdd(&red[2 * cp + 1], s1b);
                 atomicAdd(&red[64 + 2 * cp], s2a); atomicAdd(&red[64 + 2 * cp + 1], s2b);
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (col0 + (et & 63) < p.N) atomicAdd(p.stats + (et < 64 ? 0 : p.N) + col0 + (et & 63), red[et]);
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");           // staging may be overwritten by the next tile
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
+        // one global reduction per CTA and channel (instead of per tile), spread over kStatSlots slots to cut same-address
+        // contention in L2; bn_finalize sums the slots
+        if (p.stats && col0 + (et & 63) < p.N)
+            atomicAdd(p.stats + (size_t)(blockIdx.x % kStatSlots) * 2 * p.N + (et < 64 ? 0 : p.N) + col0 + (et & 63), red[et]);
     }
     tc_fence_before();
     __syncthreads();

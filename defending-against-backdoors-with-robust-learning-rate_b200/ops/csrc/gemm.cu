@@ -173,23 +173,36 @@ umma_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         // ---- coalesced 16-byte stores (optionally accumulating into the existing output) ----
         constexpr int kChunks = BN * 2 / 16;             // 16 B chunks per row
         __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
-        for (int idx = et; idx < BM * kChunks; idx += kEpiThreads) {
-            const int r = idx / kChunks, ch = idx - r * kChunks;
-            const int gi = tail->row_index[r];
-            if (gi < 0 || col0 + ch * 8 >= p.N) continue;     // masked row / column chunk beyond Cout
-            uint4 val = *reinterpret_cast<const uint4*>(staging + r * Cfg::kPitch + ch * 16);
-            uint4* gp = reinterpret_cast<uint4*>(out + (size_t)gi * p.ldc + col0 + ch * 8);
-            if (p.accumulate) {
-                const uint4 old = *gp;
-                const __nv_bfloat162* o2 = reinterpret_cast<const __nv_bfloat162*>(&old);
-                __nv_bfloat162* v2 = reinterpret_cast<__nv_bfloat162*>(&val);
+        constexpr int kIters = BM * kChunks / kEpiThreads;   // 8 (BN=64) / 16 (BN=128) chunks per thread
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float2 a = __bfloat1622float2(v2[q]), b = __bfloat1622float2(o2[q]);
-                    v2[q] = __floats2bfloat162_rn(a.x + b.x, a.y + b.y);
+        for (int it0 = 0; it0 < kIters; it0 += 8) {
+            uint4 oldv[8];
+            if (p.accumulate) {                             // batch the read-modify-write loads: one latency per 8 chunks
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int idx = et + (it0 + j) * kEpiThreads, r = idx / kChunks, ch = idx - r * kChunks;
+                    const int gi = tail->row_index[r];
+                    oldv[j] = make_uint4(0, 0, 0, 0);
+                    if (gi >= 0 && col0 + ch * 8 < p.N) oldv[j] = *reinterpret_cast<const uint4*>(out + (size_t)gi * p.ldc + col0 + ch * 8);
                 }
             }
-            *gp = val;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int idx = et + (it0 + j) * kEpiThreads, r = idx / kChunks, ch = idx - r * kChunks;
+                const int gi = tail->row_index[r];
+                if (gi < 0 || col0 + ch * 8 >= p.N) continue;     // masked row / column chunk beyond Cout
+                uint4 val = *reinterpret_cast<const uint4*>(staging + r * Cfg::kPitch + ch * 16);
+                if (p.accumulate) {
+                    const __nv_bfloat162* o2 = reinterpret_cast<const __nv_bfloat162*>(&oldv[j]);
+                    __nv_bfloat162* v2 = reinterpret_cast<__nv_bfloat162*>(&val);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float2 a = __bfloat1622float2(v2[q]), b = __bfloat1622float2(o2[q]);
+                        v2[q] = __floats2bfloat162_rn(a.x + b.x, a.y + b.y);
+                    }
+                }
+                *reinterpret_cast<uint4*>(out + (size_t)gi * p.ldc + col0 + ch * 8) = val;
+            }
         }
         // ---- per-channel statistics of the (bf16-rounded) output tile: sum and sum of squares -> BatchNorm ----
         // 128 threads = (BN/2 column pairs) x (256/BN row slices); partials meet in shared memory, one global atomic
@@ -213,7 +226,8 @@ umma_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             atomicAdd(&red[BN + 2 * cp], s2a); atomicAdd(&red[BN + 2 * cp + 1], s2b);
             asm volatile("bar.sync 1, 128;" ::: "memory");
             for (int i = et; i < 2 * BN; i += kEpiThreads)
-                if (col0 + (i % BN) < p.N) atomicAdd(p.stats + (i < BN ? 0 : p.N) + col0 + (i % BN), red[i]);
+                if (col0 + (i % BN) < p.N)
+                    atomicAdd(p.stats + (size_t)(blockIdx.x % kStatSlots) * 2 * p.N + (i < BN ? 0 : p.N) + col0 + (i % BN), red[i]);
         }
     }
     // ---- teardown ----------------------------------------------------------------------------------------------------------

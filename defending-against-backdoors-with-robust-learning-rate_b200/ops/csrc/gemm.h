@@ -7,6 +7,10 @@
 
 namespace rlr {
 
+// conv epilogues reduce per-channel statistics into one of kStatSlots partial buffers ([slots][2][C]) chosen by CTA index, so
+// same-address atomics in L2 are spread 16x; bn_finalize sums the slots.
+constexpr int kStatSlots = 16;
+
 struct ConvGemmParams {
     int M, N, num_kb;
     int mode;                  // 0 plain [M][K] A operand, 1 implicit conv (4-D NHWC A operand)
@@ -38,14 +42,16 @@ cudaError_t launch_conv3x3_halo_bf16(const void* x, const void* w, void* out, in
 cudaError_t launch_conv_wgrad_bf16(const void* dy, const void* x, float* dW, int NB, int planes, int Hin, int Win, int Cin, int Cin_valid,
                                    int Ho, int Wo, int Cout, int ntaps, const int* dh, const int* dw, const int* dplane, int num_sms,
                                    cudaStream_t st);
+cudaError_t launch_conv_wgrad_halo_bf16(const void* dy, const void* x, float* dW, int NB, int H, int W, int Cin_valid, int Cout,
+                                        int num_sms, cudaStream_t st);
 cudaError_t launch_linear_wgrad_bf16(const void* dy, const void* x, float* dW, int B, int N, int K, int num_sms, cudaStream_t st);
 
 // ---- norm.cu: NHWC bf16 layer kernels -----------------------------------------------------------------------------
 // per-channel sum / sum of squares of x[M][C]
 cudaError_t launch_channel_stats(const __nv_bfloat16* x, long long M, int C, float* stats /*[2][C], accumulates*/, int num_sms, cudaStream_t st);
 // finalize statistics: mean/rstd (+ running stats update with momentum, unbiased variance)
-cudaError_t launch_bn_finalize(const float* stats, float* mean_rstd, float* running_mean, float* running_var, int C, float count,
-                               float eps, float momentum, int train, cudaStream_t st);
+cudaError_t launch_bn_finalize(const float* stats, int slots, float* mean_rstd, float* running_mean, float* running_var, int C,
+                               float count, float eps, float momentum, int train, cudaStream_t st);
 // y = act(gamma * (x - mean) * rstd + beta [+ res])
 cudaError_t launch_bn_apply(const __nv_bfloat16* x, const __nv_bfloat16* res, __nv_bfloat16* y, const float* gamma, const float* beta,
                             const float* mean_rstd, long long M, int C, int relu, int num_sms, cudaStream_t st);

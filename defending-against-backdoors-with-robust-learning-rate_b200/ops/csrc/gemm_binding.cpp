@@ -31,6 +31,7 @@ void gemm_bf16(at::Tensor A, at::Tensor B, at::Tensor out, c10::optional<at::Ten
     c10::cuda::CUDAGuard g(A.device());
     const int M = A.size(0), K = A.size(1), N = B.size(0);
     TORCH_CHECK(B.size(1) == K && out.size(0) == M && out.size(1) == N);
+    TORCH_CHECK(!stats.has_value() || !stats->defined() || stats->numel() == (int64_t)rlr::kStatSlots * 2 * N, "stats must be [STAT_SLOTS,2,N]");
     check(rlr::launch_gemm_bf16(bf(A), bf(B), bfm(out), M, N, K, K, K, N, opt<const float>(bias), relu, accumulate, opt<float>(stats),
                                 cur_stream()), "gemm_bf16");
 }
@@ -43,6 +44,7 @@ void conv_bf16(at::Tensor x, at::Tensor w, at::Tensor out, int64_t NB, int64_t p
     const int Hin = x.size(1), Win = x.size(2), Cin = x.size(3), Ho = out.size(1), Wo = out.size(2), Cout = out.size(3);
     const int T = (int)dh.size();
     TORCH_CHECK(x.size(0) == planes * NB && out.size(0) == NB && w.size(0) == Cout && w.size(1) == (int64_t)T * Cin);
+    TORCH_CHECK(!stats.has_value() || !stats->defined() || stats->numel() == (int64_t)rlr::kStatSlots * 2 * Cout, "stats must be [STAT_SLOTS,2,Cout]");
     int a[9], b[9], c[9];
     for (int t = 0; t < T; ++t) { a[t] = (int)dh[t]; b[t] = (int)dw[t]; c[t] = (int)dplane[t]; }
     check(rlr::launch_conv_bf16(bf(x), bf(w), bfm(out), (int)NB, (int)planes, Hin, Win, Cin, Ho, Wo, Cout, Cout, T, a, b, c,
@@ -55,6 +57,7 @@ void conv3x3_halo_bf16(at::Tensor x, at::Tensor w, at::Tensor out, c10::optional
     c10::cuda::CUDAGuard g(x.device());
     TORCH_CHECK(x.dim() == 4 && x.size(3) == 64 && out.dim() == 4 && w.dim() == 2 && w.size(1) == 9 * 64 && w.size(0) == out.size(3));
     TORCH_CHECK(out.size(0) == x.size(0) && out.size(1) == x.size(1) && out.size(2) == x.size(2));
+    TORCH_CHECK(!stats.has_value() || !stats->defined() || stats->numel() == (int64_t)rlr::kStatSlots * 2 * out.size(3), "stats must be [STAT_SLOTS,2,Cout]");
     check(rlr::launch_conv3x3_halo_bf16(bf(x), bf(w), bfm(out), x.size(0), x.size(1), x.size(2), out.size(3), opt<const float>(bias), relu,
                                         accumulate, opt<float>(stats), (int)bo_mode, num_sms(), cur_stream()), "conv3x3_halo_bf16");
 }
@@ -73,6 +76,14 @@ void conv_wgrad_bf16(at::Tensor dy, at::Tensor x, at::Tensor dW, int64_t NB, int
     check(rlr::launch_conv_wgrad_bf16(bf(dy), bf(x), f32(dW), (int)NB, (int)planes, Hin, Win, Cin, (int)cin_valid, Ho, Wo, Cout, T, a, b, c,
                                       num_sms(), cur_stream()), "conv_wgrad_bf16");
 }
+// 3x3/s1/p1 weight gradient with smem halo reuse: x [NB,H,W,64], dy [NB,H,W,Cout], dW [Cout,9,cin_valid]
+void conv_wgrad_halo_bf16(at::Tensor dy, at::Tensor x, at::Tensor dW, int64_t cin_valid) {
+    c10::cuda::CUDAGuard g(x.device());
+    TORCH_CHECK(x.dim() == 4 && x.size(3) == 64 && dy.dim() == 4 && dy.size(0) == x.size(0) && dy.size(1) == x.size(1) && dy.size(2) == x.size(2));
+    TORCH_CHECK(dW.numel() == dy.size(3) * 9 * cin_valid);
+    check(rlr::launch_conv_wgrad_halo_bf16(bf(dy), bf(x), f32(dW), x.size(0), x.size(1), x.size(2), (int)cin_valid, dy.size(3), num_sms(),
+                                           cur_stream()), "conv_wgrad_halo_bf16");
+}
 void linear_wgrad_bf16(at::Tensor dy, at::Tensor x, at::Tensor dW) {
     c10::cuda::CUDAGuard g(x.device());
     const int B = x.size(0), K = x.size(1), N = dy.size(1);
@@ -88,7 +99,9 @@ void channel_stats(at::Tensor x, at::Tensor stats) {
 void bn_finalize(at::Tensor stats, at::Tensor mean_rstd, at::Tensor rm, at::Tensor rv, double count, double eps, double momentum, bool train) {
     c10::cuda::CUDAGuard g(stats.device());
     const int C = mean_rstd.size(-1);
-    check(rlr::launch_bn_finalize(f32(stats), f32(mean_rstd), (float*)rm.data_ptr(), (float*)rv.data_ptr(), C, (float)count, (float)eps,
+    const int slots = (int)(stats.numel() / (2 * C));
+    TORCH_CHECK(slots >= 1 && stats.numel() == (int64_t)slots * 2 * C, "stats must be [slots, 2, C]");
+    check(rlr::launch_bn_finalize(f32(stats), slots, f32(mean_rstd), (float*)rm.data_ptr(), (float*)rv.data_ptr(), C, (float)count, (float)eps,
                                   (float)momentum, train, cur_stream()), "bn_finalize");
 }
 void bn_apply(at::Tensor x, c10::optional<at::Tensor> res, at::Tensor y, at::Tensor gamma, at::Tensor beta, at::Tensor mean_rstd, bool relu) {
@@ -170,11 +183,13 @@ void linear_small_bwd(at::Tensor x, at::Tensor dy, at::Tensor w, c10::optional<a
 }  // namespace
 
 void register_gemm_bindings(py::module_& m) {
+    m.attr("STAT_SLOTS") = rlr::kStatSlots;
     m.def("gemm_bf16", &gemm_bf16);
     m.def("conv_bf16", &conv_bf16);
     m.def("conv3x3_halo_bf16", &conv3x3_halo_bf16);
     m.def("conv_wgrad_bf16", &conv_wgrad_bf16);
     m.def("linear_wgrad_bf16", &linear_wgrad_bf16);
+    m.def("conv_wgrad_halo_bf16", &conv_wgrad_halo_bf16);
     m.def("channel_stats", &channel_stats);
     m.def("bn_finalize", &bn_finalize);
     m.def("bn_apply", &bn_apply);

@@ -87,13 +87,15 @@ cudaError_t launch_bn_bwd_reduce(const __nv_bfloat16* dy, const __nv_bfloat16* y
     return cudaGetLastError();
 }
 
-__global__ void bn_finalize_kernel(const float* __restrict__ stats, float* __restrict__ mean_rstd, float* running_mean,
+__global__ void bn_finalize_kernel(const float* __restrict__ stats, int slots, float* __restrict__ mean_rstd, float* running_mean,
                                    float* running_var, int C, float count, float eps, float momentum, int train) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     if (train) {
-        const float mean = stats[c] / count;
-        const float var = fmaxf(stats[C + c] / count - mean * mean, 0.f);
+        float s1 = 0.f, s2 = 0.f;
+        for (int k = 0; k < slots; ++k) { s1 += stats[(size_t)k * 2 * C + c]; s2 += stats[(size_t)k * 2 * C + C + c]; }
+        const float mean = s1 / count;
+        const float var = fmaxf(s2 / count - mean * mean, 0.f);
         mean_rstd[c] = mean;
         mean_rstd[C + c] = rsqrtf(var + eps);
         running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
@@ -104,9 +106,9 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, float* __res
         mean_rstd[C + c] = rsqrtf(running_var[c] + eps);
     }
 }
-cudaError_t launch_bn_finalize(const float* stats, float* mean_rstd, float* running_mean, float* running_var, int C, float count,
-                               float eps, float momentum, int train, cudaStream_t st) {
-    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(stats, mean_rstd, running_mean, running_var, C, count, eps, momentum, train);
+cudaError_t launch_bn_finalize(const float* stats, int slots, float* mean_rstd, float* running_mean, float* running_var, int C,
+                               float count, float eps, float momentum, int train, cudaStream_t st) {
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(stats, slots, mean_rstd, running_mean, running_var, C, count, eps, momentum, train);
     return cudaGetLastError();
 }
 

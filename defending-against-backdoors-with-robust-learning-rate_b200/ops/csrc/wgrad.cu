@@ -197,6 +197,173 @@ static cudaError_t launch_wg(const CUtensorMap& tmA, const CUtensorMap& tmB, Wgr
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Halo-reuse variant for 3x3 / stride-1 / pad-1 filters over 64 input channels (stem, layer1, first VGG block).
+// A k-block is one 16x8 output tile (128 pixels); its dY tile (128 px x 64/128 co) and ONE 18x16-pixel halo of X (36 KB)
+// are loaded once and serve every filter tap: the B operand of tap (dy,dx) and MMA k-step j (16 pixels = image rows 2j,2j+1)
+// is the MN-major view starting at halo + ((2j+dy)*16 + dx)*128 B with an 8-row group stride (SBO) of 2048 B -- the tensor
+// core applies the 128-byte swizzle on absolute smem address bits, so unaligned starts need no special handling
+// (see conv_halo.cu).  The 9 taps do not fit TMEM at once (9 x 64 > 512 columns): grid.y = 2 tap groups (5 + 4 taps).
+// L2 traffic per 128 pixels: 2 x (36 + 16..32) KB instead of 3 x 2 x (24 + 8..16) KB.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int WH_STAGES = 3;
+constexpr int WH_A_BYTES = 2 * 128 * 128;                      // up to two 64-channel groups x 128 pixel rows x 128 B
+constexpr int WH_HALO_BYTES = 18 * 16 * 128;                   // 36864
+constexpr int WH_STAGE_BYTES = WH_A_BYTES + WH_HALO_BYTES;     // 69632
+constexpr int WH_SMEM = WH_STAGES * WH_STAGE_BYTES + 2048;
+
+struct WgHaloParams {
+    int NB, H, W, tiles_h, tiles_w;
+    int num_kb, kb_per_cta;
+    int a_groups;
+    int Cout, Cin_valid;
+    float* dW;                // [Cout][9][Cin_valid]
+};
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+umma_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const WgHaloParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    WgShared* sh = reinterpret_cast<WgShared*>(smem + WH_STAGES * WH_STAGE_BYTES);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int co_tile = blockIdx.x;
+    const int tap0 = blockIdx.y * 5, ntaps = blockIdx.y == 0 ? 5 : 4;
+    const int kb_begin = blockIdx.z * p.kb_per_cta;
+    const int kb_end = min(p.num_kb, kb_begin + p.kb_per_cta);
+    const int nkb = kb_end - kb_begin;
+    const int tiles_per_img = p.tiles_h * p.tiles_w;
+
+    if (warp == 0 && lane == 0) { prefetch_tmap(&tmA); prefetch_tmap(&tmB); }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < WH_STAGES; ++s) { mbar_init(&sh->full[s], 1); mbar_init(&sh->empty[s], 1); }
+        mbar_init(&sh->tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(&sh->tmem_base, 512);
+    if (p.a_groups == 1) {
+        for (int s = 0; s < WH_STAGES; ++s) {
+            uint4* z = reinterpret_cast<uint4*>(smem + s * WH_STAGE_BYTES + 16384);
+            for (int i = threadIdx.x; i < 16384 / 16; i += WG_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_acc = sh->tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const uint32_t bytes = p.a_groups * 16384 + WH_HALO_BYTES;
+            for (int i = 0; i < nkb; ++i) {
+                const int kb = kb_begin + i;
+                const int n = kb / tiles_per_img, r = kb - n * tiles_per_img;
+                const int h0 = (r / p.tiles_w) * 16, w0 = (r % p.tiles_w) * 8;
+                mbar_wait(&sh->empty[stage], phase ^ 1);
+                uint8_t* sa = smem + stage * WH_STAGE_BYTES;
+                mbar_expect_tx(&sh->full[stage], bytes);
+                for (int g = 0; g < p.a_groups; ++g)
+                    tma_load_4d(&tmA, &sh->full[stage], sa + g * 16384, co_tile * WG_BM + g * 64, w0, h0, n);
+                tma_load_4d(&tmB, &sh->full[stage], sa + WH_A_BYTES, 0, w0 - 1, h0 - 1, n);
+                if (++stage == WH_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = idesc_bf16(WG_BM, 64, 1, 1);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int i = 0; i < nkb; ++i) {
+                mbar_wait(&sh->full[stage], phase);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + stage * WH_STAGE_BYTES);
+                const uint32_t halo = sa + WH_A_BYTES;
+                for (int t = 0; t < ntaps; ++t) {
+                    const int tap = tap0 + t, dy = tap / 3, dx = tap - dy * 3;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {                 // 16 pixels = output rows 2j, 2j+1 of the tile
+                        const uint64_t da = smem_desc_sw128(sa + j * 2048, 16384, 1024);
+                        const uint64_t db = smem_desc_sw128(halo + ((2 * j + dy) * 16 + dx) * 128, 16384, 2048);
+                        umma_bf16(tmem_acc + t * 64, da, db, idesc, (i > 0 || j > 0) ? 1u : 0u);
+                    }
+                }
+                umma_commit(&sh->empty[stage]);
+                if (++stage == WH_STAGES) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(&sh->tmem_full);
+        }
+    } else if (nkb > 0) {
+        const int lane_base = (warp & 3) * 32;
+        const int co = co_tile * WG_BM + lane_base + lane;
+        mbar_wait(&sh->tmem_full, 0);
+        tc_fence_after();
+        for (int t = 0; t < ntaps; ++t) {
+#pragma unroll
+            for (int c0 = 0; c0 < 64; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_acc + ((uint32_t)lane_base << 16) + t * 64 + c0, v);
+                if (co < p.Cout) {
+                    float* dst = p.dW + ((size_t)co * 9 + tap0 + t) * p.Cin_valid + c0;
+                    if ((p.Cin_valid & 3) == 0) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            if (c0 + j < p.Cin_valid)
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(v[j])),
+                                             "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                                             : "memory");
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (c0 + j < p.Cin_valid) atomicAdd(dst + j, __uint_as_float(v[j]));
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_acc, 512);
+}
+
+// dW[Cout][9][Cin_valid] += wgrad3x3(dy[NB][H][W][Cout], x[NB][H][W][64]); stride 1, pad 1, H % 16 == 0, W % 8 == 0
+cudaError_t launch_conv_wgrad_halo_bf16(const void* dy, const void* x, float* dW, int NB, int H, int W, int Cin_valid, int Cout,
+                                        int num_sms, cudaStream_t st) {
+    if (H % 16 || W % 8 || Cout % 8 || !((Cout <= 64) || Cout % 128 == 0)) return cudaErrorInvalidValue;
+    static bool configured = false;
+    if (!configured) {
+        RLR_CUDA_CHECK(cudaFuncSetAttribute(umma_wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WH_SMEM));
+        configured = true;
+    }
+    WgHaloParams p{};
+    p.NB = NB; p.H = H; p.W = W; p.tiles_h = H / 16; p.tiles_w = W / 8; p.num_kb = NB * p.tiles_h * p.tiles_w;
+    p.a_groups = (Cout % 128 == 0) ? 2 : 1; p.Cout = Cout; p.Cin_valid = Cin_valid; p.dW = dW;
+    const int co_tiles = (Cout + WG_BM - 1) / WG_BM;
+    const int base = co_tiles * 2;
+    int waves = base >= num_sms ? (base + num_sms - 1) / num_sms : 1;
+    int splits = (waves * num_sms) / base;
+    if (splits > p.num_kb) splits = p.num_kb;
+    if (splits < 1) splits = 1;
+    p.kb_per_cta = (p.num_kb + splits - 1) / splits;
+    splits = (p.num_kb + p.kb_per_cta - 1) / p.kb_per_cta;
+    CUtensorMap tmA, tmB;
+    {
+        const uint64_t d[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)NB};
+        const uint64_t s[3] = {(uint64_t)Cout * 2, (uint64_t)W * Cout * 2, (uint64_t)H * W * Cout * 2};
+        const uint32_t b[4] = {64, 8, 16, 1};
+        RLR_CUDA_CHECK(make_tmap_bf16(&tmA, dy, 4, d, s, b));
+    }
+    {
+        const uint64_t d[4] = {64, (uint64_t)W, (uint64_t)H, (uint64_t)NB};
+        const uint64_t s[3] = {128, (uint64_t)W * 128, (uint64_t)H * W * 128};
+        const uint32_t b[4] = {64, 16, 18, 1};
+        RLR_CUDA_CHECK(make_tmap_bf16(&tmB, x, 4, d, s, b));
+    }
+    umma_wgrad_halo_kernel<<<dim3(co_tiles, 2, splits), WG_THREADS, WH_SMEM, st>>>(tmA, tmB, p);
+    return cudaGetLastError();
+}
+
 static int pow2_ceil_(int x) { int q = 1; while (q < x) q <<= 1; return q; }
 
 // dW[Cout][T][Cin_valid] += wgrad(dy[NB][Ho][Wo][Cout], x[planes*NB][Hin][Win][Cin])   (Cin multiple of 64)

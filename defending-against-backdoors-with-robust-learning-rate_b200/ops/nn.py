@@ -7,6 +7,8 @@ import torch
 import torch.nn.functional as F
 
 _scratch = {}
+STAT_SLOTS = 16         # conv epilogues spread their BatchNorm statistics over this many partial buffers (gemm.h kStatSlots)
+USE_WGRAD_HALO = True   # 3x3/s1/p1, 64 input channels: halo-reuse weight-gradient kernel (wgrad.cu)
 
 
 def _ext():
@@ -42,6 +44,10 @@ def conv_supported(in_shape, a, kind):
     return False
 
 
+def _halo_ok(k, stride, pad, cin, h, w):
+    return k == 3 and stride == 1 and pad == 1 and cin == 64 and h % 16 == 0 and w % 8 == 0
+
+
 def _taps(k, stride, pad):
     dh, dw, pl = [], [], []
     for dy in range(k):
@@ -55,7 +61,8 @@ def _taps(k, stride, pad):
 
 
 def conv2d_fwd_sm100(x, w, bias, y, stride, pad, relu, stats, tag="fwd", zero_stats=True):
-    """y[B,Ho,Wo,Cout] = conv(x[B,H,W,Cin], w[Cout,k,k,Cin]) (+bias)(ReLU); ``stats`` [2,Cout] gets per-channel sum / sum^2."""
+    """y[B,Ho,Wo,Cout] = conv(x[B,H,W,Cin], w[Cout,k,k,Cin]) (+bias)(ReLU); ``stats`` [STAT_SLOTS,2,Cout] accumulates per-channel
+    sum / sum^2 partials (sum over dim 0 for the totals)."""
     e = _ext()
     B, H, W, Cin = x.shape
     Cout, k = w.shape[0], w.shape[1]
@@ -66,6 +73,12 @@ def conv2d_fwd_sm100(x, w, bias, y, stride, pad, relu, stats, tag="fwd", zero_st
         wp = scratch(("wpad", tag, w.data_ptr()), (Cout, k, k, cp), w.dtype, w.device)
         wp[..., :Cin].copy_(w)
         x, w, Cin = xp, wp, cp
+    if _halo_ok(k, stride, pad, Cin, H, W):
+        # persistent halo-reuse kernel (conv_halo.cu): 36 KB of L2 traffic per 128-pixel tile instead of 216 KB
+        if stats is not None and zero_stats:
+            stats.zero_()
+        e.conv3x3_halo_bf16(x, w.reshape(Cout, 9 * 64), y, bias, bool(relu), False, stats, 0)
+        return y
     planes = 1
     if stride == 2:
         x4 = scratch(("s2d", tag), (4 * B, H // 2, W // 2, Cin), x.dtype, x.device)
@@ -88,6 +101,9 @@ def conv2d_dgrad_sm100(dy, w, dx, stride, pad, accumulate):
         return _conv2d_dgrad_s2(e, dy, w, dx, pad, accumulate)
     wt = scratch(("wt", w.data_ptr()), (Cin, k * k * Cout), w.dtype, w.device)
     e.filter_transpose(w, wt, Cout, k * k, Cin)
+    if _halo_ok(k, 1, k - 1 - pad, Cout, dy.shape[1], dy.shape[2]) and dx.shape[1:3] == dy.shape[1:3]:
+        e.conv3x3_halo_bf16(dy, wt, dx, None, False, bool(accumulate), None, 0)
+        return dx
     dh, dw, pl = _taps(k, 1, k - 1 - pad)
     e.conv_bf16(dy, wt, dx, B, 1, dh, dw, pl, None, False, bool(accumulate), None)
     return dx
@@ -138,7 +154,10 @@ def conv2d_wgrad_sm100(x, dy, gw, gb, stride, pad, tag="fwd", zero=True):
     dh, dw, pl = _taps(k, stride, pad)
     if zero:
         gw.zero_()
-    e.conv_wgrad_bf16(dy, x, gw, B, planes, cin_valid, dh, dw, pl)
+    if USE_WGRAD_HALO and _halo_ok(k, stride, pad, Cin, H, W) and (Cout <= 64 or Cout % 128 == 0):
+        e.conv_wgrad_halo_bf16(dy, x, gw, cin_valid)
+    else:
+        e.conv_wgrad_bf16(dy, x, gw, B, planes, cin_valid, dh, dw, pl)
     if gb is not None:
         st = scratch(("dbias", tag), (2, Cout), torch.float32, dy.device)
         st.zero_()
@@ -154,7 +173,7 @@ def bn_fwd(x, y, res, gamma, beta, rm, rv, stats, mean_rstd, count, eps, momentu
     if impl == "sm100":
         e = _ext()
         if train and stats is None:
-            stats = scratch(("bnstats", mean_rstd.data_ptr()), (2, C), torch.float32, x.device)
+            stats = scratch(("bnstats", mean_rstd.data_ptr()), (1, 2, C), torch.float32, x.device)
             stats.zero_()
             e.channel_stats(x, stats)
         e.bn_finalize(stats if stats is not None else mean_rstd, mean_rstd, rm, rv, float(count), float(eps), float(momentum), bool(train))
@@ -163,8 +182,9 @@ def bn_fwd(x, y, res, gamma, beta, rm, rv, stats, mean_rstd, count, eps, momentu
     xf = x.float().reshape(-1, C)
     if train:
         if stats is not None:
-            mean = stats[0] / count
-            var = (stats[1] / count - mean * mean).clamp_min(0)
+            tot = stats.reshape(-1, 2, C).sum(0)
+            mean = tot[0] / count
+            var = (tot[1] / count - mean * mean).clamp_min(0)
         else:
             mean = xf.mean(0)
             var = xf.var(0, unbiased=False)

@@ -16,7 +16,7 @@ def conv_case(B, H, C, Cout, tag):
     x = torch.randn(B, H, H, C, device=DEV).to(BF)
     w = (torch.randn(Cout, 3, 3, C, device=DEV) * 0.05).to(BF)
     y = torch.empty(B, H, H, Cout, device=DEV, dtype=BF)
-    stats = torch.zeros(2, Cout, device=DEV)
+    stats = torch.zeros(ops.STAT_SLOTS, 2, Cout, device=DEV)
     dy = torch.randn(B, H, H, Cout, device=DEV).to(BF)
     gw = torch.zeros(Cout, 3, 3, C, device=DEV)
     dx = torch.empty_like(x)

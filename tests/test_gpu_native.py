@@ -25,8 +25,9 @@ def test_gemm_bf16(M, N, K):
     Bm = (torch.randn(N, K, device=DEV) * 0.5).to(BF)
     bias = torch.randn(N, device=DEV)
     out = torch.empty(M, N, device=DEV, dtype=BF)
-    stats = torch.zeros(2, N, device=DEV)
-    ops.ext().gemm_bf16(A, Bm, out, bias, True, False, stats)
+    stats_slots = torch.zeros(ops.STAT_SLOTS, 2, N, device=DEV)
+    ops.ext().gemm_bf16(A, Bm, out, bias, True, False, stats_slots)
+    stats = stats_slots.sum(0)
     ref = F.relu(A.float() @ Bm.float().t() + bias)
     assert _rel(out, ref) < 1e-2
     torch.testing.assert_close(stats[0], out.float().sum(0), rtol=2e-3, atol=2e-2 * M ** 0.5)
@@ -54,8 +55,9 @@ def test_conv_fwd(B, H, W, Cin, Cout, k, s, p):
     Ho, Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
     assert ops.conv_supported((H, W, Cin), dict(k=k, stride=s, pad=p, cout=Cout), "fwd")
     y = torch.full((B, Ho, Wo, Cout), 7.0, device=DEV, dtype=BF)
-    stats = torch.zeros(2, Cout, device=DEV)
-    ops.conv2d_fwd_sm100(x, w, bias, y, s, p, True, stats, tag=("t", B, H, Cin, k, s))
+    stats_slots = torch.zeros(ops.STAT_SLOTS, 2, Cout, device=DEV)
+    ops.conv2d_fwd_sm100(x, w, bias, y, s, p, True, stats_slots, tag=("t", B, H, Cin, k, s))
+    stats = stats_slots.sum(0)
     ref = F.relu(F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), bias, s, p)).permute(0, 2, 3, 1)
     assert _rel(y, ref) < 1e-2
     torch.testing.assert_close(stats[0], y.float().sum((0, 1, 2)), rtol=2e-3, atol=0.5)
@@ -269,14 +271,15 @@ def test_conv3x3_halo_kernel(B, H, W, Cout, acc):
     if acc:
         ref = ref + base.float()
     errs = {}
-    for bo in (1, 0):
+    for bo in (0, 1):
         y = base.clone() if acc else torch.full_like(base, 5.0)
-        stats = torch.zeros(2, Cout, device=DEV)
+        stats = torch.zeros(ops.STAT_SLOTS, 2, Cout, device=DEV)
         ops.ext().conv3x3_halo_bf16(x, w.reshape(Cout, 576), y, bias, True, acc, stats, bo)
         torch.cuda.synchronize()
         errs[bo] = _rel(y, ref)
-        if bo == 1:
-            s_ok = acc or torch.allclose(stats[0], y.float().sum((0, 1, 2)), rtol=2e-3, atol=0.5)
+        if bo == 0:
+            s_ok = acc or torch.allclose(stats.sum(0)[0], y.float().sum((0, 1, 2)), rtol=2e-3, atol=0.5)
+    # bo=0 (base-offset field zero) is the mode that is correct on B200: the swizzle follows absolute smem address bits
     print("halo conv rel err by base-offset mode:", errs)
-    assert errs[1] < 1e-2, errs
+    assert errs[0] < 1e-2, errs
     assert s_ok
