@@ -56,6 +56,7 @@ class NativeNet:
         self.impl = dict(conv_fwd=default, conv_dgrad=default, conv_wgrad=default, bn=default, pool=default,
                          linear=default, dropout=default) if not isinstance(impl, dict) else dict(impl)
         self.seed = seed
+        self.fuse_bn_stats = False
         self.step_counter = torch.zeros(1, dtype=torch.int64, device=device)  # Philox offset for dropout
         self._build_plan()
         self._alloc()
@@ -274,7 +275,9 @@ class NativeNet:
         a = op.attrs
         x, y = self.T(op.x, B), self.T(op.y, B)
         bias = self.pw.get(op.name + ".bias")
-        stats = op.saved.get("stats") if (train and op.saved.get("want_stats")) else None
+        # BatchNorm statistics: fused into the conv epilogue (FUSE_BN_STATS) or taken by one streaming pass over the conv output
+        # while it is still L2-resident (default: measured cheaper than the in-epilogue reduction, profiles/r1c notes)
+        stats = op.saved.get("stats") if (train and op.saved.get("want_stats") and self.fuse_bn_stats) else None
         if self.impl["conv_fwd"] == "sm100" and ops.conv_supported(op.in_shape, a, "fwd"):
             ops.conv2d_fwd_sm100(x, self.pwb[op.name + ".weight"], bias, y, a.get("stride", 1), a.get("pad", 0), op.relu, stats, tag=(id(self), op.name), zero_stats=False)
             return
@@ -327,10 +330,11 @@ class NativeNet:
         gamma, beta = self.pw[op.name + ".weight"], self.pw[op.name + ".bias"]
         rm, rv = self.pw[op.name + ".running_mean"], self.pw[op.name + ".running_var"]
         prod = op.saved["producer"]
-        stats = prod.saved["stats"] if (prod is not None and prod.saved.get("want_stats")) else None
+        stats = prod.saved["stats"] if (prod is not None and prod.saved.get("want_stats") and self.fuse_bn_stats) else None
         count = x.numel() // x.shape[-1]
         ops.bn_fwd(x, y, res, gamma, beta, rm, rv, stats, op.saved["mean_rstd"], count, a.get("eps", 1e-5),
-                   a.get("momentum", 0.1), train, op.relu, self.impl["bn"])
+                   a.get("momentum", 0.1), train, op.relu, self.impl["bn"],
+                   stats_buf=op.saved["stats"][0:1] if train else None)   # slot 0 of the (pre-zeroed) statistics arena
 
     def _bwd_bn(self, op, B):
         x, y, dy = self.T(op.x, B), self.T(op.y, B), self.G(op.y, B)

@@ -35,6 +35,23 @@ __device__ __forceinline__ int warp_sum(int v) {
     return v;
 }
 
+// Column sums of a 32(lanes) x 32(values) tile held one row per lane: after the call lane l returns sum_over_lanes v[l].
+// Butterfly that halves the live values per stage: 31 shuffles instead of 32 x 5.
+__device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane) {
+#define RLR_TSTAGE(O, N)                                                         \
+    {                                                                            \
+        const bool up = (lane & (O)) != 0;                                       \
+        _Pragma("unroll") for (int i = 0; i < (N); ++i) {                        \
+            const float send = up ? v[i] : v[i + (N)];                           \
+            const float keep = up ? v[i + (N)] : v[i];                           \
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, (O));               \
+        }                                                                        \
+    }
+    RLR_TSTAGE(16, 16) RLR_TSTAGE(8, 8) RLR_TSTAGE(4, 4) RLR_TSTAGE(2, 2) RLR_TSTAGE(1, 1)
+#undef RLR_TSTAGE
+    return v[0];
+}
+
 // Block-wide sum; result valid in thread 0. `scratch` must hold >= 32 elements.
 template <typename T>
 __device__ __forceinline__ T block_sum(T v, T* scratch) {

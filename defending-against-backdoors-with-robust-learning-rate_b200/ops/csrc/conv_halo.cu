@@ -46,6 +46,7 @@ struct HaloParams {
     const float* bias;
     float* stats;
     int relu, accumulate;
+    long long* dbg;               // optional per-tile clock64 timeline of CTA 0 (tuning aid): [tile][8]
     int bo_mode;                  // 0 (correct on B200): base-offset field 0;  1: (addr >> 7) & 7 -- kept for the experiment
 };
 
@@ -64,6 +65,7 @@ __device__ __forceinline__ uint64_t desc_sw128_bo(uint32_t saddr, uint32_t sbo_b
            (1ull << 46) | ((uint64_t)(base_offset & 7u) << 49) | (2ull << 61);
 }
 
+template <bool kStats, bool kAcc>
 __global__ void __launch_bounds__(HL_THREADS, 1)
 umma_conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const HaloParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -114,8 +116,13 @@ umma_conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
             uint32_t phase = 0, acc_phase = 0;
             const uint32_t w_base = smem_u32(s_w);
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const bool trace = p.dbg && blockIdx.x == 0 && blockIdx.y == 0;
+                const int tix = (tile - blockIdx.x) / gridDim.x;
+                if (trace) p.dbg[tix * 8 + 0] = clock64();
                 mbar_wait(&sh->acc_empty[acc], acc_phase ^ 1);       // epilogue has drained this accumulator
+                if (trace) p.dbg[tix * 8 + 1] = clock64();
                 mbar_wait(&sh->halo_full[stage], phase);
+                if (trace) p.dbg[tix * 8 + 2] = clock64();
                 tc_fence_after();
                 const uint32_t halo = smem_u32(s_halo + stage * HL_HALO_BYTES);
                 const uint32_t d_tmem = tmem_acc + acc * 64;
@@ -133,6 +140,7 @@ umma_conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
                 }
                 umma_commit(&sh->halo_empty[stage]);
                 umma_commit(&sh->acc_full[acc]);
+                if (trace) p.dbg[tix * 8 + 3] = clock64();
                 if (++stage == HL_STAGES) { stage = 0; phase ^= 1; }
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
@@ -148,13 +156,13 @@ umma_conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
         __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
         int acc = 0;
         uint32_t acc_phase = 0;
-        if (p.stats) red[et] = 0.f;                                 // per-CTA statistics, flushed once at the end
+        if (kStats) red[et] = 0.f;                                 // per-CTA statistics, flushed once at the end
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             const int n = tile / tiles_per_img, r = tile - n * tiles_per_img;
             const int h0 = (r / p.tiles_w) * HL_TH, w0 = (r % p.tiles_w) * HL_TW;
             // residual-accumulate operand: issue all loads BEFORE waiting for the accumulator so their latency overlaps the MMAs
             uint4 oldv[8];
-            if (p.accumulate) {
+            if (kAcc) {
 #pragma unroll
                 for (int it = 0; it < 8; ++it) {
                     const int idx = et + it * 128, rr = idx >> 3, ch = idx & 7;
@@ -164,26 +172,41 @@ umma_conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
                         oldv[it] = *reinterpret_cast<const uint4*>(out + (((size_t)n * p.H + h) * p.W + w) * p.ldc + col0 + ch * 8);
                 }
             }
+            const bool trace = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && et == 0;
+            const int tix = (tile - blockIdx.x) / gridDim.x;
+            if (trace) p.dbg[tix * 8 + 4] = clock64();
             mbar_wait(&sh->acc_full[acc], acc_phase);
+            if (trace) p.dbg[tix * 8 + 5] = clock64();
             tc_fence_after();
 #pragma unroll
             for (int c0 = 0; c0 < 64; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld_32x32(tmem_acc + ((uint32_t)lane_base << 16) + acc * 64 + c0, v);
                 uint32_t packed[16];
+                float f1[32], f2[32];
 #pragma unroll
                 for (int j = 0; j < 32; j += 2) {
                     float a = __uint_as_float(v[j]), b = __uint_as_float(v[j + 1]);
                     if (p.bias && col0 + c0 + j < p.N) { a += p.bias[col0 + c0 + j]; b += p.bias[col0 + c0 + j + 1]; }
                     if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
                     packed[j >> 1] = pack_bf16x2(a, b);
+                    if (kStats) {   // statistics of the bf16-rounded values that BatchNorm will read back
+                        const float2 rq = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&packed[j >> 1]));
+                        f1[j] = rq.x; f1[j + 1] = rq.y; f2[j] = rq.x * rq.x; f2[j + 1] = rq.y * rq.y;
+                    }
                 }
                 uint4* dst = reinterpret_cast<uint4*>(s_stage + row * HL_PITCH_OUT + c0 * 2);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) dst[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+                if (kStats) {   // every tile row is a valid pixel (H % 16 == 0, W % 8 == 0): warp-level column sums
+                    const float c1 = warp_transpose_sum32(f1, lane), c2 = warp_transpose_sum32(f2, lane);
+                    atomicAdd(&red[c0 + lane], c1);
+                    atomicAdd(&red[64 + c0 + lane], c2);
+                }
             }
             tc_fence_before();
             mbar_arrive(&sh->acc_empty[acc]);                        // 128 arrivals release the accumulator to the MMA warp
+            if (trace) p.dbg[tix * 8 + 6] = clock64();
             asm volatile("bar.sync 1, 128;" ::: "memory");
             // coalesced stores: tile row rr = g*8 + px  ->  image pixel (h0+g, w0+px)
 #pragma unroll
@@ -196,7 +219,7 @@ umma_conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
                 const size_t gi = ((size_t)n * p.H + h) * p.W + w;
                 uint4 val = *reinterpret_cast<const uint4*>(s_stage + rr * HL_PITCH_OUT + ch * 16);
                 uint4* gp = reinterpret_cast<uint4*>(out + gi * p.ldc + col0 + ch * 8);
-                if (p.accumulate) {
+                if (kAcc) {
                     const __nv_bfloat162* o2 = reinterpret_cast<const __nv_bfloat162*>(&oldv[it]);
                     __nv_bfloat162* v2 = reinterpret_cast<__nv_bfloat162*>(&val);
 #pragma unroll
@@ -207,25 +230,14 @@ umma_conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
                 }
                 *gp = val;
             }
-            if (p.stats) {
-                const int cp = et & 31, sl = et >> 5;               // 32 column pairs x 4 row slices of 32 rows
-                float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
-#pragma unroll 4
-                for (int rr = sl * 32; rr < sl * 32 + 32; ++rr) {
-                    if (h0 + (rr >> 3) >= p.H || w0 + (rr & 7) >= p.W) continue;
-                    const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(s_stage + rr * HL_PITCH_OUT + cp * 4));
-                    s1a += x.x; s1b += x.y; s2a += x.x * x.x; s2b += x.y * x.y;
-                }
-                atomicAdd(&red[2 * cp], s1a); atomicAdd(&red[2 * cp + 1], s1b);
-                atomicAdd(&red[64 + 2 * cp], s2a); atomicAdd(&red[64 + 2 * cp + 1], s2b);
-            }
             asm volatile("bar.sync 1, 128;" ::: "memory");           // staging may be overwritten by the next tile
+            if (trace) p.dbg[tix * 8 + 7] = clock64();
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
         // one global reduction per CTA and channel (instead of per tile), spread over kStatSlots slots to cut same-address
         // contention in L2; bn_finalize sums the slots
-        if (p.stats && col0 + (et & 63) < p.N)
+        if (kStats && col0 + (et & 63) < p.N)
             atomicAdd(p.stats + (size_t)(blockIdx.x % kStatSlots) * 2 * p.N + (et < 64 ? 0 : p.N) + col0 + (et & 63), red[et]);
     }
     tc_fence_before();
@@ -235,16 +247,19 @@ umma_conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
 
 // y[NB][H][W][Cout] = conv3x3(x[NB][H][W][64], w[Cout][9*64]), stride 1, pad 1; H % 16 == 0 and W % 8 == 0.
 cudaError_t launch_conv3x3_halo_bf16(const void* x, const void* w, void* out, int NB, int H, int W, int Cout, const float* bias, int relu,
-                                     int accumulate, float* stats, int bo_mode, int num_sms, cudaStream_t st) {
+                                     int accumulate, float* stats, int bo_mode, long long* dbg, int num_sms, cudaStream_t st) {
     if (H % HL_TH || W % HL_TW || Cout % 8) return cudaErrorInvalidValue;
     static bool configured = false;
     if (!configured) {
-        RLR_CUDA_CHECK(cudaFuncSetAttribute(umma_conv3x3_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HL_SMEM));
+        RLR_CUDA_CHECK(cudaFuncSetAttribute(umma_conv3x3_halo_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, HL_SMEM));
+        RLR_CUDA_CHECK(cudaFuncSetAttribute(umma_conv3x3_halo_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, HL_SMEM));
+        RLR_CUDA_CHECK(cudaFuncSetAttribute(umma_conv3x3_halo_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HL_SMEM));
         configured = true;
     }
+    if (stats && accumulate) return cudaErrorInvalidValue;
     HaloParams p{};
     p.NB = NB; p.H = H; p.W = W; p.tiles_h = H / HL_TH; p.tiles_w = W / HL_TW; p.num_tiles = NB * p.tiles_h * p.tiles_w;
-    p.N = Cout; p.out = out; p.ldc = Cout; p.bias = bias; p.stats = stats; p.relu = relu; p.accumulate = accumulate; p.bo_mode = bo_mode;
+    p.N = Cout; p.out = out; p.ldc = Cout; p.bias = bias; p.stats = stats; p.relu = relu; p.accumulate = accumulate; p.bo_mode = bo_mode; p.dbg = dbg;
     CUtensorMap tmX, tmW;
     {
         const uint64_t d[4] = {64, (uint64_t)W, (uint64_t)H, (uint64_t)NB};
@@ -261,7 +276,10 @@ cudaError_t launch_conv3x3_halo_bf16(const void* x, const void* w, void* out, in
     int gx = num_sms / n_tiles_n;
     if (gx > p.num_tiles) gx = p.num_tiles;
     if (gx < 1) gx = 1;
-    umma_conv3x3_halo_kernel<<<dim3(gx, n_tiles_n), HL_THREADS, HL_SMEM, st>>>(tmX, tmW, p);
+    const dim3 grid(gx, n_tiles_n);
+    if (stats) umma_conv3x3_halo_kernel<true, false><<<grid, HL_THREADS, HL_SMEM, st>>>(tmX, tmW, p);
+    else if (accumulate) umma_conv3x3_halo_kernel<false, true><<<grid, HL_THREADS, HL_SMEM, st>>>(tmX, tmW, p);
+    else umma_conv3x3_halo_kernel<false, false><<<grid, HL_THREADS, HL_SMEM, st>>>(tmX, tmW, p);
     return cudaGetLastError();
 }
 

@@ -53,7 +53,7 @@ struct __align__(8) SharedTail {
     int row_index[BM];   // global output row of each tile row, -1 = masked
 };
 
-template <int BN>
+template <int BN, bool kStats>
 __global__ void __launch_bounds__(kThreads, 2)
 umma_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvGemmParams p) {
     using Cfg = TileCfg<BN>;
@@ -152,21 +152,38 @@ umma_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         tc_fence_after();
         uint8_t* staging = smem;                         // operand ring is idle now: reuse it
         const int col0 = tile_n * BN;
+        float* red = reinterpret_cast<float*>(staging + Cfg::kStagingBytes);   // [2][BN] per-tile column sums
+        const bool row_ok = tail->row_index[row] >= 0;
+        if (kStats) {
+            for (int i = et; i < 2 * BN; i += kEpiThreads) red[i] = 0.f;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
 #pragma unroll
         for (int c0 = 0; c0 < BN; c0 += 32) {
             uint32_t v[32];
             tmem_ld_32x32(tmem_acc + ((uint32_t)lane_base << 16) + c0, v);
             uint32_t packed[16];
+            float f1[32], f2[32];
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
                 float a = __uint_as_float(v[j]), b = __uint_as_float(v[j + 1]);
                 if (p.bias && col0 + c0 + j < p.N) { a += p.bias[col0 + c0 + j]; b += p.bias[col0 + c0 + j + 1]; }
                 if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
                 packed[j >> 1] = pack_bf16x2(a, b);
+                if (kStats) {   // statistics of the bf16-rounded values BatchNorm will read back; masked rows count as zero
+                    const float2 rq = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&packed[j >> 1]));
+                    f1[j] = row_ok ? rq.x : 0.f; f1[j + 1] = row_ok ? rq.y : 0.f;
+                    f2[j] = f1[j] * f1[j]; f2[j + 1] = f1[j + 1] * f1[j + 1];
+                }
             }
             uint4* dst = reinterpret_cast<uint4*>(staging + row * Cfg::kPitch + c0 * 2);
 #pragma unroll
             for (int q = 0; q < 4; ++q) dst[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+            if (kStats) {   // warp-level column sums (31 shuffles each), 4 warps meet in shared memory
+                const float c1 = warp_transpose_sum32(f1, lane), c2 = warp_transpose_sum32(f2, lane);
+                atomicAdd(&red[c0 + lane], c1);
+                atomicAdd(&red[BN + c0 + lane], c2);
+            }
         }
         tc_fence_before();
         asm volatile("bar.sync 1, 128;" ::: "memory");   // epilogue-only named barrier: staging tile complete
@@ -204,27 +221,9 @@ umma_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 *reinterpret_cast<uint4*>(out + (size_t)gi * p.ldc + col0 + ch * 8) = val;
             }
         }
-        // ---- per-channel statistics of the (bf16-rounded) output tile: sum and sum of squares -> BatchNorm ----
-        // 128 threads = (BN/2 column pairs) x (256/BN row slices); partials meet in shared memory, one global atomic
-        // per column and statistic per tile.
-        if (p.stats) {
-            float* red = reinterpret_cast<float*>(staging + Cfg::kStagingBytes);   // [2][BN], behind the staging tile
-            for (int i = et; i < 2 * BN; i += kEpiThreads) red[i] = 0.f;
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            constexpr int kPairs = BN / 2, kSlices = kEpiThreads / kPairs, kRows = BM / kSlices;
-            const int cp = et % kPairs, sl = et / kPairs;
-            float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
-            const uint8_t* colp = staging + cp * 4;
-#pragma unroll 4
-            for (int r = sl * kRows; r < (sl + 1) * kRows; ++r) {
-                if (tail->row_index[r] < 0) continue;
-                const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(colp + r * Cfg::kPitch);
-                const float2 x = __bfloat1622float2(h);
-                s1a += x.x; s1b += x.y; s2a += x.x * x.x; s2b += x.y * x.y;
-            }
-            atomicAdd(&red[2 * cp], s1a); atomicAdd(&red[2 * cp + 1], s1b);
-            atomicAdd(&red[BN + 2 * cp], s2a); atomicAdd(&red[BN + 2 * cp + 1], s2b);
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+        // ---- per-channel statistics: one global reduction per column and tile, spread over kStatSlots partial buffers ----
+        if (kStats) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");   // (also orders the smem atomics above; the bar before the stores did too)
             for (int i = et; i < 2 * BN; i += kEpiThreads)
                 if (col0 + (i % BN) < p.N)
                     atomicAdd(p.stats + (size_t)(blockIdx.x % kStatSlots) * 2 * p.N + (i < BN ? 0 : p.N) + col0 + (i % BN), red[i]);
@@ -274,11 +273,13 @@ static cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, con
     using Cfg = TileCfg<BN>;
     static bool configured = false;
     if (!configured) {
-        RLR_CUDA_CHECK(cudaFuncSetAttribute(umma_conv_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        RLR_CUDA_CHECK(cudaFuncSetAttribute(umma_conv_gemm_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        RLR_CUDA_CHECK(cudaFuncSetAttribute(umma_conv_gemm_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         configured = true;
     }
     dim3 grid(m_tiles, (p.N + BN - 1) / BN);
-    umma_conv_gemm_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
+    if (p.stats) umma_conv_gemm_kernel<BN, true><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
+    else umma_conv_gemm_kernel<BN, false><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
     return cudaGetLastError();
 }
 

@@ -36,7 +36,7 @@ cudaError_t launch_conv_bf16(const void* x, const void* w, void* out, int NB, in
 
 // ---- conv_halo.cu: persistent 3x3/s1/p1 conv for 64 input channels with smem halo reuse + resident filter ------------------
 cudaError_t launch_conv3x3_halo_bf16(const void* x, const void* w, void* out, int NB, int H, int W, int Cout, const float* bias, int relu,
-                                     int accumulate, float* stats, int bo_mode, int num_sms, cudaStream_t st);
+                                     int accumulate, float* stats, int bo_mode, long long* dbg, int num_sms, cudaStream_t st);
 
 // ---- wgrad.cu: MN-major tcgen05 weight gradients (fp32, accumulated with red.add) -----------------------------------
 cudaError_t launch_conv_wgrad_bf16(const void* dy, const void* x, float* dW, int NB, int planes, int Hin, int Win, int Cin, int Cin_valid,

@@ -129,12 +129,24 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 tc_fence_after();
                 const uint32_t sa = smem_u32(smem + stage * WG_STAGE_BYTES);
                 const uint32_t sb = sa + WG_A_BYTES;
-                for (int t = 0; t < p.ntaps_cta; ++t) {
+                if (BNW == 64 && p.ntaps_cta == 3) {
+                    // the three tap tiles are 64-channel groups 8 KB apart: one N = 192 MMA (LBO = 8192) covers all of them,
+                    // which lifts the instruction out of the smem-bandwidth-bound N = 64 regime
+                    constexpr uint32_t idesc3 = idesc_bf16(WG_BM, 192, 1, 1);
 #pragma unroll
-                    for (int k = 0; k < WG_BK / 16; ++k) {   // 16 pixel rows (2 swizzle atoms) per MMA
+                    for (int k = 0; k < WG_BK / 16; ++k) {
                         const uint64_t da = smem_desc_sw128(sa + k * 2048, 8192, 1024);
-                        const uint64_t db = smem_desc_sw128(sb + t * WG_B_BYTES + k * 2048, 8192, 1024);
-                        umma_bf16(tmem_acc + t * WG_BN, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                        const uint64_t db = smem_desc_sw128(sb + k * 2048, 8192, 1024);
+                        umma_bf16(tmem_acc, da, db, idesc3, (i > 0 || k > 0) ? 1u : 0u);
+                    }
+                } else {
+                    for (int t = 0; t < p.ntaps_cta; ++t) {
+#pragma unroll
+                        for (int k = 0; k < WG_BK / 16; ++k) {   // 16 pixel rows (2 swizzle atoms) per MMA
+                            const uint64_t da = smem_desc_sw128(sa + k * 2048, 8192, 1024);
+                            const uint64_t db = smem_desc_sw128(sb + t * WG_B_BYTES + k * 2048, 8192, 1024);
+                            umma_bf16(tmem_acc + t * WG_BN, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                        }
                     }
                 }
                 umma_commit(&sh->empty[stage]);
@@ -203,8 +215,10 @@ static cudaError_t launch_wg(const CUtensorMap& tmA, const CUtensorMap& tmB, Wgr
 // are loaded once and serve every filter tap: the B operand of tap (dy,dx) and MMA k-step j (16 pixels = image rows 2j,2j+1)
 // is the MN-major view starting at halo + ((2j+dy)*16 + dx)*128 B with an 8-row group stride (SBO) of 2048 B -- the tensor
 // core applies the 128-byte swizzle on absolute smem address bits, so unaligned starts need no special handling
-// (see conv_halo.cu).  The 9 taps do not fit TMEM at once (9 x 64 > 512 columns): grid.y = 2 tap groups (5 + 4 taps).
-// L2 traffic per 128 pixels: 2 x (36 + 16..32) KB instead of 3 x 2 x (24 + 8..16) KB.
+// (see conv_halo.cu).  The three dx taps of a filter row are the SAME view shifted by one pixel (128 B), i.e. three
+// 64-channel "N groups" with a leading-dimension byte offset of 128: one N = 192 MMA per k-step computes all three, which
+// moves the instruction out of the smem-bandwidth-bound N = 64 regime.  grid.y = 3 filter rows (3 x 192 columns do not fit
+// TMEM).  L2 traffic per 128 pixels: 3 x (36 + 16..32) KB instead of 3 x 2 x (24 + 8..16) KB.
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int WH_STAGES = 3;
 constexpr int WH_A_BYTES = 2 * 128 * 128;                      // up to two 64-channel groups x 128 pixel rows x 128 B
@@ -227,7 +241,7 @@ umma_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     WgShared* sh = reinterpret_cast<WgShared*>(smem + WH_STAGES * WH_STAGE_BYTES);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int co_tile = blockIdx.x;
-    const int tap0 = blockIdx.y * 5, ntaps = blockIdx.y == 0 ? 5 : 4;
+    const int dy = blockIdx.y, tap0 = dy * 3, ntaps = 3;
     const int kb_begin = blockIdx.z * p.kb_per_cta;
     const int kb_end = min(p.num_kb, kb_begin + p.kb_per_cta);
     const int nkb = kb_end - kb_begin;
@@ -239,7 +253,7 @@ umma_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         mbar_init(&sh->tmem_full, 1);
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc(&sh->tmem_base, 512);
+    if (warp == 2) tmem_alloc(&sh->tmem_base, 256);
     if (p.a_groups == 1) {
         for (int s = 0; s < WH_STAGES; ++s) {
             uint4* z = reinterpret_cast<uint4*>(smem + s * WH_STAGE_BYTES + 16384);
@@ -272,7 +286,7 @@ umma_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = idesc_bf16(WG_BM, 64, 1, 1);
+            constexpr uint32_t idesc = idesc_bf16(WG_BM, 192, 1, 1);
             int stage = 0;
             uint32_t phase = 0;
             for (int i = 0; i < nkb; ++i) {
@@ -280,14 +294,12 @@ umma_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 tc_fence_after();
                 const uint32_t sa = smem_u32(smem + stage * WH_STAGE_BYTES);
                 const uint32_t halo = sa + WH_A_BYTES;
-                for (int t = 0; t < ntaps; ++t) {
-                    const int tap = tap0 + t, dy = tap / 3, dx = tap - dy * 3;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {                 // 16 pixels = output rows 2j, 2j+1 of the tile
-                        const uint64_t da = smem_desc_sw128(sa + j * 2048, 16384, 1024);
-                        const uint64_t db = smem_desc_sw128(halo + ((2 * j + dy) * 16 + dx) * 128, 16384, 2048);
-                        umma_bf16(tmem_acc + t * 64, da, db, idesc, (i > 0 || j > 0) ? 1u : 0u);
-                    }
+                for (int j = 0; j < 8; ++j) {                     // 16 pixels = output rows 2j, 2j+1 of the tile
+                    const uint64_t da = smem_desc_sw128(sa + j * 2048, 16384, 1024);
+                    // N groups 0,1,2 = taps dx = 0,1,2: same halo view shifted by one pixel -> LBO = 128 B; SBO = one image row
+                    const uint64_t db = smem_desc_sw128(halo + ((2 * j + dy) * 16) * 128, 128, 2048);
+                    umma_bf16(tmem_acc, da, db, idesc, (i > 0 || j > 0) ? 1u : 0u);
                 }
                 umma_commit(&sh->empty[stage]);
                 if (++stage == WH_STAGES) { stage = 0; phase ^= 1; }
@@ -324,7 +336,7 @@ umma_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_acc, 512);
+    if (warp == 2) tmem_dealloc(tmem_acc, 256);
 }
 
 // dW[Cout][9][Cin_valid] += wgrad3x3(dy[NB][H][W][Cout], x[NB][H][W][64]); stride 1, pad 1, H % 16 == 0, W % 8 == 0
@@ -340,7 +352,7 @@ cudaError_t launch_conv_wgrad_halo_bf16(const void* dy, const void* x, float* dW
     p.NB = NB; p.H = H; p.W = W; p.tiles_h = H / 16; p.tiles_w = W / 8; p.num_kb = NB * p.tiles_h * p.tiles_w;
     p.a_groups = (Cout % 128 == 0) ? 2 : 1; p.Cout = Cout; p.Cin_valid = Cin_valid; p.dW = dW;
     const int co_tiles = (Cout + WG_BM - 1) / WG_BM;
-    const int base = co_tiles * 2;
+    const int base = co_tiles * 3;
     int waves = base >= num_sms ? (base + num_sms - 1) / num_sms : 1;
     int splits = (waves * num_sms) / base;
     if (splits > p.num_kb) splits = p.num_kb;
@@ -360,7 +372,7 @@ cudaError_t launch_conv_wgrad_halo_bf16(const void* dy, const void* x, float* dW
         const uint32_t b[4] = {64, 16, 18, 1};
         RLR_CUDA_CHECK(make_tmap_bf16(&tmB, x, 4, d, s, b));
     }
-    umma_wgrad_halo_kernel<<<dim3(co_tiles, 2, splits), WG_THREADS, WH_SMEM, st>>>(tmA, tmB, p);
+    umma_wgrad_halo_kernel<<<dim3(co_tiles, 3, splits), WG_THREADS, WH_SMEM, st>>>(tmA, tmB, p);
     return cudaGetLastError();
 }
 

@@ -77,7 +77,7 @@ def conv2d_fwd_sm100(x, w, bias, y, stride, pad, relu, stats, tag="fwd", zero_st
         # persistent halo-reuse kernel (conv_halo.cu): 36 KB of L2 traffic per 128-pixel tile instead of 216 KB
         if stats is not None and zero_stats:
             stats.zero_()
-        e.conv3x3_halo_bf16(x, w.reshape(Cout, 9 * 64), y, bias, bool(relu), False, stats, 0)
+        e.conv3x3_halo_bf16(x, w.reshape(Cout, 9 * 64), y, bias, bool(relu), False, stats, 0, None)
         return y
     planes = 1
     if stride == 2:
@@ -102,7 +102,7 @@ def conv2d_dgrad_sm100(dy, w, dx, stride, pad, accumulate):
     wt = scratch(("wt", w.data_ptr()), (Cin, k * k * Cout), w.dtype, w.device)
     e.filter_transpose(w, wt, Cout, k * k, Cin)
     if _halo_ok(k, 1, k - 1 - pad, Cout, dy.shape[1], dy.shape[2]) and dx.shape[1:3] == dy.shape[1:3]:
-        e.conv3x3_halo_bf16(dy, wt, dx, None, False, bool(accumulate), None, 0)
+        e.conv3x3_halo_bf16(dy, wt, dx, None, False, bool(accumulate), None, 0, None)
         return dx
     dh, dw, pl = _taps(k, 1, k - 1 - pad)
     e.conv_bf16(dy, wt, dx, B, 1, dh, dw, pl, None, False, bool(accumulate), None)
@@ -168,13 +168,18 @@ def conv2d_wgrad_sm100(x, dy, gw, gb, stride, pad, tag="fwd", zero=True):
 # =====================================================================================================================
 # batch norm (+ residual + relu)
 # =====================================================================================================================
-def bn_fwd(x, y, res, gamma, beta, rm, rv, stats, mean_rstd, count, eps, momentum, train, relu, impl):
+def bn_fwd(x, y, res, gamma, beta, rm, rv, stats, mean_rstd, count, eps, momentum, train, relu, impl, stats_buf=None):
+    """``stats``: per-channel sum / sum^2 partials already produced by the conv epilogue, or None -> one streaming pass over
+    ``x`` computes them here (into ``stats_buf`` [1,2,C], assumed zeroed, or a scratch buffer)."""
     C = x.shape[-1]
     if impl == "sm100":
         e = _ext()
         if train and stats is None:
-            stats = scratch(("bnstats", mean_rstd.data_ptr()), (1, 2, C), torch.float32, x.device)
-            stats.zero_()
+            if stats_buf is not None:
+                stats = stats_buf
+            else:
+                stats = scratch(("bnstats", mean_rstd.data_ptr()), (1, 2, C), torch.float32, x.device)
+                stats.zero_()
             e.channel_stats(x, stats)
         e.bn_finalize(stats if stats is not None else mean_rstd, mean_rstd, rm, rv, float(count), float(eps), float(momentum), bool(train))
         e.bn_apply(x, res, y, gamma, beta, mean_rstd, bool(relu))

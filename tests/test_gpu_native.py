@@ -273,8 +273,8 @@ def test_conv3x3_halo_kernel(B, H, W, Cout, acc):
     errs = {}
     for bo in (0, 1):
         y = base.clone() if acc else torch.full_like(base, 5.0)
-        stats = torch.zeros(ops.STAT_SLOTS, 2, Cout, device=DEV)
-        ops.ext().conv3x3_halo_bf16(x, w.reshape(Cout, 576), y, bias, True, acc, stats, bo)
+        stats = None if acc else torch.zeros(ops.STAT_SLOTS, 2, Cout, device=DEV)
+        ops.ext().conv3x3_halo_bf16(x, w.reshape(Cout, 576), y, bias, True, acc, stats, bo, None)
         torch.cuda.synchronize()
         errs[bo] = _rel(y, ref)
         if bo == 0:
