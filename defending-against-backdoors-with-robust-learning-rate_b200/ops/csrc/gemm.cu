@@ -53,7 +53,7 @@ struct __align__(8) SharedTail {
     int row_index[BM];   // global output row of each tile row, -1 = masked
 };
 
-template <int BN, bool kStats>
+template <int BN, bool kStats, bool kBMN>
 __global__ void __launch_bounds__(kThreads, 2)
 umma_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvGemmParams p) {
     using Cfg = TileCfg<BN>;
@@ -117,14 +117,22 @@ umma_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 } else {
                     tma_load_2d(&tmA, &tail->full[stage], sa, kb * BK, tile_m * BM);
                 }
-                tma_load_2d(&tmB, &tail->full[stage], sb, kb * BK, tile_n * BN);
+                if (kBMN) {
+                    // data gradient: B[k = co][n = ci] is a 64 x 64 box of the ORIGINAL filter W[co][tap][ci] (ci contiguous ->
+                    // MN-major operand); one box per 64-wide ci group.  No transposed filter copy is ever materialised.
+                    const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
+                    for (int g = 0; g < BN / 64; ++g)
+                        tma_load_2d(&tmB, &tail->full[stage], sb + g * 8192, p.wtap[tap] * p.wcols + tile_n * BN + g * 64, cb * BK);
+                } else {
+                    tma_load_2d(&tmB, &tail->full[stage], sb, kb * BK, tile_n * BN);
+                }
                 if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
         // ================================ MMA issuer (one thread) ==============================================================
         if (lane == 0) {
-            constexpr uint32_t idesc = idesc_bf16(BM, BN, 0, 0);
+            constexpr uint32_t idesc = idesc_bf16(BM, BN, 0, kBMN ? 1 : 0);
             int stage = 0;
             uint32_t phase = 0;
             for (int kb = 0; kb < p.num_kb; ++kb) {
@@ -135,7 +143,8 @@ umma_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll
                 for (int k = 0; k < BK / 16; ++k) {
                     const uint64_t da = smem_desc_sw128(sa + k * 32, 16, 1024);
-                    const uint64_t db = smem_desc_sw128(sb + k * 32, 16, 1024);
+                    // K-major B: 32-byte k-slices inside the 128-byte rows; MN-major B: 16 k-rows (2 KB) per slice, N groups 8 KB apart
+                    const uint64_t db = kBMN ? smem_desc_sw128(sb + k * 2048, 8192, 1024) : smem_desc_sw128(sb + k * 32, 16, 1024);
                     umma_bf16(tmem_acc, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
                 }
                 umma_commit(&tail->empty[stage]);   // frees this smem stage once the MMAs above have read it
@@ -273,13 +282,15 @@ static cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, con
     using Cfg = TileCfg<BN>;
     static bool configured = false;
     if (!configured) {
-        RLR_CUDA_CHECK(cudaFuncSetAttribute(umma_conv_gemm_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-        RLR_CUDA_CHECK(cudaFuncSetAttribute(umma_conv_gemm_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        RLR_CUDA_CHECK(cudaFuncSetAttribute(umma_conv_gemm_kernel<BN, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        RLR_CUDA_CHECK(cudaFuncSetAttribute(umma_conv_gemm_kernel<BN, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        RLR_CUDA_CHECK(cudaFuncSetAttribute(umma_conv_gemm_kernel<BN, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         configured = true;
     }
     dim3 grid(m_tiles, (p.N + BN - 1) / BN);
-    if (p.stats) umma_conv_gemm_kernel<BN, true><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
-    else umma_conv_gemm_kernel<BN, false><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
+    if (p.b_mn) umma_conv_gemm_kernel<BN, false, true><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
+    else if (p.stats) umma_conv_gemm_kernel<BN, true, false><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
+    else umma_conv_gemm_kernel<BN, false, false><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
     return cudaGetLastError();
 }
 
@@ -314,8 +325,9 @@ static int pow2_ceil(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 // `w` is [Cout][ntaps*Cin] bf16 (tap-major K), out is [NB*Ho*Wo][ldc] bf16.  Taps are given as input offsets.
 cudaError_t launch_conv_bf16(const void* x, const void* w, void* out, int NB, int planes, int Hin, int Win, int Cin, int Ho, int Wo,
                              int Cout, int ldc, int ntaps, const int* dh, const int* dw, const int* dplane, const float* bias,
-                             int relu, int accumulate, float* stats, cudaStream_t st) {
+                             int relu, int accumulate, float* stats, cudaStream_t st, const int* wtap, int w_taps_total) {
     if (Cin % BK || Cout % 8 || ntaps < 1 || ntaps > 9) return cudaErrorInvalidValue;
+    if (wtap && (stats || Cout % 64)) return cudaErrorInvalidValue;   // MN-major filter path: whole 64-wide ci groups, no statistics
     const int bn = pick_bn(Cout);
     ConvGemmParams p{};
     // output tile: TW x TH x TN = 128 output pixels, TW/TH powers of two covering the image
@@ -337,7 +349,15 @@ cudaError_t launch_conv_bf16(const void* x, const void* w, void* out, int NB, in
         const uint32_t b[4] = {BK, (uint32_t)TW, (uint32_t)TH, (uint32_t)TN};
         RLR_CUDA_CHECK(make_tmap_bf16(&tmA, x, 4, d, s, b));
     }
-    {
+    if (wtap) {
+        // data gradient on the un-transposed filter: w is the forward filter [K = Cin of this call][w_taps_total * Cout of this call]
+        p.b_mn = 1; p.wcols = Cout;
+        for (int t = 0; t < ntaps; ++t) p.wtap[t] = wtap[t];
+        const uint64_t cols = (uint64_t)w_taps_total * Cout;
+        const uint64_t d[2] = {cols, (uint64_t)Cin}, s[1] = {cols * 2};
+        const uint32_t b[2] = {64, BK};
+        RLR_CUDA_CHECK(make_tmap_bf16(&tmB, w, 2, d, s, b));
+    } else {
         const uint64_t K = (uint64_t)ntaps * Cin;
         const uint64_t d[2] = {K, (uint64_t)Cout}, s[1] = {K * 2};
         const uint32_t b[2] = {BK, (uint32_t)bn};

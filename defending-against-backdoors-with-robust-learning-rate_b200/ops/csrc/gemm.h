@@ -21,6 +21,9 @@ struct ConvGemmParams {
     int ntaps;
     int8_t dh[9], dw[9];       // per tap: input row / col offset relative to the output pixel (in plane coordinates)
     int dn[9];                 // per tap: image offset (parity plane * NB) for strided convs
+    int b_mn;                  // 1: B operand is read MN-major straight from the un-transposed filter (data gradients)
+    int wtap[9];               // b_mn: filter tap that k-block tap t multiplies (flipped / parity-selected)
+    int wcols;                 // b_mn: columns per filter tap in the 2-D filter view (= Cin of the forward conv)
     void* out;                 // bf16 [M][ldc]
     int ldc;
     const float* bias;         // [N] or null
@@ -32,7 +35,7 @@ cudaError_t launch_gemm_bf16(const void* A, const void* B, void* out, int M, int
                              const float* bias, int relu, int accumulate, float* stats, cudaStream_t st);
 cudaError_t launch_conv_bf16(const void* x, const void* w, void* out, int NB, int planes, int Hin, int Win, int Cin, int Ho, int Wo,
                              int Cout, int ldc, int ntaps, const int* dh, const int* dw, const int* dplane, const float* bias,
-                             int relu, int accumulate, float* stats, cudaStream_t st);
+                             int relu, int accumulate, float* stats, cudaStream_t st, const int* wtap = nullptr, int w_taps_total = 0);
 
 // ---- conv_halo.cu: persistent 3x3/s1/p1 conv for 64 input channels with smem halo reuse + resident filter ------------------
 cudaError_t launch_conv3x3_halo_bf16(const void* x, const void* w, void* out, int NB, int H, int W, int Cout, const float* bias, int relu,

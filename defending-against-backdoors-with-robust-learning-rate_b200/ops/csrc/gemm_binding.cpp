@@ -38,17 +38,22 @@ void gemm_bf16(at::Tensor A, at::Tensor B, at::Tensor out, c10::optional<at::Ten
 
 // x: [planes*NB, Hin, Win, Cin]; w: [Cout, ntaps*Cin]; out: [NB, Ho, Wo, Cout]
 void conv_bf16(at::Tensor x, at::Tensor w, at::Tensor out, int64_t NB, int64_t planes, std::vector<int64_t> dh, std::vector<int64_t> dw,
-               std::vector<int64_t> dplane, c10::optional<at::Tensor> bias, bool relu, bool accumulate, c10::optional<at::Tensor> stats) {
+               std::vector<int64_t> dplane, c10::optional<at::Tensor> bias, bool relu, bool accumulate, c10::optional<at::Tensor> stats,
+               std::vector<int64_t> wtap, int64_t w_taps_total) {
     c10::cuda::CUDAGuard g(x.device());
     TORCH_CHECK(x.dim() == 4 && out.dim() == 4 && w.dim() == 2);
     const int Hin = x.size(1), Win = x.size(2), Cin = x.size(3), Ho = out.size(1), Wo = out.size(2), Cout = out.size(3);
     const int T = (int)dh.size();
-    TORCH_CHECK(x.size(0) == planes * NB && out.size(0) == NB && w.size(0) == Cout && w.size(1) == (int64_t)T * Cin);
+    const bool bmn = !wtap.empty();   // data gradient reading the forward filter w[Cin_here][w_taps_total * Cout_here] MN-major
+    TORCH_CHECK(x.size(0) == planes * NB && out.size(0) == NB);
+    TORCH_CHECK(bmn ? (w.size(0) == Cin && w.size(1) == w_taps_total * Cout && (int)wtap.size() == T)
+                    : (w.size(0) == Cout && w.size(1) == (int64_t)T * Cin), "filter shape");
     TORCH_CHECK(!stats.has_value() || !stats->defined() || stats->numel() == (int64_t)rlr::kStatSlots * 2 * Cout, "stats must be [STAT_SLOTS,2,Cout]");
-    int a[9], b[9], c[9];
-    for (int t = 0; t < T; ++t) { a[t] = (int)dh[t]; b[t] = (int)dw[t]; c[t] = (int)dplane[t]; }
+    int a[9], b[9], c[9], wt[9];
+    for (int t = 0; t < T; ++t) { a[t] = (int)dh[t]; b[t] = (int)dw[t]; c[t] = (int)dplane[t]; wt[t] = bmn ? (int)wtap[t] : 0; }
     check(rlr::launch_conv_bf16(bf(x), bf(w), bfm(out), (int)NB, (int)planes, Hin, Win, Cin, Ho, Wo, Cout, Cout, T, a, b, c,
-                                opt<const float>(bias), relu, accumulate, opt<float>(stats), cur_stream()), "conv_bf16");
+                                opt<const float>(bias), relu, accumulate, opt<float>(stats), cur_stream(), bmn ? wt : nullptr,
+                                (int)w_taps_total), "conv_bf16");
 }
 
 // x: [NB,H,W,64]; w: [Cout, 9*64]; out: [NB,H,W,Cout]   (3x3, stride 1, pad 1)

@@ -481,21 +481,27 @@ cudaError_t launch_filter_transpose(const __nv_bfloat16* w, __nv_bfloat16* wt, i
 // ---------------------------------------------------------------------------------------------------------------------
 // small dense layers (classifier heads, N <= 32): CUDA cores, fp32 accumulation
 // ---------------------------------------------------------------------------------------------------------------------
+// forward: one warp per sample row, lanes stride over K, NMAX accumulators in registers
+template <int NMAX>
 __global__ void __launch_bounds__(128) linear_small_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
                                                                  const float* __restrict__ bias, __nv_bfloat16* __restrict__ y,
                                                                  int B, int K, int N, int relu) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= B) return;
-    float acc[32];
+    float acc[NMAX];
 #pragma unroll
-    for (int n = 0; n < 32; ++n) acc[n] = 0.f;
-    for (int k = lane; k < K; k += 32) {
-        const float xv = __bfloat162float(x[(size_t)warp * K + k]);
+    for (int n = 0; n < NMAX; ++n) acc[n] = 0.f;
+    for (int k = lane * 2; k < K; k += 64) {   // K is even for every head in the zoo
+        const float2 xv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(x + (size_t)warp * K + k));
 #pragma unroll
-        for (int n = 0; n < 32; ++n) if (n < N) acc[n] += xv * __bfloat162float(w[(size_t)n * K + k]);
+        for (int n = 0; n < NMAX; ++n)
+            if (n < N) {
+                const float2 wv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(w + (size_t)n * K + k));
+                acc[n] += xv.x * wv.x + xv.y * wv.y;
+            }
     }
 #pragma unroll
-    for (int n = 0; n < 32; ++n) {
+    for (int n = 0; n < NMAX; ++n) {
         if (n < N) {
             float v = warp_sum(acc[n]);
             if (lane == 0) {
@@ -508,40 +514,62 @@ __global__ void __launch_bounds__(128) linear_small_fwd_kernel(const __nv_bfloat
 }
 cudaError_t launch_linear_small_fwd(const __nv_bfloat16* x, const __nv_bfloat16* w, const float* bias, __nv_bfloat16* y, int B, int K,
                                     int N, int relu, cudaStream_t st) {
-    if (N > 32) return cudaErrorInvalidValue;
-    linear_small_fwd_kernel<<<(B * 32 + 127) / 128, 128, 0, st>>>(x, w, bias, y, B, K, N, relu);
+    if (N > 32 || (K & 1)) return cudaErrorInvalidValue;
+    const int blocks = (B * 32 + 127) / 128;
+    if (N <= 16) linear_small_fwd_kernel<16><<<blocks, 128, 0, st>>>(x, w, bias, y, B, K, N, relu);
+    else linear_small_fwd_kernel<32><<<blocks, 128, 0, st>>>(x, w, bias, y, B, K, N, relu);
     return cudaGetLastError();
 }
 
+// backward: grid.x = K/64 column chunks (+1 block for dx rows); dW/db: 256 threads = 64 k x 4 batch slices, partials via smem
 __global__ void __launch_bounds__(256) linear_small_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
                                                                  const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ dx,
                                                                  float* __restrict__ dw, float* __restrict__ db, int B, int K, int N,
                                                                  int accumulate_dx) {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long n_dx = dx ? (long long)B * K : 0, n_dw = (long long)N * K;
-    if (t < n_dx) {                                   // dx[b][k] = sum_n dy[b][n] w[n][k]
-        const int b = (int)(t / K), k = (int)(t % K);
-        float acc = 0.f;
-        for (int n = 0; n < N; ++n) acc += __bfloat162float(dy[(size_t)b * N + n]) * __bfloat162float(w[(size_t)n * K + k]);
-        if (accumulate_dx) acc += __bfloat162float(dx[t]);
-        dx[t] = __float2bfloat16(acc);
-    } else if (t < n_dx + n_dw) {                     // dw[n][k] = sum_b dy[b][n] x[b][k]
-        const long long u = t - n_dx;
-        const int n = (int)(u / K), k = (int)(u % K);
-        float acc = 0.f;
-        for (int b = 0; b < B; ++b) acc += __bfloat162float(dy[(size_t)b * N + n]) * __bfloat162float(x[(size_t)b * K + k]);
-        dw[u] = acc;
-    } else if (db && t < n_dx + n_dw + N) {           // db[n] = sum_b dy[b][n]
-        const int n = (int)(t - n_dx - n_dw);
-        float acc = 0.f;
-        for (int b = 0; b < B; ++b) acc += __bfloat162float(dy[(size_t)b * N + n]);
-        db[n] = acc;
+    __shared__ float part[4][32][64];   // [batch slice][n][k in chunk]  (N <= 32)
+    const int kchunks = (K + 63) / 64;
+    if ((int)blockIdx.x < kchunks) {
+        const int kk = threadIdx.x & 63, sl = threadIdx.x >> 6, k = blockIdx.x * 64 + kk;
+        float acc[32];
+#pragma unroll
+        for (int n = 0; n < 32; ++n) acc[n] = 0.f;
+        if (k < K) {
+            for (int b = sl; b < B; b += 4) {
+                const float xv = __bfloat162float(x[(size_t)b * K + k]);
+#pragma unroll
+                for (int n = 0; n < 32; ++n) if (n < N) acc[n] += xv * __bfloat162float(dy[(size_t)b * N + n]);
+            }
+        }
+#pragma unroll
+        for (int n = 0; n < 32; ++n) if (n < N) part[sl][n][kk] = acc[n];
+        __syncthreads();
+        for (int i = threadIdx.x; i < N * 64; i += 256) {
+            const int n = i >> 6, c = i & 63;
+            if (blockIdx.x * 64 + c < K) dw[(size_t)n * K + blockIdx.x * 64 + c] = part[0][n][c] + part[1][n][c] + part[2][n][c] + part[3][n][c];
+        }
+        if (blockIdx.x == 0 && db && threadIdx.x < N) {   // db[n] = sum_b dy[b][n]
+            float a = 0.f;
+            for (int b = 0; b < B; ++b) a += __bfloat162float(dy[(size_t)b * N + threadIdx.x]);
+            db[threadIdx.x] = a;
+        }
+    } else if (dx) {                                       // dx[b][k] = sum_n dy[b][n] w[n][k]
+        const long long total = (long long)B * K;
+        for (long long t = (long long)(blockIdx.x - kchunks) * 256 + threadIdx.x; t < total; t += (long long)(gridDim.x - kchunks) * 256) {
+            const int b = (int)(t / K), k = (int)(t % K);
+            float acc = 0.f;
+            for (int n = 0; n < N; ++n) acc += __bfloat162float(dy[(size_t)b * N + n]) * __bfloat162float(w[(size_t)n * K + k]);
+            if (accumulate_dx) acc += __bfloat162float(dx[t]);
+            dx[t] = __float2bfloat16(acc);
+        }
     }
 }
 cudaError_t launch_linear_small_bwd(const __nv_bfloat16* x, const __nv_bfloat16* dy, const __nv_bfloat16* w, __nv_bfloat16* dx,
                                     float* dw, float* db, int B, int K, int N, int accumulate_dx, cudaStream_t st) {
-    const long long total = (dx ? (long long)B * K : 0) + (long long)N * K + N;
-    linear_small_bwd_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(x, dy, w, dx, dw, db, B, K, N, accumulate_dx);
+    if (N > 32) return cudaErrorInvalidValue;
+    const int kchunks = (K + 63) / 64;
+    long long dxb = dx ? ((long long)B * K + 255) / 256 : 0;
+    if (dxb > 592) dxb = 592;
+    linear_small_bwd_kernel<<<kchunks + (int)dxb, 256, 0, st>>>(x, dy, w, dx, dw, db, B, K, N, accumulate_dx);
     return cudaGetLastError();
 }
 

@@ -9,6 +9,7 @@
 // Plain mode (mode 0) is the same kernel on 2-D operands: dW[n][k] = sum_b dY[b][n] X[b][k] for linear layers.
 // Replaces cuDNN wgrad / cuBLAS GEMM^T behind loss.backward() (reference src/agent.py:48).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "gemm.h"
@@ -198,7 +199,8 @@ static cudaError_t launch_wg(const CUtensorMap& tmA, const CUtensorMap& tmB, Wgr
     }
     // split-K so that the grid is (at most) a whole number of waves of one CTA per SM: no ragged tail wave
     const int base = co_tiles * p.ci_tiles * tap_groups;
-    int waves = base >= num_sms ? (base + num_sms - 1) / num_sms : 2;
+    static const int tune_waves = [] { const char* e = getenv("RLR_WG_WAVES"); return e ? atoi(e) : 0; }();
+    int waves = base >= num_sms ? (base + num_sms - 1) / num_sms : (tune_waves > 0 ? tune_waves : 1);   // one wave measured faster (fewer split-K atomics), RLR_WG_WAVES overrides
     int splits = (waves * num_sms) / base;
     if (splits > p.num_kb) splits = p.num_kb;
     if (splits < 1) splits = 1;

@@ -87,7 +87,7 @@ def conv2d_fwd_sm100(x, w, bias, y, stride, pad, relu, stats, tag="fwd", zero_st
     dh, dw, pl = _taps(k, stride, pad)
     if stats is not None and zero_stats:
         stats.zero_()
-    e.conv_bf16(x, w.reshape(Cout, k * k * Cin), y, B, planes, dh, dw, pl, bias, bool(relu), False, stats)
+    e.conv_bf16(x, w.reshape(Cout, k * k * Cin), y, B, planes, dh, dw, pl, bias, bool(relu), False, stats, [], 0)
     return y
 
 
@@ -99,13 +99,21 @@ def conv2d_dgrad_sm100(dy, w, dx, stride, pad, accumulate):
     B = dy.shape[0]
     if stride == 2:
         return _conv2d_dgrad_s2(e, dy, w, dx, pad, accumulate)
-    wt = scratch(("wt", w.data_ptr()), (Cin, k * k * Cout), w.dtype, w.device)
-    e.filter_transpose(w, wt, Cout, k * k, Cin)
     if _halo_ok(k, 1, k - 1 - pad, Cout, dy.shape[1], dy.shape[2]) and dx.shape[1:3] == dy.shape[1:3]:
+        wt = scratch(("wt", w.data_ptr()), (Cin, k * k * Cout), w.dtype, w.device)   # resident-filter kernel wants K-major taps
+        e.filter_transpose(w, wt, Cout, k * k, Cin)
         e.conv3x3_halo_bf16(dy, wt, dx, None, False, bool(accumulate), None, 0, None)
         return dx
     dh, dw, pl = _taps(k, 1, k - 1 - pad)
-    e.conv_bf16(dy, wt, dx, B, 1, dh, dw, pl, None, False, bool(accumulate), None)
+    if Cin % 64 == 0:
+        # read the forward filter W[co][tap][ci] directly as an MN-major B operand; k-block tap t' multiplies filter tap T-1-t'
+        T = k * k
+        e.conv_bf16(dy, w.reshape(Cout, T * Cin), dx, B, 1, dh, dw, pl, None, False, bool(accumulate), None,
+                    [T - 1 - t for t in range(T)], T)
+        return dx
+    wt = scratch(("wt", w.data_ptr()), (Cin, k * k * Cout), w.dtype, w.device)
+    e.filter_transpose(w, wt, Cout, k * k, Cin)
+    e.conv_bf16(dy, wt, dx, B, 1, dh, dw, pl, None, False, bool(accumulate), None, [], 0)
     return dx
 
 
@@ -129,9 +137,13 @@ def _conv2d_dgrad_s2(e, dy, w, dx, pad, accumulate):
                 continue
             plane = pi * 2 + pj
             mask |= 1 << plane
+            if Cin % 64 == 0:   # forward filter read MN-major: the plane's sub-filter is just a tap list
+                e.conv_bf16(dy, w.reshape(Cout, k * k * Cin), dx4[plane * B:(plane + 1) * B], B, 1, dh, dw, [0] * len(taps), None,
+                            False, False, None, taps, k * k)
+                continue
             wt = scratch(("wt_s2", w.data_ptr(), plane), (Cin, len(taps) * Cout), w.dtype, w.device)
             e.filter_gather_transpose(w, wt, Cout, k * k, Cin, taps)
-            e.conv_bf16(dy, wt, dx4[plane * B:(plane + 1) * B], B, 1, dh, dw, [0] * len(taps), None, False, False, None)
+            e.conv_bf16(dy, wt, dx4[plane * B:(plane + 1) * B], B, 1, dh, dw, [0] * len(taps), None, False, False, None, [], 0)
     e.depth_to_space(dx4, dx, bool(accumulate), mask)
     return dx
 

@@ -30,6 +30,18 @@ def conv_case(B, H, C, Cout, tag):
     torch.cuda.synchronize()
 
 
+if which == "bn":
+    for (M, C) in [(256 * 32 * 32, 64), (256 * 8 * 8, 256)]:
+        x = torch.randn(M, 1, 1, C, device=DEV).to(BF); r = torch.randn_like(x); y = torch.empty_like(x)
+        g, b = torch.ones(C, device=DEV), torch.zeros(C, device=DEV)
+        rm, rv, mr = torch.zeros(C, device=DEV), torch.ones(C, device=DEV), torch.zeros(2, C, device=DEV)
+        dy = torch.randn_like(x); dx = torch.empty_like(x); dres = torch.empty_like(x)
+        dg, db, ds = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV), torch.zeros(2, C, device=DEV)
+        for _ in range(2):
+            ops.bn_fwd(x, y, r, g, b, rm, rv, None, mr, M, 1e-5, 0.1, True, True, "sm100")
+            ops.bn_bwd(dy, y, x, g, mr, ds, dx, dres, dg, db, True, "sm100")
+    torch.cuda.synchronize()
+    print("ok"); sys.exit(0)
 conv_case(256, 32, 64, 64, "l1")
 conv_case(256, 8, 256, 256, "l3")
 if which in ("all", "agg"):
