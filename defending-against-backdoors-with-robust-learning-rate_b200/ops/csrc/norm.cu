@@ -35,7 +35,7 @@ static inline bool chan_ok(int C) { return C >= 8 && C <= 2048 && (C % 8) == 0 &
 // MODE 0: a = x, b = x^2 (forward statistics)     MODE 1: a = dz, b = dz * xhat (backward)
 // ---------------------------------------------------------------------------------------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(256) channel_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+__global__ void __launch_bounds__(256, MODE == 0 ? 4 : 3) channel_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
                                                                const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean_rstd,
                                                                float* out, long long M, int C, int relu) {
     extern __shared__ float sh[];   // [2][C]
@@ -50,21 +50,43 @@ __global__ void __launch_bounds__(256) channel_reduce_kernel(const __nv_bfloat16
 #pragma unroll
         for (int i = 0; i < 8; ++i) { mu[i] = mean_rstd[cg * 8 + i]; rs[i] = mean_rstd[C + cg * 8 + i]; }
     }
-    for (long long r = (long long)blockIdx.x * rpi + ry; r < M; r += (long long)gridDim.x * rpi) {
-        const size_t off = (size_t)r * C + cg * 8;
-        const bf8 xv = load8(x + off);
-        if (MODE == 0) {
+    // U rows per iteration with every load issued before the first use: one 16-byte load per thread in flight reaches only
+    // ~20 % (forward statistics) / ~48 % (backward) of the HBM roofline (profiles/r1c_ncu_bn_kernels.md)
+    constexpr int U = MODE == 0 ? 4 : 2;
+    const long long stride = (long long)gridDim.x * rpi;
+    for (long long r0 = (long long)blockIdx.x * rpi + ry; r0 < M; r0 += stride * U) {
+        uint4 xr[U], dr[U], yr[U];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { a[i] += xv.v[i]; b[i] += xv.v[i] * xv.v[i]; }
-        } else {
-            bf8 dz = load8(dy + off);
-            if (relu) {
-                const bf8 yv = load8(y + off);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) dz.v[i] = yv.v[i] > 0.f ? dz.v[i] : 0.f;
+        for (int u = 0; u < U; ++u) {
+            const long long r = r0 + u * stride;
+            const size_t off = (size_t)(r < M ? r : r0) * C + cg * 8;
+            xr[u] = *reinterpret_cast<const uint4*>(x + off);
+            if (MODE == 1) {
+                dr[u] = *reinterpret_cast<const uint4*>(dy + off);
+                if (relu) yr[u] = *reinterpret_cast<const uint4*>(y + off);
             }
+        }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { a[i] += dz.v[i]; b[i] += dz.v[i] * (xv.v[i] - mu[i]) * rs[i]; }
+        for (int u = 0; u < U; ++u) {
+            if (r0 + u * stride >= M) continue;
+            const __nv_bfloat162* xh = reinterpret_cast<const __nv_bfloat162*>(&xr[u]);
+            const __nv_bfloat162* dh = reinterpret_cast<const __nv_bfloat162*>(&dr[u]);
+            const __nv_bfloat162* yh = reinterpret_cast<const __nv_bfloat162*>(&yr[u]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 xv = __bfloat1622float2(xh[i]);
+                if (MODE == 0) {
+                    a[2 * i] += xv.x; a[2 * i + 1] += xv.y; b[2 * i] += xv.x * xv.x; b[2 * i + 1] += xv.y * xv.y;
+                } else {
+                    float2 dz = __bfloat1622float2(dh[i]);
+                    if (relu) {
+                        const float2 yv = __bfloat1622float2(yh[i]);
+                        dz.x = yv.x > 0.f ? dz.x : 0.f; dz.y = yv.y > 0.f ? dz.y : 0.f;
+                    }
+                    a[2 * i] += dz.x; a[2 * i + 1] += dz.y;
+                    b[2 * i] += dz.x * (xv.x - mu[2 * i]) * rs[2 * i]; b[2 * i + 1] += dz.y * (xv.y - mu[2 * i + 1]) * rs[2 * i + 1];
+                }
+            }
         }
     }
 #pragma unroll
