@@ -190,7 +190,7 @@ def run_ours(a):
     e2e = None
     if not a.no_e2e:
         eng.enable_input_streaming()
-        eng.run_round(10_000, stream_inputs=True)  # warm the streaming path
+        eng.run_round(10_000, stream_inputs=True)  # warm the streaming path (captures graphs for the streamed shards)
         ms2, h2d, d2h, res, _ = timed(a.steps, 10_001, True)
         tot = torch.tensor([float(h2d), float(d2h)], dtype=torch.float64, device=dev)
         ctx.all_reduce_sum(tot)

@@ -429,6 +429,7 @@ class NativeTrainer:
             return self._graphs[key]
         keep = (self.w.clone(), self.wb.clone(), self.m.clone(), self.cursor.clone(), self.loss_sum.clone(),
                 self.net.step_counter.clone())
+        self.perm.zero_()   # warm-up / capture must only touch valid sample indices (perm may hold another dataset's indices)
         s = torch.cuda.Stream(self.device)
         s.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(s):

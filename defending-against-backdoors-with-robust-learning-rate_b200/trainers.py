@@ -70,6 +70,7 @@ class TorchTrainer:
             self.x = torch.zeros(self.bs, meta.channels, meta.height, meta.width, dtype=torch.float32, device=self.device)
         # warm-up on a side stream (cuDNN autotune, lazy inits), then capture; state is re-initialised afterwards
         keep = (self.w.clone(), self.m.clone(), self.cursor.clone(), self.loss_sum.clone())
+        self.perm.zero_()   # warm-up / capture must only touch valid sample indices (perm may hold another dataset's indices)
         s = torch.cuda.Stream(self.device)
         s.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(s):
