@@ -105,27 +105,33 @@ class FLEngine:
 
     # ---- end-to-end input streaming (bench "e2e"): shards come from pinned host memory every round ----------
     def enable_input_streaming(self):
-        """End-to-end mode: every agent's shard gets a compact device buffer plus a pinned host copy, and
-        ``run_round(stream_inputs=True)`` re-uploads (one contiguous H2D copy, no scatter, no allocation) the shards this
-        rank trains each round -- what a deployment that receives fresh client data every round does.  Returns the total
-        bytes of all shards."""
+        """End-to-end mode: every agent's shard is kept in pinned host memory and ``run_round(stream_inputs=True)`` uploads the
+        shard of each agent this rank is about to train (one contiguous H2D copy, no scatter, no allocation) into ONE per-rank
+        device staging dataset -- what a deployment that receives fresh client data every round does.  A single staging buffer
+        keeps the device addresses (and therefore the captured CUDA graphs) identical no matter which agent a rank hosts in a
+        round.  Returns the total bytes of all shards."""
         from .data import DeviceDataset
         self._stream_src = {}
-        cuda = self.ctx.device.type == "cuda"
-        pin = (lambda t: t.cpu().pin_memory()) if cuda else (lambda t: t.cpu().clone())
-        total = 0
+        dev = self.ctx.device
+        pin = (lambda t: t.cpu().pin_memory()) if dev.type == "cuda" else (lambda t: t.cpu().clone())
+        total, n_max = 0, max(a.n_data for a in self.agents)
+        ref = self.agents[0].dataset
+        buf = DeviceDataset(ref.name, torch.zeros((n_max, *ref.data.shape[1:]), dtype=ref.data.dtype, device=dev),
+                            torch.zeros(n_max, dtype=torch.int64, device=dev))
         for a in self.agents:
             x, y = a.dataset.data[a.idxs].contiguous(), a.dataset.targets[a.idxs].contiguous()
             self._stream_src[a.id] = (pin(x), pin(y))
-            a.dataset = DeviceDataset(a.dataset.name, x, y)        # compact shard; indices become local
-            a.idxs = torch.arange(a.n_data, device=self.ctx.device)
+            a.dataset = buf                                          # all agents train out of the staging buffer ...
+            a.idxs = torch.arange(a.n_data, device=dev)              # ... with local indices
             total += x.numel() * x.element_size() + y.numel() * y.element_size()
+        self._stream_buf = buf
         return total
 
     def _upload_shard(self, agent):
         x, y = self._stream_src[agent.id]
-        agent.dataset.data.copy_(x, non_blocking=True)
-        agent.dataset.targets.copy_(y, non_blocking=True)
+        n = agent.n_data
+        self._stream_buf.data[:n].copy_(x, non_blocking=True)
+        self._stream_buf.targets[:n].copy_(y, non_blocking=True)
         return x.numel() * x.element_size() + y.numel() * y.element_size()
 
     # ---- one federated round (src/federated.py:66-74) --------------------------------------------------------

@@ -283,3 +283,21 @@ def test_conv3x3_halo_kernel(B, H, W, Cout, acc):
     print("halo conv rel err by base-offset mode:", errs)
     assert errs[0] < 1e-2, errs
     assert s_ok
+
+
+def test_streaming_mode_after_resident_rounds_uses_valid_indices():
+    """Regression: switching to per-round input streaming (compact per-agent shards) after rounds on the resident dataset must
+    not replay graph warm-ups with the old dataset's (out-of-range) sample indices."""
+    from rlr_b200.engine import FLEngine
+    from rlr_b200.options import make_args
+    args = make_args(data="cifar10", model="cnn_cifar", num_agents=4, local_ep=1, bs=64, synthetic=1024, synthetic_val=128, log_dir="",
+                     device=DEV, seed=1)
+    eng = FLEngine(args, verbose=False)
+    eng.run_round(1)
+    eng.enable_input_streaming()
+    for r in (2, 3):
+        eng.run_round(r, stream_inputs=True)
+    loss, _ = eng.round_result()
+    torch.cuda.synchronize()
+    assert loss == loss and eng.evaluate(3)["val_acc"] > 0.2
+    eng.close()
