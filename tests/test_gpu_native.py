@@ -249,13 +249,16 @@ def test_native_trainer_learns_like_torch_trainer(model):
         args = make_args(data="cifar10", model=model, num_agents=2, local_ep=2, bs=64, synthetic=1000, synthetic_val=200, log_dir="",
                          device=DEV, trainer=trainer, seed=2)
         eng = FLEngine(args, verbose=False)
-        for r in range(1, 4):
+        for r in range(1, 7):
             eng.run_round(r)
-        accs[trainer] = eng.evaluate(3)["val_acc"]
+        accs[trainer] = eng.evaluate(6)["val_acc"]
         assert eng.trainer.name == trainer
         eng.close()
     print(model, accs)
-    assert accs["native"] > 0.5 and accs["native"] > accs["torch"] - 0.25
+    # Accuracy after a handful of rounds on 1000 samples depends on the dropout-mask / atomics-order realisation (scripts/
+    # debug_flaky.py: 0.73-1.0 after 3 rounds for EVERY back-end mix, incl. library kernels with a different mask stream), so
+    # the bar is "clearly learned", not "matches the torch trainer's realisation".
+    assert accs["native"] > 0.7 and accs["torch"] > 0.7
 
 
 @pytest.mark.parametrize("B,H,W,Cout,acc", [(64, 32, 32, 64, False), (37, 16, 16, 64, True), (8, 32, 32, 128, False), (5, 16, 8, 32, False)])
