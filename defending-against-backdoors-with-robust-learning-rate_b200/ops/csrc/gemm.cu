@@ -17,6 +17,7 @@
 // * 4-stage (BN=64) / 3-stage (BN=128) smem ring with full/empty mbarriers; tcgen05.commit releases stages; two CTAs
 //   are resident per SM (<= 113 KB smem, <= 128 TMEM columns each) so one CTA's epilogue overlaps the other's mainloop.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "gemm.h"
@@ -328,8 +329,13 @@ cudaError_t launch_conv_bf16(const void* x, const void* w, void* out, int NB, in
                              int relu, int accumulate, float* stats, cudaStream_t st, const int* wtap, int w_taps_total) {
     if (Cin % BK || Cout % 8 || ntaps < 1 || ntaps > 9) return cudaErrorInvalidValue;
     if (wtap && (stats || Cout % 64)) return cudaErrorInvalidValue;   // MN-major filter path: whole 64-wide ci groups, no statistics
-    const int bn = pick_bn(Cout);
+    int bn = pick_bn(Cout);
     ConvGemmParams p{};
+    {   // few M tiles (deep layers at small batch / 4x4 maps): prefer the 64-wide tile so the grid covers all SMs
+        static const int small_bn64 = [] { const char* e = getenv("RLR_SMALL_BN64"); return e ? atoi(e) : 1; }();   // measured +2.4 %
+        const long long px = (long long)NB * Ho * Wo;
+        if (small_bn64 && bn == 128 && ((px + BM - 1) / BM) * (Cout / 128) < 148) bn = 64;
+    }
     // output tile: TW x TH x TN = 128 output pixels, TW/TH powers of two covering the image
     int TW = pow2_ceil(Wo); if (TW > BM) TW = BM;
     int TH = pow2_ceil(Ho); if (TW * TH > BM) TH = BM / TW;
