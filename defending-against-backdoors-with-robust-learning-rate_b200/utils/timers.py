@@ -16,6 +16,7 @@ class PhaseTimer:
 
     def start(self, name):
         if self.cuda:
+            torch.cuda.nvtx.range_push(name)   # phases also show up as NVTX ranges in ncu / nsys timelines
             ev = torch.cuda.Event(enable_timing=True)
             ev.record()
             self._open[name] = ev
@@ -26,6 +27,7 @@ class PhaseTimer:
         if self.cuda:
             ev = torch.cuda.Event(enable_timing=True)
             ev.record()
+            torch.cuda.nvtx.range_pop()
             self._spans.setdefault(name, []).append((self._open.pop(name), ev))
         else:
             self._spans.setdefault(name, []).append((self._open.pop(name), time.perf_counter()))

@@ -129,3 +129,27 @@ def test_input_streaming_roundtrip():
     last = eng.agents[info["chosen"][-1]]                       # the staging buffer holds the shard uploaded last
     assert torch.equal(eng._stream_buf.data[: last.n_data], eng._stream_src[last.id][0])
     assert all(a.dataset is eng._stream_buf for a in eng.agents)
+
+
+def test_fedemnist_shaped_float_data_path():
+    """Fed-EMNIST stores float images in [0,1] (reference H5Dataset, src/utils.py:11-36): float gather path, `sub`-mode trojans
+    and the non-IID-style agent count with partial participation (src/runner.sh:34-38 shape, scaled down)."""
+    eng = _engine(data="fedemnist", synthetic=1500, synthetic_val=300, num_agents=30, agent_frac=0.2, num_corrupt=3, poison_frac=0.5,
+                  pattern_type="square", robustLR_threshold=2, local_ep=2, bs=32)
+    assert eng.train_dataset.data.dtype == torch.float32 and eng.n_part == 6
+    assert any(len(a.poisoned_idxs) > 0 for a in eng.agents[:3]) and all(len(a.poisoned_idxs) == 0 for a in eng.agents[3:])
+    for r in range(1, 4):
+        eng.run_round(r)
+    ev = eng.evaluate(3)
+    assert ev["val_loss"] == ev["val_loss"] and 0.0 <= ev["poison_acc"] <= 1.0
+
+
+def test_h5dataset_container_and_conversion():
+    from rlr_b200.data import H5Dataset
+    raw = {"c0": {"label": [1, 2, 3], "pixels": torch.rand(3, 28, 28).numpy()}, "c1": {"label": [4], "pixels": torch.rand(1, 28, 28).numpy()}}
+    a, b = H5Dataset(raw, "c0"), H5Dataset(raw, "c1")
+    assert len(a) == 3 and a[0][0].shape == (1, 28, 28) and set(a.classes().tolist()) == {1, 2, 3}
+    ab = a + b
+    assert len(ab) == 4 and ab.targets.tolist() == [1, 2, 3, 4]
+    dd = ab.as_device_dataset()
+    assert dd.data.shape == (4, 28, 28, 1) and dd.name == "fedemnist"
