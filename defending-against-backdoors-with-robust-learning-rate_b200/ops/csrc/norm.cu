@@ -38,11 +38,9 @@ template <int MODE>
 __global__ void __launch_bounds__(256, MODE == 0 ? 4 : 3) channel_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
                                                                const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean_rstd,
                                                                float* out, long long M, int C, int relu) {
-    extern __shared__ float sh[];   // [2][C]
+    extern __shared__ float sh[];   // [rpi][2][C] per-row-slot partials (16 KB for every C)
     const int tpr = C / 8, rpi = 256 / tpr;
     const int cg = threadIdx.x % tpr, ry = threadIdx.x / tpr;
-    for (int i = threadIdx.x; i < 2 * C; i += 256) sh[i] = 0.f;
-    __syncthreads();
     float a[8], b[8], mu[8], rs[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { a[i] = 0.f; b[i] = 0.f; mu[i] = 0.f; rs[i] = 1.f; }
@@ -89,23 +87,30 @@ __global__ void __launch_bounds__(256, MODE == 0 ? 4 : 3) channel_reduce_kernel(
             }
         }
     }
+    // block reduction without atomics: every thread parks its 16 partial sums in its row slot, then each thread sums a few
+    // columns over the rpi slots (conflict-free) and issues ONE global atomic per column and block
+    float* mine = sh + (size_t)ry * 2 * C + cg * 8;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { atomicAdd(&sh[cg * 8 + i], a[i]); atomicAdd(&sh[C + cg * 8 + i], b[i]); }
+    for (int i = 0; i < 8; ++i) { mine[i] = a[i]; mine[C + i] = b[i]; }
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * C; i += 256) atomicAdd(out + i, sh[i]);
+    for (int i = threadIdx.x; i < 2 * C; i += 256) {
+        float t = 0.f;
+        for (int r = 0; r < rpi; ++r) t += sh[(size_t)r * 2 * C + i];
+        atomicAdd(out + i, t);
+    }
 }
 
 cudaError_t launch_channel_stats(const __nv_bfloat16* x, long long M, int C, float* stats, int num_sms, cudaStream_t st) {
     if (!chan_ok(C)) return cudaErrorInvalidValue;
     const int rpi = 256 / (C / 8);
-    channel_reduce_kernel<0><<<rows_grid(M, rpi * 8, num_sms, 4), 256, 2 * C * sizeof(float), st>>>(x, nullptr, nullptr, nullptr, stats, M, C, 0);
+    channel_reduce_kernel<0><<<rows_grid(M, rpi * 8, num_sms, 2), 256, (size_t)rpi * 2 * C * sizeof(float), st>>>(x, nullptr, nullptr, nullptr, stats, M, C, 0);
     return cudaGetLastError();
 }
 cudaError_t launch_bn_bwd_reduce(const __nv_bfloat16* dy, const __nv_bfloat16* y, const __nv_bfloat16* x, const float* mean_rstd,
                                  float* dsum, long long M, int C, int relu, int num_sms, cudaStream_t st) {
     if (!chan_ok(C)) return cudaErrorInvalidValue;
     const int rpi = 256 / (C / 8);
-    channel_reduce_kernel<1><<<rows_grid(M, rpi * 8, num_sms, 4), 256, 2 * C * sizeof(float), st>>>(x, dy, y, mean_rstd, dsum, M, C, relu);
+    channel_reduce_kernel<1><<<rows_grid(M, rpi * 8, num_sms, 2), 256, (size_t)rpi * 2 * C * sizeof(float), st>>>(x, dy, y, mean_rstd, dsum, M, C, relu);
     return cudaGetLastError();
 }
 
