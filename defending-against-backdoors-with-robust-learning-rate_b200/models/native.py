@@ -253,6 +253,7 @@ class NativeNet:
         """``x_nhwc``: [B,H,W,C] bf16 (channels of the first conv, un-padded).  Returns fp32 logits [B,classes]."""
         B = x_nhwc.shape[0]
         self._x, self._B, self._train = x_nhwc, B, train
+        self._epoch = getattr(self, "_epoch", 0) + 1     # forward-pass id: lets stride-2 convs share their parity-split input copy
         if train:
             self.stats_arena.zero_()
         for op in self.plan:
@@ -279,7 +280,7 @@ class NativeNet:
         # while it is still L2-resident (default: measured cheaper than the in-epilogue reduction, profiles/r1c notes)
         stats = op.saved.get("stats") if (train and op.saved.get("want_stats") and self.fuse_bn_stats) else None
         if self.impl["conv_fwd"] == "sm100" and ops.conv_supported(op.in_shape, a, "fwd"):
-            ops.conv2d_fwd_sm100(x, self.pwb[op.name + ".weight"], bias, y, a.get("stride", 1), a.get("pad", 0), op.relu, stats, tag=(id(self), op.name), zero_stats=False)
+            ops.conv2d_fwd_sm100(x, self.pwb[op.name + ".weight"], bias, y, a.get("stride", 1), a.get("pad", 0), op.relu, stats, tag=(id(self), op.name), zero_stats=False, s2d_epoch=self._epoch)
             return
         wt = self.pwb[op.name + ".weight"].permute(0, 3, 1, 2)
         out = F.conv2d(x.permute(0, 3, 1, 2), wt, bias.to(self.act_dtype) if bias is not None else None, a.get("stride", 1), a.get("pad", 0))

@@ -56,8 +56,11 @@ cudaError_t launch_channel_stats(const __nv_bfloat16* x, long long M, int C, flo
 cudaError_t launch_bn_finalize(const float* stats, int slots, float* mean_rstd, float* running_mean, float* running_var, int C,
                                float count, float eps, float momentum, int train, cudaStream_t st);
 // y = act(gamma * (x - mean) * rstd + beta [+ res])
+// fin_mode 0: mean_rstd given | 1: training, derive from raw sums `stats` [slots][2][C] (also writes mean_rstd + running stats) |
+// 2: evaluation, derive from the running statistics
 cudaError_t launch_bn_apply(const __nv_bfloat16* x, const __nv_bfloat16* res, __nv_bfloat16* y, const float* gamma, const float* beta,
-                            const float* mean_rstd, long long M, int C, int relu, int num_sms, cudaStream_t st);
+                            float* mean_rstd, long long M, int C, int relu, int fin_mode, const float* stats, int slots, float count,
+                            float eps, float momentum, float* running_mean, float* running_var, int num_sms, cudaStream_t st);
 // dsum[0][c] = sum dz, dsum[1][c] = sum dz * xhat   (dz = dy * (y > 0) if relu)
 cudaError_t launch_bn_bwd_reduce(const __nv_bfloat16* dy, const __nv_bfloat16* y, const __nv_bfloat16* x, const float* mean_rstd,
                                  float* dsum /*accumulates*/, long long M, int C, int relu, int num_sms, cudaStream_t st);

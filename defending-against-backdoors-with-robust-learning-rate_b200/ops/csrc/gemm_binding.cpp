@@ -109,11 +109,21 @@ void bn_finalize(at::Tensor stats, at::Tensor mean_rstd, at::Tensor rm, at::Tens
     check(rlr::launch_bn_finalize(f32(stats), slots, f32(mean_rstd), (float*)rm.data_ptr(), (float*)rv.data_ptr(), C, (float)count, (float)eps,
                                   (float)momentum, train, cur_stream()), "bn_finalize");
 }
-void bn_apply(at::Tensor x, c10::optional<at::Tensor> res, at::Tensor y, at::Tensor gamma, at::Tensor beta, at::Tensor mean_rstd, bool relu) {
+void bn_apply(at::Tensor x, c10::optional<at::Tensor> res, at::Tensor y, at::Tensor gamma, at::Tensor beta, at::Tensor mean_rstd, bool relu,
+              int64_t fin_mode, c10::optional<at::Tensor> stats, double count, double eps, double momentum,
+              c10::optional<at::Tensor> rm, c10::optional<at::Tensor> rv) {
     c10::cuda::CUDAGuard g(x.device());
     const int C = x.size(-1);
+    int slots = 1;
+    if (fin_mode == 1) {
+        TORCH_CHECK(stats.has_value() && stats->defined() && rm.has_value() && rv.has_value(), "bn_apply: training finalize needs stats and running stats");
+        slots = (int)(stats->numel() / (2 * C));
+        TORCH_CHECK(slots >= 1 && stats->numel() == (int64_t)slots * 2 * C, "stats must be [slots,2,C]");
+    }
+    if (fin_mode == 2) TORCH_CHECK(rm.has_value() && rv.has_value(), "bn_apply: eval needs running stats");
     check(rlr::launch_bn_apply(bf(x), bfo(res), bfm(y), (const float*)gamma.data_ptr(), (const float*)beta.data_ptr(), f32(mean_rstd),
-                               x.numel() / C, C, relu, num_sms(), cur_stream()), "bn_apply");
+                               x.numel() / C, C, relu, (int)fin_mode, opt<const float>(stats), slots, (float)count, (float)eps, (float)momentum,
+                               opt<float>(rm), opt<float>(rv), num_sms(), cur_stream()), "bn_apply");
 }
 void bn_bwd(at::Tensor dy, at::Tensor y, at::Tensor x, at::Tensor gamma, at::Tensor mean_rstd, at::Tensor dsum, at::Tensor dx,
             c10::optional<at::Tensor> dres, at::Tensor dgamma, at::Tensor dbeta, bool relu, bool zero_dsum) {

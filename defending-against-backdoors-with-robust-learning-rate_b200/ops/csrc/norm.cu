@@ -139,18 +139,45 @@ cudaError_t launch_bn_finalize(const float* stats, int slots, float* mean_rstd, 
     return cudaGetLastError();
 }
 
+// fin.mode 0: mean/rstd are given.  1 (training): derive them from the raw per-channel sums `fin.stats` ([slots][2][C]) in every
+// thread (16 loads + rsqrt), CTA 0 also stores mean/rstd for the backward pass and updates the running statistics -- this replaces
+// the separate bn_finalize launch.  2 (evaluation): derive them from the running statistics.
+struct BnFinalize {
+    int mode;
+    const float* stats; int slots;
+    float count, eps, momentum;
+    float* running_mean; float* running_var;
+};
 __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
                                                          __nv_bfloat16* __restrict__ y, const float* __restrict__ gamma,
-                                                         const float* __restrict__ beta, const float* __restrict__ mean_rstd,
-                                                         long long M, int C, int relu) {
+                                                         const float* __restrict__ beta, float* __restrict__ mean_rstd,
+                                                         long long M, int C, int relu, BnFinalize fin) {
     const int tpr = C / 8, rpi = 256 / tpr;
     const int cg = threadIdx.x % tpr, ry = threadIdx.x / tpr;
     float sc[8], sh[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int c = cg * 8 + i;
-        sc[i] = gamma[c] * mean_rstd[C + c];
-        sh[i] = beta[c] - mean_rstd[c] * sc[i];
+        float mean, rstd;
+        if (fin.mode == 1) {
+            float s1 = 0.f, s2 = 0.f;
+            for (int k = 0; k < fin.slots; ++k) { s1 += fin.stats[(size_t)k * 2 * C + c]; s2 += fin.stats[(size_t)k * 2 * C + C + c]; }
+            mean = s1 / fin.count;
+            const float var = fmaxf(s2 / fin.count - mean * mean, 0.f);
+            rstd = rsqrtf(var + fin.eps);
+            if (blockIdx.x == 0 && ry == 0) {
+                mean_rstd[c] = mean; mean_rstd[C + c] = rstd;
+                fin.running_mean[c] = (1.f - fin.momentum) * fin.running_mean[c] + fin.momentum * mean;
+                const float unbiased = fin.count > 1.f ? var * fin.count / (fin.count - 1.f) : var;
+                fin.running_var[c] = (1.f - fin.momentum) * fin.running_var[c] + fin.momentum * unbiased;
+            }
+        } else if (fin.mode == 2) {
+            mean = fin.running_mean[c]; rstd = rsqrtf(fin.running_var[c] + fin.eps);
+        } else {
+            mean = mean_rstd[c]; rstd = mean_rstd[C + c];
+        }
+        sc[i] = gamma[c] * rstd;
+        sh[i] = beta[c] - mean * sc[i];
     }
     for (long long r = (long long)blockIdx.x * rpi + ry; r < M; r += (long long)gridDim.x * rpi) {
         const size_t off = (size_t)r * C + cg * 8;
@@ -170,10 +197,12 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __re
     }
 }
 cudaError_t launch_bn_apply(const __nv_bfloat16* x, const __nv_bfloat16* res, __nv_bfloat16* y, const float* gamma, const float* beta,
-                            const float* mean_rstd, long long M, int C, int relu, int num_sms, cudaStream_t st) {
+                            float* mean_rstd, long long M, int C, int relu, int fin_mode, const float* stats, int slots, float count,
+                            float eps, float momentum, float* running_mean, float* running_var, int num_sms, cudaStream_t st) {
     if (!chan_ok(C)) return cudaErrorInvalidValue;
     const int rpi = 256 / (C / 8);
-    bn_apply_kernel<<<rows_grid(M, rpi * 4, num_sms, 8), 256, 0, st>>>(x, res, y, gamma, beta, mean_rstd, M, C, relu);
+    BnFinalize fin{fin_mode, stats, slots, count, eps, momentum, running_mean, running_var};
+    bn_apply_kernel<<<rows_grid(M, rpi * 4, num_sms, 8), 256, 0, st>>>(x, res, y, gamma, beta, mean_rstd, M, C, relu, fin);
     return cudaGetLastError();
 }
 

@@ -7,6 +7,7 @@ import torch
 import torch.nn.functional as F
 
 _scratch = {}
+_s2d_done = {}
 STAT_SLOTS = 16         # conv epilogues spread their BatchNorm statistics over this many partial buffers (gemm.h kStatSlots)
 USE_WGRAD_HALO = True   # 3x3/s1/p1, 64 input channels: halo-reuse weight-gradient kernel (wgrad.cu)
 
@@ -60,7 +61,7 @@ def _taps(k, stride, pad):
     return dh, dw, pl
 
 
-def conv2d_fwd_sm100(x, w, bias, y, stride, pad, relu, stats, tag="fwd", zero_stats=True):
+def conv2d_fwd_sm100(x, w, bias, y, stride, pad, relu, stats, tag="fwd", zero_stats=True, s2d_epoch=None):
     """y[B,Ho,Wo,Cout] = conv(x[B,H,W,Cin], w[Cout,k,k,Cin]) (+bias)(ReLU); ``stats`` [STAT_SLOTS,2,Cout] accumulates per-channel
     sum / sum^2 partials (sum over dim 0 for the totals)."""
     e = _ext()
@@ -81,8 +82,13 @@ def conv2d_fwd_sm100(x, w, bias, y, stride, pad, relu, stats, tag="fwd", zero_st
         return y
     planes = 1
     if stride == 2:
-        x4 = scratch(("s2d", tag), (4 * B, H // 2, W // 2, Cin), x.dtype, x.device)
-        e.space_to_depth(x, x4)
+        # parity-split copy keyed by the INPUT tensor: the 3x3/s2 conv and the 1x1/s2 shortcut of a ResNet block read the same
+        # input, so within one forward pass (same `s2d_epoch`) the copy is made once and shared (also with both weight gradients)
+        key = ("s2d", x.data_ptr(), Cin)
+        x4 = scratch(key, (4 * B, H // 2, W // 2, Cin), x.dtype, x.device)
+        if s2d_epoch is None or _s2d_done.get(key + (B,)) != s2d_epoch:
+            e.space_to_depth(x, x4)
+            _s2d_done[key + (B,)] = s2d_epoch
         x, planes = x4, 4
     dh, dw, pl = _taps(k, stride, pad)
     if stats is not None and zero_stats:
@@ -161,7 +167,7 @@ def conv2d_wgrad_sm100(x, dy, gw, gb, stride, pad, tag="fwd", zero=True):
         Cin = cp
     planes = 1
     if stride == 2:
-        x = scratch(("s2d", tag), (4 * B, H // 2, W // 2, Cin), x.dtype, x.device)  # filled by the forward pass
+        x = scratch(("s2d", x.data_ptr(), Cin), (4 * B, H // 2, W // 2, Cin), x.dtype, x.device)  # filled by the forward pass
         planes = 4
     dh, dw, pl = _taps(k, stride, pad)
     if zero:
@@ -193,8 +199,10 @@ def bn_fwd(x, y, res, gamma, beta, rm, rv, stats, mean_rstd, count, eps, momentu
                 stats = scratch(("bnstats", mean_rstd.data_ptr()), (1, 2, C), torch.float32, x.device)
                 stats.zero_()
             e.channel_stats(x, stats)
-        e.bn_finalize(stats if stats is not None else mean_rstd, mean_rstd, rm, rv, float(count), float(eps), float(momentum), bool(train))
-        e.bn_apply(x, res, y, gamma, beta, mean_rstd, bool(relu))
+        # mean / rstd are derived inside bn_apply from the raw sums (training) or the running statistics (evaluation): no
+        # separate finalize launch; CTA 0 stores mean/rstd for the backward pass and updates the running statistics
+        e.bn_apply(x, res, y, gamma, beta, mean_rstd, bool(relu), 1 if train else 2, stats if train else None, float(count), float(eps),
+                   float(momentum), rm, rv)
         return
     xf = x.float().reshape(-1, C)
     if train:
