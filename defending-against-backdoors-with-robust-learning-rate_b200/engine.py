@@ -60,7 +60,8 @@ class FLEngine:
             for _id in range(args.num_agents):
                 self.agents.append(Agent(_id, args, seed=args.seed))
         else:
-            groups = distribute_data(self.train_dataset, args, n_classes=self.n_classes)
+            groups = distribute_data(self.train_dataset, args, n_classes=self.n_classes,
+                                     class_per_agent=getattr(args, "class_per_agent", 10))
             for _id in range(args.num_agents):
                 self.agents.append(Agent(_id, args, self.train_dataset, groups[_id], seed=args.seed))
         for a in self.agents:

@@ -24,6 +24,7 @@ _ext_err = None
 _lock = threading.Lock()
 
 MODE_IDS = {"avg": 0, "comed": 1, "sign": 2}
+MAX_FUSED_AGENTS = 128   # kMaxAgents of ops/csrc/aggregate.cu
 
 
 class _Counter:
@@ -227,6 +228,21 @@ def fused_aggregate(w_global, w_agents, weights, mode="avg", theta=0, server_lr=
             flipped += nflip
         return out
     dev = w_global.device
+    if len(w_agents) > MAX_FUSED_AGENTS:
+        # more participants than the kernel's per-coordinate register/local-memory budget: exact torch evaluation on the device
+        # (fp64, same semantics; only reached by very large --num_agents * --agent_frac)
+        noise = None
+        if noise_std > 0:
+            gen = torch.Generator(device=dev).manual_seed(int(seed) * 1000003 + int(noise_stream))
+            noise = torch.randn(n, generator=gen, dtype=torch.float64, device=dev) * noise_std
+            noise[n_vote:] = 0
+        new, nflip = aggregate_oracle(w_global, w_agents, weights, mode, theta, server_lr, noise, n_vote, scales)
+        out.copy_(new)
+        if out_bf16 is not None:
+            out_bf16.copy_(new.to(torch.bfloat16))
+        if flipped is not None:
+            flipped += nflip
+        return out
     assert n % 4 == 0 and n_vote % 4 == 0, "flat buffers are padded to multiples of 4"
     for w in w_agents:
         assert w.is_cuda and w.dtype == torch.float32 and w.is_contiguous() and w.numel() == n

@@ -56,6 +56,9 @@ def build_parser() -> argparse.ArgumentParser:
                    help="aggregation transport: fused = P2P/multicast sm_100a kernel; nccl/gloo = all_gather + kernel")
     p.add_argument("--trainer", type=str, default="auto", choices=("auto", "native", "torch"),
                    help="local-training executor: native = sm_100a kernels, torch = autograd oracle (CPU / baseline)")
+    p.add_argument("--class_per_agent", type=int, default=10,
+                   help="classes per agent in the partitioner (10 = IID like the reference's calls; fewer = label-skewed non-IID; "
+                        "reference distribute_data parameter, src/utils.py:58)")
     p.add_argument("--synthetic", type=int, default=0, help=">0: use a synthetic dataset with this many training samples")
     p.add_argument("--synthetic_val", type=int, default=0, help="synthetic validation-set size (default train/5)")
     p.add_argument("--data_dir", type=str, default="../data", help="dataset root (reference: '../data', src/utils.py:98)")

@@ -87,7 +87,7 @@ class FusedAggregator:
         n_part = len(weights)
         ctx, dev = self.ctx, self.ctx.device
         self.flipped.zero_()
-        if self.backend == "fused" and ctx.is_dist:
+        if self.backend == "fused" and ctx.is_dist and n_part <= ops.MAX_FUSED_AGENTS:
             self.epoch += 1
             wt = torch.as_tensor(weights, dtype=torch.float64).to(dev)
             sc = torch.as_tensor(scales, dtype=torch.float32).to(dev) if scales is not None else None

@@ -124,3 +124,16 @@ def test_property_oracle_invariants(K, theta, seed, aggr):
     assert nflip == (int((s < theta).sum()) if theta > 0 else 0)
     if theta > K:  # unreachable threshold: every coordinate is flipped
         assert nflip == n
+
+
+def test_more_participants_than_the_kernel_limit_uses_exact_fallback():
+    K, n = ops.MAX_FUSED_AGENTS + 22, 512
+    w0, ws = _mk(K, n, seed=9)
+    wt = [1.0 + (i % 3) for i in range(K)]
+    for mode in ("avg", "comed", "sign"):
+        ref, nflip = ops.aggregate_oracle(w0, ws, wt, mode, 40, 1.0)
+        out = torch.empty_like(w0)
+        flipped = torch.zeros(1, dtype=torch.int64)
+        ops.fused_aggregate(w0, ws, wt, mode, 40, 1.0, out=out, flipped=flipped)
+        torch.testing.assert_close(out, ref)
+        assert int(flipped) == nflip

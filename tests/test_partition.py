@@ -46,3 +46,12 @@ class _Wrap:
 
     def __len__(self):
         return len(self.targets)
+
+
+def test_class_per_agent_flag_reaches_the_engine():
+    from rlr_b200.engine import FLEngine
+    from rlr_b200.options import make_args
+    eng = FLEngine(make_args(data="fmnist", synthetic=2000, synthetic_val=100, num_agents=10, class_per_agent=2, log_dir="", device="cpu"),
+                   verbose=False)
+    for a in eng.agents:
+        assert len(torch.unique(eng.train_dataset.targets[a.idxs])) <= 2
