@@ -1,0 +1,42 @@
+"""The command-line entry points run as the reference's would (``python federated.py --flags``), on CPU."""
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(args, timeout=300):
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    return subprocess.run([sys.executable, *args], cwd=ROOT, env=env, capture_output=True, text=True, timeout=timeout)
+
+
+def test_federated_py_reference_style_command_line(tmp_path):
+    r = _run(["federated.py", "--data=fmnist", "--local_ep=1", "--bs=64", "--num_agents=3", "--rounds=2", "--num_corrupt=1",
+              "--poison_frac=0.5", "--robustLR_threshold=2", "--synthetic=300", "--synthetic_val=60", f"--log_dir={tmp_path}",
+              "--no_tensorboard", "--device=cpu"])
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "| Val_Loss/Val_Acc:" in r.stdout and "| Poison Loss/Poison Acc:" in r.stdout and "Training has finished!" in r.stdout
+    assert "Aggregation Function: avg" in r.stdout and "RobustLR_threshold: 2" in r.stdout
+
+
+def test_module_entry_point_and_help():
+    r = _run(["-m", "rlr_b200.federated", "--help"])
+    assert r.returncode == 0
+    for flag in ["--data", "--num_agents", "--agent_frac", "--num_corrupt", "--rounds", "--aggr", "--local_ep", "--bs", "--client_lr",
+                 "--client_moment", "--server_lr", "--base_class", "--target_class", "--poison_frac", "--pattern_type",
+                 "--robustLR_threshold", "--clip", "--noise", "--top_frac", "--snap", "--device", "--num_workers"]:
+        assert flag in r.stdout, flag
+
+
+def test_runner_script_is_valid_bash_and_lists_the_reference_experiments():
+    path = os.path.join(ROOT, "scripts", "runner.sh")
+    assert subprocess.run(["bash", "-n", path]).returncode == 0
+    txt = open(path).read()
+    assert txt.count("$RUN --data=fmnist") == 3 and txt.count("$RUN --data=fedemnist") == 3 and "--num_agents=3383" in txt
+
+
+def test_bench_reference_arm_reports_unavailable_or_runs_without_gpu():
+    r = _run(["bench.py", "--impl", "reference", "--steps", "1", "--warmup", "1"])
+    assert r.returncode == 0, r.stderr[-1000:]
+    assert '"impl": "reference"' in r.stdout
