@@ -33,7 +33,15 @@ def test_runner_script_is_valid_bash_and_lists_the_reference_experiments():
     path = os.path.join(ROOT, "scripts", "runner.sh")
     assert subprocess.run(["bash", "-n", path]).returncode == 0
     txt = open(path).read()
-    assert txt.count("$RUN --data=fmnist") == 3 and txt.count("$RUN --data=fedemnist") == 3 and "--num_agents=3383" in txt
+    for frag in ("--data=fmnist --local_ep=2 --bs=256 --num_agents=10 --rounds=200", "--num_agents=40", "--num_agents=3383 --agent_frac=0.01",
+                 "[fmnist]=4 [cifar10]=8 [fedemnist]=8", "--model=resnet18", "--model=vgg11 --aggr=comed"):
+        assert frag in txt, frag
+    # dry run: replace the launcher by `echo` and check the 3 x 3 + 2 command lines it generates
+    dry = subprocess.run(["bash", "-c", f"sed 's/^  *python /  echo python /' {path} | sed 's/^rm -rf logs.*//' | bash -s 1"],
+                         capture_output=True, text=True, cwd=ROOT)
+    cmds = [l for l in dry.stdout.splitlines() if l.startswith("python federated.py")]
+    assert len(cmds) == 11, dry.stdout + dry.stderr
+    assert sum("--robustLR_threshold" in c for c in cmds) == 4 and sum("--data=fedemnist" in c for c in cmds) == 3
 
 
 def test_bench_reference_arm_reports_unavailable_or_runs_without_gpu():
