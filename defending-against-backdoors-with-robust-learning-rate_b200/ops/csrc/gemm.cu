@@ -278,9 +278,30 @@ cudaError_t make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const u
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
+// gemm_persistent.cu (opt-in, RLR_PERSISTENT_CONV=1): one CTA per SM looping over tiles, double-buffered TMEM accumulators
+template <int BN>
+cudaError_t launch_persistent_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, int m_tiles, int num_sms,
+                                 cudaStream_t st);
+
+static int g_persistent = -1;   // -1: take RLR_PERSISTENT_CONV from the environment on first use
+void set_persistent_conv(int on) { g_persistent = on ? 1 : 0; }
+
+static int persistent_sms() {
+    if (g_persistent < 0) { const char* e = getenv("RLR_PERSISTENT_CONV"); g_persistent = (e && atoi(e) > 0) ? 1 : 0; }
+    if (!g_persistent) return 0;
+    static const int sms = [] {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+        return n;
+    }();
+    return sms;
+}
+
 template <int BN>
 static cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, int m_tiles, cudaStream_t st) {
     using Cfg = TileCfg<BN>;
+    if (!p.stats && persistent_sms() > 0 && m_tiles * ((p.N + BN - 1) / BN) > persistent_sms())
+        return launch_persistent_bn<BN>(tmA, tmB, p, m_tiles, persistent_sms(), st);
     static bool configured = false;
     if (!configured) {
         RLR_CUDA_CHECK(cudaFuncSetAttribute(umma_conv_gemm_kernel<BN, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));

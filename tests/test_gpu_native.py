@@ -304,3 +304,46 @@ def test_streaming_mode_after_resident_rounds_uses_valid_indices():
     torch.cuda.synchronize()
     assert loss == loss and eng.evaluate(3)["val_acc"] > 0.2
     eng.close()
+
+
+PERSIST_CASES = [  # B, H, W, Cin, Cout, k, stride, pad  (all with more output tiles than SMs)
+    (128, 32, 32, 64, 128, 3, 2, 1), (128, 16, 16, 128, 128, 3, 1, 1), (128, 16, 16, 128, 256, 1, 2, 0), (256, 8, 8, 256, 256, 3, 1, 1),
+    (256, 32, 32, 3, 64, 3, 1, 1), (96, 15, 15, 64, 128, 3, 1, 0),
+]
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,s,p", PERSIST_CASES)
+def test_persistent_conv_matches_default(B, H, W, Cin, Cout, k, s, p):
+    """Opt-in persistent tile scheduler (gemm_persistent.cu): same MMAs in the same order per tile -> bit-identical to the
+    default kernel for forward (bias+ReLU), data gradient (overwrite and accumulate) and the plain GEMM."""
+    torch.manual_seed(B + H + Cin)
+    x = torch.randn(B, H, W, Cin, device=DEV).to(BF)
+    w = (torch.randn(Cout, k, k, Cin, device=DEV) / (k * k * Cin) ** 0.5).to(BF)
+    bias = torch.randn(Cout, device=DEV) * 0.1
+    Ho, Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    dy = torch.randn(B, Ho, Wo, Cout, device=DEV).to(BF)
+    base = torch.randn(B, H, W, Cin, device=DEV).to(BF)
+    A = torch.randn(B * 64, 512, device=DEV).to(BF)
+    Bm = (torch.randn(256, 512, device=DEV) / 16).to(BF)
+    outs = {}
+    try:
+        for on in (False, True):
+            ops.ext().set_persistent_conv(on)
+            y = torch.full((B, Ho, Wo, Cout), 7.0, device=DEV, dtype=BF)
+            ops.conv2d_fwd_sm100(x, w, bias, y, s, p, True, None, tag=("persist", on, B, H, Cin, k, s))
+            dx0 = torch.full_like(base, 3.0)
+            dx1 = base.clone()
+            if Cin % 64 == 0:
+                ops.conv2d_dgrad_sm100(dy, w, dx0, s, p, False)
+                ops.conv2d_dgrad_sm100(dy, w, dx1, s, p, True)
+            g = torch.empty(A.shape[0], 256, device=DEV, dtype=BF)
+            ops.ext().gemm_bf16(A, Bm, g, None, False, False, None)
+            torch.cuda.synchronize()
+            outs[on] = (y, dx0, dx1, g)
+    finally:
+        ops.ext().set_persistent_conv(False)
+    ref = F.relu(F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), bias, s, p)).permute(0, 2, 3, 1)
+    assert _rel(outs[True][0], ref) < 1e-2
+    assert _rel(outs[True][3], A.float() @ Bm.float().t()) < 1e-2
+    for a, b in zip(outs[False], outs[True]):
+        assert torch.equal(a, b)
