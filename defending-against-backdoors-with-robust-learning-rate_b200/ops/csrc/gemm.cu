@@ -32,9 +32,9 @@ constexpr int BK = 64;
 constexpr int kThreads = 192;
 constexpr int kEpiThreads = 128;
 
-template <int BN>
+template <int BN, int kOcc = 2>
 struct TileCfg {
-    static constexpr int kStages = BN == 64 ? 4 : 3;
+    static constexpr int kStages = (BN == 64 && kOcc == 2) ? 4 : 3;   // kOcc = 3 (BN = 64 only): 3 x 24 KB ring, three CTAs per SM
     static constexpr int kABytes = BM * BK * 2;
     static constexpr int kBBytes = BN * BK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
@@ -54,10 +54,10 @@ struct __align__(8) SharedTail {
     int row_index[BM];   // global output row of each tile row, -1 = masked
 };
 
-template <int BN, bool kStats, bool kBMN>
-__global__ void __launch_bounds__(kThreads, 2)
+template <int BN, bool kStats, bool kBMN, int kOcc = 2>
+__global__ void __launch_bounds__(kThreads, kOcc)
 umma_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvGemmParams p) {
-    using Cfg = TileCfg<BN>;
+    using Cfg = TileCfg<BN, kOcc>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     SharedTail* tail = reinterpret_cast<SharedTail*>(smem + Cfg::kRingBytes);
@@ -283,6 +283,28 @@ template <int BN>
 cudaError_t launch_persistent_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, int m_tiles, int num_sms,
                                  cudaStream_t st);
 
+static int g_occ3 = -1;         // -1: take RLR_CONV_OCC3 from the environment on first use (unset = on)
+void set_conv_occ3(int on) { g_occ3 = on ? 1 : 0; }
+static bool conv_occ3() {
+    if (g_occ3 < 0) { const char* e = getenv("RLR_CONV_OCC3"); g_occ3 = (!e || atoi(e) > 0) ? 1 : 0; }   // default on: -1.4 % / round
+    return g_occ3 == 1;
+}
+
+// default (RLR_CONV_OCC3=0 disables): 64-wide tiles with a 3-stage ring at three CTAs per SM (three TMA producers / MMA issue threads per SM)
+static cudaError_t launch_bn64_occ3(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, int m_tiles, cudaStream_t st) {
+    using Cfg = TileCfg<64, 3>;
+    static bool configured = false;
+    if (!configured) {
+        RLR_CUDA_CHECK(cudaFuncSetAttribute(umma_conv_gemm_kernel<64, false, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        RLR_CUDA_CHECK(cudaFuncSetAttribute(umma_conv_gemm_kernel<64, false, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        configured = true;
+    }
+    dim3 grid(m_tiles, (p.N + 63) / 64);
+    if (p.b_mn) umma_conv_gemm_kernel<64, false, true, 3><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
+    else umma_conv_gemm_kernel<64, false, false, 3><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
+    return cudaGetLastError();
+}
+
 static int g_persistent = -1;   // -1: take RLR_PERSISTENT_CONV from the environment on first use
 void set_persistent_conv(int on) { g_persistent = on ? 1 : 0; }
 
@@ -302,6 +324,7 @@ static cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, con
     using Cfg = TileCfg<BN>;
     if (!p.stats && persistent_sms() > 0 && m_tiles * ((p.N + BN - 1) / BN) > persistent_sms())
         return launch_persistent_bn<BN>(tmA, tmB, p, m_tiles, persistent_sms(), st);
+    if (BN == 64 && !p.stats && conv_occ3()) return launch_bn64_occ3(tmA, tmB, p, m_tiles, st);
     static bool configured = false;
     if (!configured) {
         RLR_CUDA_CHECK(cudaFuncSetAttribute(umma_conv_gemm_kernel<BN, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));

@@ -314,8 +314,9 @@ PERSIST_CASES = [  # B, H, W, Cin, Cout, k, stride, pad  (all with more output t
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout,k,s,p", PERSIST_CASES)
 def test_persistent_conv_matches_default(B, H, W, Cin, Cout, k, s, p):
-    """Opt-in persistent tile scheduler (gemm_persistent.cu): same MMAs in the same order per tile -> bit-identical to the
-    default kernel for forward (bias+ReLU), data gradient (overwrite and accumulate) and the plain GEMM."""
+    """Opt-in schedulers of the generic conv kernel -- persistent tiles (gemm_persistent.cu) and the 3-CTAs-per-SM 64-wide
+    variant: same MMAs in the same order per tile -> bit-identical to the default kernel for forward (bias+ReLU), data
+    gradient (overwrite and accumulate) and the plain GEMM."""
     torch.manual_seed(B + H + Cin)
     x = torch.randn(B, H, W, Cin, device=DEV).to(BF)
     w = (torch.randn(Cout, k, k, Cin, device=DEV) / (k * k * Cin) ** 0.5).to(BF)
@@ -327,8 +328,9 @@ def test_persistent_conv_matches_default(B, H, W, Cin, Cout, k, s, p):
     Bm = (torch.randn(256, 512, device=DEV) / 16).to(BF)
     outs = {}
     try:
-        for on in (False, True):
-            ops.ext().set_persistent_conv(on)
+        for on in (False, True, "occ3"):
+            ops.ext().set_persistent_conv(on is True)
+            ops.ext().set_conv_occ3(on == "occ3")
             y = torch.full((B, Ho, Wo, Cout), 7.0, device=DEV, dtype=BF)
             ops.conv2d_fwd_sm100(x, w, bias, y, s, p, True, None, tag=("persist", on, B, H, Cin, k, s))
             dx0 = torch.full_like(base, 3.0)
@@ -342,8 +344,10 @@ def test_persistent_conv_matches_default(B, H, W, Cin, Cout, k, s, p):
             outs[on] = (y, dx0, dx1, g)
     finally:
         ops.ext().set_persistent_conv(False)
+        ops.ext().set_conv_occ3(False)
     ref = F.relu(F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), bias, s, p)).permute(0, 2, 3, 1)
     assert _rel(outs[True][0], ref) < 1e-2
     assert _rel(outs[True][3], A.float() @ Bm.float().t()) < 1e-2
-    for a, b in zip(outs[False], outs[True]):
-        assert torch.equal(a, b)
+    for mode in (True, "occ3"):
+        for a, b in zip(outs[False], outs[mode]):
+            assert torch.equal(a, b), mode
