@@ -13,7 +13,7 @@ import random
 import torch
 
 from .data import DatasetSplit, poison_dataset
-from .data.datasets import load_fedemnist_client
+from .data.datasets import h5_to_device_dataset, load_fedemnist_client
 
 
 class Agent:
@@ -25,7 +25,7 @@ class Agent:
         rng = random.Random(1_000_003 * (seed + 1) + id)
         if train_dataset is None:
             # Fed-EMNIST: one pre-partitioned file per client (src/agent.py:16-20)
-            shard = load_fedemnist_client(args.data_dir, id).as_device_dataset(args.device)
+            shard = h5_to_device_dataset(load_fedemnist_client(args.data_dir, id), args.device)
             self.dataset = shard
             self.idxs = torch.arange(len(shard), device=shard.device)
             if self.is_corrupt:

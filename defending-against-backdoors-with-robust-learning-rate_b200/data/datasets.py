@@ -160,8 +160,15 @@ class H5Dataset:
         return self.inputs[item], self.targets[item]
 
     def as_device_dataset(self, device="cpu") -> DeviceDataset:
-        x = self.inputs.to(torch.float32).reshape(len(self), 28, 28, 1)
-        return DeviceDataset("fedemnist", x.to(device), self.targets.to(device))
+        return h5_to_device_dataset(self, device)
+
+
+def h5_to_device_dataset(obj, device="cpu") -> DeviceDataset:
+    """Engine representation of any Fed-EMNIST container with ``inputs`` [N,1,28,28] float and ``targets`` -- ours or an
+    unpickled instance of the reference's own ``utils.H5Dataset`` (when that module is importable, pickle resolves to it)."""
+    n = int(obj.targets.shape[0])
+    x = torch.as_tensor(obj.inputs).to(torch.float32).reshape(n, 28, 28, 1)
+    return DeviceDataset("fedemnist", x.to(device), torch.as_tensor(obj.targets).to(torch.int64).to(device))
 
 
 def _install_unpickle_shim():
@@ -238,7 +245,7 @@ def get_datasets(data: str, data_dir: str = "../data", synthetic: int = 0, synth
         _install_unpickle_shim()
         tr = torch.load(os.path.join(data_dir, "Fed_EMNIST", "fed_emnist_all_trainset.pt"), weights_only=False)
         te = torch.load(os.path.join(data_dir, "Fed_EMNIST", "fed_emnist_all_valset.pt"), weights_only=False)
-        return tr.as_device_dataset(device), te.as_device_dataset(device)
+        return h5_to_device_dataset(tr, device), h5_to_device_dataset(te, device)
     try:
         (xtr, ytr), (xte, yte) = _load_torchvision(data, data_dir)
     except Exception as e:  # noqa: BLE001 - any failure means "not on disk"

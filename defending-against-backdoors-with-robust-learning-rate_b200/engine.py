@@ -26,6 +26,7 @@ from . import ops
 from .agent import Agent
 from .aggregation import Aggregation
 from .data import distribute_data, get_datasets, make_poisoned_val
+from .data.datasets import DeviceDataset, h5_to_device_dataset, load_fedemnist_client
 from .models import get_layout
 from .options import print_exp_details
 from .parallel import FusedAggregator, init_distributed
@@ -57,8 +58,16 @@ class FLEngine:
         # ---- agents (src/federated.py:49-56) --------------------------------------------------------------------
         self.agents, self.agent_data_sizes = [], {}
         if args.data == "fedemnist" and not args.synthetic:
-            for _id in range(args.num_agents):
-                self.agents.append(Agent(_id, args, seed=args.seed))
+            # One pre-partitioned file per client (src/agent.py:16-20).  The shards are concatenated into ONE device-resident
+            # dataset and every agent gets its index range, so all clients share the trainer's CUDA graphs (keyed by dataset).
+            shards = [h5_to_device_dataset(load_fedemnist_client(args.data_dir, _id), "cpu") for _id in range(args.num_agents)]
+            self.train_dataset = DeviceDataset("fedemnist", torch.cat([s.data for s in shards]).to(dev),
+                                               torch.cat([s.targets for s in shards]).to(dev))
+            off = 0
+            for _id, s in enumerate(shards):
+                self.agents.append(Agent(_id, args, self.train_dataset, range(off, off + len(s)), seed=args.seed))
+                off += len(s)
+            del shards
         else:
             groups = distribute_data(self.train_dataset, args, n_classes=self.n_classes,
                                      class_per_agent=getattr(args, "class_per_agent", 10))
