@@ -26,7 +26,7 @@ namespace rlr {
 using namespace umma;
 
 cudaError_t make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                           const uint32_t* box);  // gemm.cu
+                           const uint32_t* box, const uint32_t* elem_strides = nullptr);  // gemm.cu
 
 constexpr int HL_THREADS = 192;
 constexpr int HL_TH = 16, HL_TW = 8;                  // output tile: 16 rows x 8 cols = 128 pixels

@@ -90,7 +90,7 @@ umma_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         if (p.mode == 1) {
             const int tw = r % p.TW, th = (r / p.TW) % p.TH, tn = r / (p.TW * p.TH);
             const int w = w0 + tw, h = h0 + th, n = n0 + tn;
-            gi = (w < p.Wo && h < p.Ho && n < p.NB) ? ((n * p.Ho + h) * p.Wo + w) : -1;
+            gi = (w < p.Wo && h < p.Ho && n < p.NB) ? ((n * p.OutH + h * p.out_stride + p.out_ph) * p.OutW + w * p.out_stride + p.out_pw) : -1;
         } else {
             gi = tile_m * BM + r;
             if (gi >= p.M) gi = -1;
@@ -114,7 +114,8 @@ umma_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 mbar_expect_tx(&tail->full[stage], Cfg::kStageBytes);
                 if (p.mode == 1) {
                     const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
-                    tma_load_4d(&tmA, &tail->full[stage], sa, cb * BK, w0 + p.dw[tap], h0 + p.dh[tap], n0 + p.dn[tap]);
+                    tma_load_4d(&tmA, &tail->full[stage], sa, cb * BK, w0 * p.in_stride + p.dw[tap], h0 * p.in_stride + p.dh[tap],
+                                n0 + p.dn[tap]);
                 } else {
                     tma_load_2d(&tmA, &tail->full[stage], sa, kb * BK, tile_m * BM);
                 }
@@ -264,13 +265,21 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // bf16 tensor of `rank` dims (innermost first), 128-byte swizzle, zero fill out of bounds.
+// `elem_strides` (optional, per dimension, 1..8): traversal stride -- the box then covers box[i] * stride elements of dimension i
+// and TMA loads every stride-th one (box[i] elements land in shared memory).  Used for stride-2 convolutions without a
+// parity-split copy of the input.
 cudaError_t make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                           const uint32_t* box) {
+                           const uint32_t* box, const uint32_t* elem_strides = nullptr) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return cudaErrorNotSupported;
     cuuint64_t gd[5], gs[4];
     cuuint32_t bx[5], es[5];
-    for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i < rank; ++i) {
+        gd[i] = dims[i];
+        es[i] = elem_strides ? elem_strides[i] : 1;
+        bx[i] = box[i] * es[i];       // "to load N elements along dimension i, boxDim[i] must be N * elementStrides[i]"
+        if (bx[i] > 256 || es[i] < 1 || es[i] > 8) return cudaErrorInvalidValue;
+    }
     for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
     const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -358,7 +367,7 @@ cudaError_t launch_gemm_bf16(const void* A, const void* B, void* out, int M, int
         RLR_CUDA_CHECK(make_tmap_bf16(&tmB, B, 2, d, s, b));
     }
     ConvGemmParams p{};
-    p.M = M; p.N = N; p.num_kb = K / BK; p.mode = 0;
+    p.M = M; p.N = N; p.num_kb = K / BK; p.mode = 0; p.in_stride = 1; p.out_stride = 1;
     p.out = out; p.ldc = ldc; p.bias = bias; p.stats = stats; p.relu = relu; p.accumulate = accumulate;
     const int m_tiles = (M + BM - 1) / BM;
     return bn == 128 ? launch_bn<128>(tmA, tmB, p, m_tiles, st) : launch_bn<64>(tmA, tmB, p, m_tiles, st);
@@ -370,8 +379,10 @@ static int pow2_ceil(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 // `w` is [Cout][ntaps*Cin] bf16 (tap-major K), out is [NB*Ho*Wo][ldc] bf16.  Taps are given as input offsets.
 cudaError_t launch_conv_bf16(const void* x, const void* w, void* out, int NB, int planes, int Hin, int Win, int Cin, int Ho, int Wo,
                              int Cout, int ldc, int ntaps, const int* dh, const int* dw, const int* dplane, const float* bias,
-                             int relu, int accumulate, float* stats, cudaStream_t st, const int* wtap, int w_taps_total) {
+                             int relu, int accumulate, float* stats, cudaStream_t st, const int* wtap, int w_taps_total,
+                             int in_stride, int out_stride, int out_ph, int out_pw) {
     if (Cin % BK || Cout % 8 || ntaps < 1 || ntaps > 9) return cudaErrorInvalidValue;
+    if (in_stride < 1 || in_stride > 2 || out_stride < 1 || out_stride > 2 || (in_stride > 1 && planes != 1)) return cudaErrorInvalidValue;
     if (wtap && (stats || Cout % 64)) return cudaErrorInvalidValue;   // MN-major filter path: whole 64-wide ci groups, no statistics
     int bn = pick_bn(Cout);
     ConvGemmParams p{};
@@ -390,6 +401,9 @@ cudaError_t launch_conv_bf16(const void* x, const void* w, void* out, int NB, in
     const int m_tiles = p.tiles_w * p.tiles_h * tiles_n;
     p.M = NB * Ho * Wo; p.N = Cout; p.mode = 1; p.cblocks = Cin / BK; p.num_kb = ntaps * p.cblocks; p.ntaps = ntaps;
     p.Ho = Ho; p.Wo = Wo; p.NB = NB;
+    // Ho x Wo is the logical output grid; it is stored into an image of (out_stride * Ho) x (out_stride * Wo) pixels at parity
+    // (out_ph, out_pw) -- stride-2 data gradients write their four parity planes straight into dX
+    p.in_stride = in_stride; p.out_stride = out_stride; p.out_ph = out_ph; p.out_pw = out_pw; p.OutH = Ho * out_stride; p.OutW = Wo * out_stride;
     for (int t = 0; t < ntaps; ++t) { p.dh[t] = (int8_t)dh[t]; p.dw[t] = (int8_t)dw[t]; p.dn[t] = dplane[t] * NB; }
     p.out = out; p.ldc = ldc; p.bias = bias; p.stats = stats; p.relu = relu; p.accumulate = accumulate;
     CUtensorMap tmA, tmB;
@@ -397,7 +411,8 @@ cudaError_t launch_conv_bf16(const void* x, const void* w, void* out, int NB, in
         const uint64_t d[4] = {(uint64_t)Cin, (uint64_t)Win, (uint64_t)Hin, (uint64_t)planes * NB};
         const uint64_t s[3] = {(uint64_t)Cin * 2, (uint64_t)Win * Cin * 2, (uint64_t)Hin * Win * Cin * 2};
         const uint32_t b[4] = {BK, (uint32_t)TW, (uint32_t)TH, (uint32_t)TN};
-        RLR_CUDA_CHECK(make_tmap_bf16(&tmA, x, 4, d, s, b));
+        const uint32_t es[4] = {1, (uint32_t)in_stride, (uint32_t)in_stride, 1};
+        RLR_CUDA_CHECK(make_tmap_bf16(&tmA, x, 4, d, s, b, in_stride > 1 ? es : nullptr));
     }
     if (wtap) {
         // data gradient on the un-transposed filter: w is the forward filter [K = Cin of this call][w_taps_total * Cout of this call]

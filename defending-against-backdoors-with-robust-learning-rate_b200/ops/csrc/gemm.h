@@ -19,6 +19,8 @@ struct ConvGemmParams {
     int Ho, Wo, NB;
     int tiles_w, tiles_h;
     int ntaps;
+    int in_stride;             // input pixel of output pixel o and tap t is in_stride * o + d[t]: 2 = strided TMA box (element strides)
+    int out_stride, out_ph, out_pw, OutH, OutW;   // output pixel (h, w) of the Ho x Wo grid is stored at (out_stride*h + out_ph, ...)
     int8_t dh[9], dw[9];       // per tap: input row / col offset relative to the output pixel (in plane coordinates)
     int dn[9];                 // per tap: image offset (parity plane * NB) for strided convs
     int b_mn;                  // 1: B operand is read MN-major straight from the un-transposed filter (data gradients)
@@ -39,7 +41,8 @@ void set_persistent_conv(int on);
 void set_conv_occ3(int on);
 cudaError_t launch_conv_bf16(const void* x, const void* w, void* out, int NB, int planes, int Hin, int Win, int Cin, int Ho, int Wo,
                              int Cout, int ldc, int ntaps, const int* dh, const int* dw, const int* dplane, const float* bias,
-                             int relu, int accumulate, float* stats, cudaStream_t st, const int* wtap = nullptr, int w_taps_total = 0);
+                             int relu, int accumulate, float* stats, cudaStream_t st, const int* wtap = nullptr, int w_taps_total = 0,
+                             int in_stride = 1, int out_stride = 1, int out_ph = 0, int out_pw = 0);
 
 // ---- conv_halo.cu: persistent 3x3/s1/p1 conv for 64 input channels with smem halo reuse + resident filter ------------------
 cudaError_t launch_conv3x3_halo_bf16(const void* x, const void* w, void* out, int NB, int H, int W, int Cout, const float* bias, int relu,
@@ -48,7 +51,7 @@ cudaError_t launch_conv3x3_halo_bf16(const void* x, const void* w, void* out, in
 // ---- wgrad.cu: MN-major tcgen05 weight gradients (fp32, accumulated with red.add) -----------------------------------
 cudaError_t launch_conv_wgrad_bf16(const void* dy, const void* x, float* dW, int NB, int planes, int Hin, int Win, int Cin, int Cin_valid,
                                    int Ho, int Wo, int Cout, int ntaps, const int* dh, const int* dw, const int* dplane, int num_sms,
-                                   cudaStream_t st);
+                                   cudaStream_t st, int in_stride = 1);
 cudaError_t launch_conv_wgrad_halo_bf16(const void* dy, const void* x, float* dW, int NB, int H, int W, int Cin_valid, int Cout,
                                         int num_sms, cudaStream_t st);
 cudaError_t launch_linear_wgrad_bf16(const void* dy, const void* x, float* dW, int B, int N, int K, int num_sms, cudaStream_t st);

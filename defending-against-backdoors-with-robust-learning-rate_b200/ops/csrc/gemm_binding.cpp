@@ -56,6 +56,29 @@ void conv_bf16(at::Tensor x, at::Tensor w, at::Tensor out, int64_t NB, int64_t p
                                 (int)w_taps_total), "conv_bf16");
 }
 
+// Strided variant without parity-split copies: x [NB,Hin,Win,Cin] is the ORIGINAL input, read through a TMA box with element
+// strides (in_stride, 2 for stride-2 forward convs); `out` [NB,OutH,OutW,Cout] is the FULL output image and this launch fills the
+// pixels (out_stride*h + out_ph, out_stride*w + out_pw) of it (out_stride 2 = one parity plane of a stride-2 data gradient).
+// Tap offsets dh/dw are in input pixels relative to in_stride * (output grid coordinate).
+void conv_bf16_strided(at::Tensor x, at::Tensor w, at::Tensor out, std::vector<int64_t> dh, std::vector<int64_t> dw,
+                       c10::optional<at::Tensor> bias, bool relu, bool accumulate, std::vector<int64_t> wtap, int64_t w_taps_total,
+                       int64_t in_stride, int64_t out_stride, int64_t out_ph, int64_t out_pw) {
+    c10::cuda::CUDAGuard g(x.device());
+    TORCH_CHECK(x.dim() == 4 && out.dim() == 4 && w.dim() == 2 && x.size(0) == out.size(0));
+    TORCH_CHECK(out.size(1) % out_stride == 0 && out.size(2) % out_stride == 0, "output image must be a multiple of out_stride");
+    const int NB = x.size(0), Hin = x.size(1), Win = x.size(2), Cin = x.size(3), Cout = out.size(3);
+    const int Ho = out.size(1) / out_stride, Wo = out.size(2) / out_stride;
+    const int T = (int)dh.size();
+    const bool bmn = !wtap.empty();
+    TORCH_CHECK(bmn ? (w.size(0) == Cin && w.size(1) == w_taps_total * Cout && (int)wtap.size() == T)
+                    : (w.size(0) == Cout && w.size(1) == (int64_t)T * Cin), "filter shape");
+    int a[9], b[9], c[9] = {0}, wt[9];
+    for (int t = 0; t < T; ++t) { a[t] = (int)dh[t]; b[t] = (int)dw[t]; wt[t] = bmn ? (int)wtap[t] : 0; }
+    check(rlr::launch_conv_bf16(bf(x), bf(w), bfm(out), NB, 1, Hin, Win, Cin, Ho, Wo, Cout, Cout, T, a, b, c, opt<const float>(bias), relu,
+                                accumulate, nullptr, cur_stream(), bmn ? wt : nullptr, (int)w_taps_total, (int)in_stride, (int)out_stride,
+                                (int)out_ph, (int)out_pw), "conv_bf16_strided");
+}
+
 // x: [NB,H,W,64]; w: [Cout, 9*64]; out: [NB,H,W,Cout]   (3x3, stride 1, pad 1)
 void conv3x3_halo_bf16(at::Tensor x, at::Tensor w, at::Tensor out, c10::optional<at::Tensor> bias, bool relu, bool accumulate,
                        c10::optional<at::Tensor> stats, int64_t bo_mode, c10::optional<at::Tensor> dbg) {
@@ -80,6 +103,20 @@ void conv_wgrad_bf16(at::Tensor dy, at::Tensor x, at::Tensor dW, int64_t NB, int
     for (int t = 0; t < T; ++t) { a[t] = (int)dh[t]; b[t] = (int)dw[t]; c[t] = (int)dplane[t]; }
     check(rlr::launch_conv_wgrad_bf16(bf(dy), bf(x), f32(dW), (int)NB, (int)planes, Hin, Win, Cin, (int)cin_valid, Ho, Wo, Cout, T, a, b, c,
                                       num_sms(), cur_stream()), "conv_wgrad_bf16");
+}
+// stride-2 weight gradient on the ORIGINAL input x [NB,Hin,Win,Cin] (strided TMA box, no parity-split copy); dh/dw in input pixels
+void conv_wgrad_bf16_strided(at::Tensor dy, at::Tensor x, at::Tensor dW, int64_t cin_valid, std::vector<int64_t> dh, std::vector<int64_t> dw,
+                             int64_t in_stride) {
+    c10::cuda::CUDAGuard g(x.device());
+    TORCH_CHECK(x.dim() == 4 && dy.dim() == 4 && x.size(0) == dy.size(0));
+    const int NB = x.size(0), Hin = x.size(1), Win = x.size(2), Cin = x.size(3), Ho = dy.size(1), Wo = dy.size(2), Cout = dy.size(3);
+    const int T = (int)dh.size();
+    TORCH_CHECK(dW.numel() == (int64_t)Cout * T * cin_valid);
+    TORCH_CHECK((Cout <= 64 && Cout % 8 == 0) || Cout % 128 == 0, "wgrad: Cout must be <= 64 or a multiple of 128");
+    int a[9], b[9], c[9] = {0};
+    for (int t = 0; t < T; ++t) { a[t] = (int)dh[t]; b[t] = (int)dw[t]; }
+    check(rlr::launch_conv_wgrad_bf16(bf(dy), bf(x), f32(dW), NB, 1, Hin, Win, Cin, (int)cin_valid, Ho, Wo, Cout, T, a, b, c, num_sms(),
+                                      cur_stream(), (int)in_stride), "conv_wgrad_bf16_strided");
 }
 // 3x3/s1/p1 weight gradient with smem halo reuse: x [NB,H,W,64], dy [NB,H,W,Cout], dW [Cout,9,cin_valid]
 void conv_wgrad_halo_bf16(at::Tensor dy, at::Tensor x, at::Tensor dW, int64_t cin_valid) {
@@ -203,6 +240,8 @@ void register_gemm_bindings(py::module_& m) {
     m.def("set_conv_occ3", [](bool on) { rlr::set_conv_occ3(on ? 1 : 0); });
     m.def("gemm_bf16", &gemm_bf16);
     m.def("conv_bf16", &conv_bf16);
+    m.def("conv_bf16_strided", &conv_bf16_strided);
+    m.def("conv_wgrad_bf16_strided", &conv_wgrad_bf16_strided);
     m.def("conv3x3_halo_bf16", &conv3x3_halo_bf16);
     m.def("conv_wgrad_bf16", &conv_wgrad_bf16);
     m.def("linear_wgrad_bf16", &linear_wgrad_bf16);

@@ -86,7 +86,8 @@ umma_conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const 
                     uint8_t* sb = sa + Cfg::kABytes;
                     mbar_expect_tx(&sh->full[stage], Cfg::kStageBytes);
                     const int tap = p.mode == 1 ? kb / p.cblocks : 0, cb = p.mode == 1 ? kb - tap * p.cblocks : 0;
-                    if (p.mode == 1) tma_load_4d(&tmA, &sh->full[stage], sa, cb * PBK, w0 + p.dw[tap], h0 + p.dh[tap], n0 + p.dn[tap]);
+                    if (p.mode == 1) tma_load_4d(&tmA, &sh->full[stage], sa, cb * PBK, w0 * p.in_stride + p.dw[tap], h0 * p.in_stride + p.dh[tap],
+                                                n0 + p.dn[tap]);
                     else tma_load_2d(&tmA, &sh->full[stage], sa, kb * PBK, tile_m * PBM);
                     if (kBMN) {
                         for (int g = 0; g < BN / 64; ++g)
@@ -144,7 +145,8 @@ umma_conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const 
                 if (p.mode == 1) {
                     const int tw = row % p.TW, th = (row / p.TW) % p.TH, tn = row / (p.TW * p.TH);
                     const int w = w0 + tw, h = h0 + th, n = n0 + tn;
-                    gi = (w < p.Wo && h < p.Ho && n < p.NB) ? ((n * p.Ho + h) * p.Wo + w) : -1;
+                    gi = (w < p.Wo && h < p.Ho && n < p.NB)
+                             ? ((n * p.OutH + h * p.out_stride + p.out_ph) * p.OutW + w * p.out_stride + p.out_pw) : -1;
                 } else {
                     gi = tile_m * PBM + row;
                     if (gi >= p.M) gi = -1;

@@ -20,7 +20,7 @@ namespace rlr {
 using namespace umma;
 
 cudaError_t make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                           const uint32_t* box);  // gemm.cu
+                           const uint32_t* box, const uint32_t* elem_strides = nullptr);  // gemm.cu
 
 constexpr int WG_BM = 128, WG_BK = 64;                        // co tile, pixels per k-block
 constexpr int WG_STAGES = 3;
@@ -45,6 +45,7 @@ struct WgradParams {
     int TW, TH, TN, tiles_w, tiles_h;
     int8_t dh[9], dw[9];
     int dn[9];
+    int in_stride;            // 2: x is read through a strided TMA box (every other pixel), no parity-split copy
     int ci_tiles;
     int Cout, Cin_valid;      // rows / columns of dW that exist (Cin_valid < 64 for the channel-padded stem)
     float* dW;                // [Cout][T][Cin_valid] fp32 (accumulated)
@@ -110,7 +111,7 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     for (int t = 0; t < p.ntaps_cta; ++t)
                         for (int g = 0; g < Cfg::kGroups; ++g)
                             tma_load_4d(&tmB, &sh->full[stage], sb + t * WG_B_BYTES + g * 8192, ci_tile * WG_BN + g * 64,
-                                        w0 + p.dw[tap0 + t], h0 + p.dh[tap0 + t], n0 + p.dn[tap0 + t]);
+                                        w0 * p.in_stride + p.dw[tap0 + t], h0 * p.in_stride + p.dh[tap0 + t], n0 + p.dn[tap0 + t]);
                 } else {
                     for (int g = 0; g < p.a_groups; ++g)
                         tma_load_2d(&tmA, &sh->full[stage], sa + g * 8192, co_tile * WG_BM + g * 64, kb * WG_BK);
@@ -383,9 +384,11 @@ static int pow2_ceil_(int x) { int q = 1; while (q < x) q <<= 1; return q; }
 // dW[Cout][T][Cin_valid] += wgrad(dy[NB][Ho][Wo][Cout], x[planes*NB][Hin][Win][Cin])   (Cin multiple of 64)
 cudaError_t launch_conv_wgrad_bf16(const void* dy, const void* x, float* dW, int NB, int planes, int Hin, int Win, int Cin, int Cin_valid,
                                    int Ho, int Wo, int Cout, int ntaps, const int* dh, const int* dw, const int* dplane, int num_sms,
-                                   cudaStream_t st) {
+                                   cudaStream_t st, int in_stride) {
     if (Cin % 64 || Cout % 8 || (ntaps != 1 && ntaps != 9)) return cudaErrorInvalidValue;
+    if (in_stride < 1 || in_stride > 2 || (in_stride > 1 && planes != 1)) return cudaErrorInvalidValue;
     WgradParams p{};
+    p.in_stride = in_stride;
     int TW = pow2_ceil_(Wo); if (TW > 64) TW = 64;
     int TH = pow2_ceil_(Ho); if (TW * TH > 64) TH = 64 / TW;
     const int TN = 64 / (TW * TH);
@@ -409,7 +412,8 @@ cudaError_t launch_conv_wgrad_bf16(const void* dy, const void* x, float* dW, int
         const uint64_t d[4] = {(uint64_t)Cin, (uint64_t)Win, (uint64_t)Hin, (uint64_t)planes * NB};
         const uint64_t s[3] = {(uint64_t)Cin * 2, (uint64_t)Win * Cin * 2, (uint64_t)Hin * Win * Cin * 2};
         const uint32_t b[4] = {64, (uint32_t)TW, (uint32_t)TH, (uint32_t)TN};
-        RLR_CUDA_CHECK(make_tmap_bf16(&tmB, x, 4, d, s, b));
+        const uint32_t es[4] = {1, (uint32_t)in_stride, (uint32_t)in_stride, 1};
+        RLR_CUDA_CHECK(make_tmap_bf16(&tmB, x, 4, d, s, b, in_stride > 1 ? es : nullptr));
     }
     return wide ? launch_wg<128>(tmA, tmB, p, co_tiles, ntaps / p.ntaps_cta, num_sms, st)
                 : launch_wg<64>(tmA, tmB, p, co_tiles, ntaps / p.ntaps_cta, num_sms, st);
@@ -419,7 +423,7 @@ cudaError_t launch_conv_wgrad_bf16(const void* dy, const void* x, float* dW, int
 cudaError_t launch_linear_wgrad_bf16(const void* dy, const void* x, float* dW, int B, int N, int K, int num_sms, cudaStream_t st) {
     if (N % 8 || K % 64) return cudaErrorInvalidValue;
     WgradParams p{};
-    p.mode = 0; p.num_kb = (B + WG_BK - 1) / WG_BK; p.T = 1; p.ntaps_cta = 1;
+    p.mode = 0; p.num_kb = (B + WG_BK - 1) / WG_BK; p.T = 1; p.ntaps_cta = 1; p.in_stride = 1;
     const bool wide = K % 128 == 0;
     p.ci_tiles = wide ? K / 128 : K / 64; p.Cout = N; p.Cin_valid = K; p.dW = dW;
     p.a_groups = (N % 128 == 0) ? 2 : 1;

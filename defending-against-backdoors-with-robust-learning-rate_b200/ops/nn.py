@@ -3,6 +3,8 @@ of ops/csrc: gemm.cu = tcgen05/TMEM/TMA implicit-GEMM convolution + GEMM, norm.c
 ``aten`` back-end (the same math through PyTorch library calls on the same buffers: CPU path + in-place oracle)."""
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn.functional as F
 
@@ -10,6 +12,10 @@ _scratch = {}
 _s2d_done = {}
 STAT_SLOTS = 16         # conv epilogues spread their BatchNorm statistics over this many partial buffers (gemm.h kStatSlots)
 USE_WGRAD_HALO = True   # 3x3/s1/p1, 64 input channels: halo-reuse weight-gradient kernel (wgrad.cu)
+# Stride-2 convolutions without parity-split copies: the forward conv and the weight gradient read the original input through a
+# TMA box with element strides 2, and the four parity planes of the data gradient are stored straight into dX (strided epilogue
+# rows) -- no space_to_depth / depth_to_space passes.  Opt-in until measured on hardware (RLR_STRIDED_TMA=1).
+USE_STRIDED_TMA = bool(int(os.environ.get("RLR_STRIDED_TMA", "0")))
 
 
 def _ext():
@@ -80,6 +86,10 @@ def conv2d_fwd_sm100(x, w, bias, y, stride, pad, relu, stats, tag="fwd", zero_st
             stats.zero_()
         e.conv3x3_halo_bf16(x, w.reshape(Cout, 9 * 64), y, bias, bool(relu), False, stats, 0, None)
         return y
+    if stride == 2 and USE_STRIDED_TMA and stats is None:
+        e.conv_bf16_strided(x, w.reshape(Cout, k * k * Cin), y, [dy_ - pad for dy_ in range(k) for _ in range(k)],
+                            [dx_ - pad for _ in range(k) for dx_ in range(k)], bias, bool(relu), False, [], 0, 2, 1, 0, 0)
+        return y
     planes = 1
     if stride == 2:
         # parity-split copy keyed by the INPUT tensor: the 3x3/s2 conv and the 1x1/s2 shortcut of a ResNet block read the same
@@ -127,11 +137,11 @@ def _conv2d_dgrad_s2(e, dy, w, dx, pad, accumulate):
     """Stride-2 data gradient by input parity: input pixel (2a+pi, 2b+pj) only receives the taps with
     (pi + pad - dy) and (pj + pad - dx) even, from output pixel (a + (pi+pad-dy)/2, b + (pj+pad-dx)/2).  Each parity
     plane is therefore a small stride-1 convolution of dY with a sub-filter (1/2/2/4 taps for 3x3, pad 1); the four
-    planes are computed by the tcgen05 conv kernel into a parity-split buffer and interleaved by depth_to_space."""
+    planes are computed by the tcgen05 conv kernel into a parity-split buffer and interleaved by depth_to_space, or (strided
+    mode) stored directly at their pixels of dX."""
     Cout, k, _, Cin = w.shape
     B, Ho, Wo, _ = dy.shape
-    dx4 = scratch(("dx4", w.data_ptr()), (4 * B, Ho, Wo, Cin), dy.dtype, dy.device)
-    mask = 0
+    plan = []
     for pi in range(2):
         for pj in range(2):
             taps, dh, dw = [], [], []
@@ -139,17 +149,27 @@ def _conv2d_dgrad_s2(e, dy, w, dx, pad, accumulate):
                 for fx in range(k):
                     if (pi + pad - fy) % 2 == 0 and (pj + pad - fx) % 2 == 0:
                         taps.append(fy * k + fx); dh.append((pi + pad - fy) // 2); dw.append((pj + pad - fx) // 2)
-            if not taps:
-                continue
-            plane = pi * 2 + pj
-            mask |= 1 << plane
-            if Cin % 64 == 0:   # forward filter read MN-major: the plane's sub-filter is just a tap list
-                e.conv_bf16(dy, w.reshape(Cout, k * k * Cin), dx4[plane * B:(plane + 1) * B], B, 1, dh, dw, [0] * len(taps), None,
-                            False, False, None, taps, k * k)
-                continue
-            wt = scratch(("wt_s2", w.data_ptr(), plane), (Cin, len(taps) * Cout), w.dtype, w.device)
-            e.filter_gather_transpose(w, wt, Cout, k * k, Cin, taps)
-            e.conv_bf16(dy, wt, dx4[plane * B:(plane + 1) * B], B, 1, dh, dw, [0] * len(taps), None, False, False, None, [], 0)
+            if taps:
+                plan.append((pi, pj, taps, dh, dw))
+    if USE_STRIDED_TMA and Cin % 64 == 0 and dx.shape[1] == 2 * Ho and dx.shape[2] == 2 * Wo:
+        # each parity plane is stored straight into dX by the conv epilogue (row index = strided pixel): no parity buffer, no merge
+        if not accumulate and len(plan) < 4:
+            dx.zero_()                     # planes that receive no tap (1x1 shortcut: three of four)
+        for pi, pj, taps, dh, dw in plan:
+            e.conv_bf16_strided(dy, w.reshape(Cout, k * k * Cin), dx, dh, dw, None, False, bool(accumulate), taps, k * k, 1, 2, pi, pj)
+        return dx
+    dx4 = scratch(("dx4", w.data_ptr()), (4 * B, Ho, Wo, Cin), dy.dtype, dy.device)
+    mask = 0
+    for pi, pj, taps, dh, dw in plan:
+        plane = pi * 2 + pj
+        mask |= 1 << plane
+        if Cin % 64 == 0:   # forward filter read MN-major: the plane's sub-filter is just a tap list
+            e.conv_bf16(dy, w.reshape(Cout, k * k * Cin), dx4[plane * B:(plane + 1) * B], B, 1, dh, dw, [0] * len(taps), None,
+                        False, False, None, taps, k * k)
+            continue
+        wt = scratch(("wt_s2", w.data_ptr(), plane), (Cin, len(taps) * Cout), w.dtype, w.device)
+        e.filter_gather_transpose(w, wt, Cout, k * k, Cin, taps)
+        e.conv_bf16(dy, wt, dx4[plane * B:(plane + 1) * B], B, 1, dh, dw, [0] * len(taps), None, False, False, None, [], 0)
     e.depth_to_space(dx4, dx, bool(accumulate), mask)
     return dx
 
@@ -166,13 +186,17 @@ def conv2d_wgrad_sm100(x, dy, gw, gb, stride, pad, tag="fwd", zero=True):
         x = scratch(("xpad", tag), (B, H, W, cp), x.dtype, x.device)      # filled by the forward pass
         Cin = cp
     planes = 1
-    if stride == 2:
+    strided = stride == 2 and USE_STRIDED_TMA
+    if stride == 2 and not strided:
         x = scratch(("s2d", x.data_ptr(), Cin), (4 * B, H // 2, W // 2, Cin), x.dtype, x.device)  # filled by the forward pass
         planes = 4
     dh, dw, pl = _taps(k, stride, pad)
     if zero:
         gw.zero_()
-    if USE_WGRAD_HALO and _halo_ok(k, stride, pad, Cin, H, W) and (Cout <= 64 or Cout % 128 == 0):
+    if strided:
+        e.conv_wgrad_bf16_strided(dy, x, gw, cin_valid, [dy_ - pad for dy_ in range(k) for _ in range(k)],
+                                  [dx_ - pad for _ in range(k) for dx_ in range(k)], 2)
+    elif USE_WGRAD_HALO and _halo_ok(k, stride, pad, Cin, H, W) and (Cout <= 64 or Cout % 128 == 0):
         e.conv_wgrad_halo_bf16(dy, x, gw, cin_valid)
     else:
         e.conv_wgrad_bf16(dy, x, gw, B, planes, cin_valid, dh, dw, pl)
