@@ -85,6 +85,9 @@ cudaError_t launch_dropout_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, uint8_t
 cudaError_t launch_dropout_bwd(const __nv_bfloat16* dy, const uint8_t* mask, __nv_bfloat16* dx, long long n, float p, cudaStream_t st);
 // x[NB][H][W][C] -> four parity planes [4][NB][H/2][W/2][C] (plane = (h&1)*2 + (w&1)); H, W even
 cudaError_t launch_space_to_depth(const __nv_bfloat16* x, __nv_bfloat16* y, int NB, int H, int W, int C, int num_sms, cudaStream_t st);
+// stem convs (C*k*k <= 64, stride 1): A[NB*Ho*Wo][64] = zero-padded patches of x[NB][H][W][C] in (tap, channel) order
+cudaError_t launch_im2col_small(const __nv_bfloat16* x, __nv_bfloat16* A, int NB, int H, int W, int C, int Ho, int Wo, int k, int pad,
+                                int num_sms, cudaStream_t st);
 cudaError_t launch_depth_to_space(const __nv_bfloat16* x4, __nv_bfloat16* y, int NB, int H, int W, int C, int accumulate, int plane_mask,
                                   int num_sms, cudaStream_t st);
 cudaError_t launch_filter_gather_transpose(const __nv_bfloat16* w, __nv_bfloat16* wt, int Cout, int T, int Cin, int nsub, const int* taps,

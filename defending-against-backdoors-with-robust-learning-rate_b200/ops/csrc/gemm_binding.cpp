@@ -206,6 +206,13 @@ void space_to_depth(at::Tensor x, at::Tensor y) {
     c10::cuda::CUDAGuard g(x.device());
     check(rlr::launch_space_to_depth(bf(x), bfm(y), x.size(0), x.size(1), x.size(2), x.size(3), num_sms(), cur_stream()), "space_to_depth");
 }
+void im2col_small(at::Tensor x, at::Tensor A, int64_t k, int64_t pad) {
+    c10::cuda::CUDAGuard g(x.device());
+    const int NB = x.size(0), H = x.size(1), W = x.size(2), C = x.size(3);
+    const int Ho = H + 2 * pad - k + 1, Wo = W + 2 * pad - k + 1;
+    TORCH_CHECK(x.dim() == 4 && x.is_contiguous() && A.is_contiguous() && A.numel() == (int64_t)NB * Ho * Wo * 64, "im2col_small: A must be [NB*Ho*Wo, 64]");
+    check(rlr::launch_im2col_small(bf(x), bfm(A), NB, H, W, C, Ho, Wo, (int)k, (int)pad, num_sms(), cur_stream()), "im2col_small");
+}
 void depth_to_space(at::Tensor x4, at::Tensor y, bool accumulate, int64_t plane_mask) {
     c10::cuda::CUDAGuard g(y.device());
     check(rlr::launch_depth_to_space(bf(x4), bfm(y), y.size(0), y.size(1), y.size(2), y.size(3), accumulate, (int)plane_mask, num_sms(),
@@ -258,6 +265,7 @@ void register_gemm_bindings(py::module_& m) {
     m.def("dropout_fwd", &dropout_fwd);
     m.def("dropout_bwd", &dropout_bwd);
     m.def("space_to_depth", &space_to_depth);
+    m.def("im2col_small", &im2col_small);
     m.def("filter_transpose", &filter_transpose);
     m.def("depth_to_space", &depth_to_space);
     m.def("filter_gather_transpose", &filter_gather_transpose);

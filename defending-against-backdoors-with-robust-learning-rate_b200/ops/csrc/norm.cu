@@ -456,6 +456,41 @@ cudaError_t launch_space_to_depth(const __nv_bfloat16* x, __nv_bfloat16* y, int 
     return cudaGetLastError();
 }
 
+// Small-K im2col for stem convolutions (C * k * k <= 64, stride 1): A[(b,ho,wo)][j] = x[b][ho + dy - pad][wo + dx - pad][c] with
+// j = (dy * k + dx) * C + c, zero outside the image and for j >= C*k*k.  The stem conv then is ONE 64-deep k-block of the plain
+// GEMM (instead of k*k channel-padded ones) and its weight gradient a [Cout x 64] GEMM over the same matrix.
+__global__ void __launch_bounds__(256) im2col_small_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ A, int NB, int H,
+                                                             int W, int C, int Ho, int Wo, int k, int pad) {
+    const long long total = (long long)NB * Ho * Wo * 8;          // 8 chunks of 8 bf16 per 64-wide row
+    const int kkc = k * k * C;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int chunk = (int)(t & 7);
+        const long long pix = t >> 3;
+        const int wo = (int)(pix % Wo), ho = (int)((pix / Wo) % Ho), b = (int)(pix / ((long long)Wo * Ho));
+        __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int j = chunk * 8 + e;
+            float val = 0.f;
+            if (j < kkc) {
+                const int tap = j / C, c = j - tap * C;
+                const int dy = tap / k, dx = tap - dy * k;
+                const int h = ho + dy - pad, w = wo + dx - pad;
+                if (h >= 0 && h < H && w >= 0 && w < W) val = __bfloat162float(x[(((long long)b * H + h) * W + w) * C + c]);
+            }
+            v[e] = __float2bfloat16(val);
+        }
+        *reinterpret_cast<uint4*>(A + pix * 64 + chunk * 8) = *reinterpret_cast<const uint4*>(v);
+    }
+}
+cudaError_t launch_im2col_small(const __nv_bfloat16* x, __nv_bfloat16* A, int NB, int H, int W, int C, int Ho, int Wo, int k, int pad,
+                                int num_sms, cudaStream_t st) {
+    if (C * k * k > 64 || k < 1) return cudaErrorInvalidValue;
+    const long long total = (long long)NB * Ho * Wo * 8;
+    im2col_small_kernel<<<rows_grid(total, 256, num_sms, 8), 256, 0, st>>>(x, A, NB, H, W, C, Ho, Wo, k, pad);
+    return cudaGetLastError();
+}
+
 // inverse of space_to_depth with optional accumulation; planes missing from `plane_mask` count as zero
 __global__ void __launch_bounds__(256) depth_to_space_kernel(const __nv_bfloat16* __restrict__ x4, __nv_bfloat16* __restrict__ y, int NB,
                                                                int H, int W, int C, int accumulate, int plane_mask) {

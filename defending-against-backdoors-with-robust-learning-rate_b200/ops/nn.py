@@ -16,6 +16,14 @@ USE_WGRAD_HALO = True   # 3x3/s1/p1, 64 input channels: halo-reuse weight-gradie
 # TMA box with element strides 2, and the four parity planes of the data gradient are stored straight into dX (strided epilogue
 # rows) -- no space_to_depth / depth_to_space passes.  Opt-in until measured on hardware (RLR_STRIDED_TMA=1).
 USE_STRIDED_TMA = bool(int(os.environ.get("RLR_STRIDED_TMA", "0")))
+# Stem convolutions (Cin * k * k <= 64, stride 1): gather the k x k x Cin patch of every output pixel into ONE 64-wide K block
+# (im2col_small) and run the plain tcgen05 GEMM on it, instead of k*k k-blocks of a 64-channel zero-padded input; the weight
+# gradient is a [Cout x 64] GEMM over the same matrix.  Opt-in until measured on hardware (RLR_IM2COL_STEM=1).
+USE_IM2COL_STEM = bool(int(os.environ.get("RLR_IM2COL_STEM", "0")))
+
+
+def _stem_ok(k, stride, cin, cout):
+    return USE_IM2COL_STEM and stride == 1 and cin * k * k <= 64 and cout % 8 == 0 and (cout <= 64 or cout % 128 == 0)
 
 
 def _ext():
@@ -73,6 +81,16 @@ def conv2d_fwd_sm100(x, w, bias, y, stride, pad, relu, stats, tag="fwd", zero_st
     e = _ext()
     B, H, W, Cin = x.shape
     Cout, k = w.shape[0], w.shape[1]
+    if _stem_ok(k, stride, Cin, Cout):
+        Ho, Wo = y.shape[1], y.shape[2]
+        A = scratch(("im2col", tag), (B * Ho * Wo, 64), x.dtype, x.device)
+        e.im2col_small(x.contiguous(), A, k, pad)
+        wp = scratch(("wstem", tag, w.data_ptr()), (Cout, 64), w.dtype, w.device)       # columns >= k*k*Cin stay zero
+        wp[:, :k * k * Cin].copy_(w.reshape(Cout, k * k * Cin))
+        if stats is not None and zero_stats:
+            stats.zero_()
+        e.gemm_bf16(A, wp, y.view(B * Ho * Wo, Cout), bias, bool(relu), False, stats)
+        return y
     if Cin % 64:
         cp = (Cin + 63) // 64 * 64
         xp = scratch(("xpad", tag), (B, H, W, cp), x.dtype, x.device)
@@ -181,6 +199,21 @@ def conv2d_wgrad_sm100(x, dy, gw, gb, stride, pad, tag="fwd", zero=True):
     B, H, W, Cin = x.shape
     Cout, k = gw.shape[0], gw.shape[1]
     cin_valid = Cin
+    if _stem_ok(k, stride, Cin, Cout):
+        Ho, Wo = dy.shape[1], dy.shape[2]
+        A = scratch(("im2col", tag), (B * Ho * Wo, 64), x.dtype, x.device)               # filled by the forward pass
+        dW = scratch(("dwstem", tag), (Cout, 64), torch.float32, x.device)
+        dW.zero_()
+        e.linear_wgrad_bf16(dy.view(B * Ho * Wo, Cout), A, dW)
+        if zero:
+            gw.zero_()
+        gw.view(Cout, k * k * Cin).add_(dW[:, :k * k * Cin])
+        if gb is not None:
+            st = scratch(("dbias", tag), (2, Cout), torch.float32, dy.device)
+            st.zero_()
+            e.channel_stats(dy, st)
+            gb.copy_(st[0])
+        return
     if Cin % 64:
         cp = (Cin + 63) // 64 * 64
         x = scratch(("xpad", tag), (B, H, W, cp), x.dtype, x.device)      # filled by the forward pass

@@ -85,3 +85,35 @@ def test_native_net_with_strided_tma_matches_default():
     assert float((res[False][0] - res[True][0]).abs().max() / res[False][0].abs().max()) < 2e-2
     cos = torch.nn.functional.cosine_similarity(res[False][1].double(), res[True][1].double(), dim=0)
     assert float(cos) > 0.999, float(cos)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,p", [(64, 32, 32, 3, 64, 3, 1), (32, 28, 28, 1, 32, 3, 0), (32, 32, 32, 3, 64, 3, 0), (256, 32, 32, 3, 64, 3, 1)])
+def test_im2col_stem_conv_and_wgrad(B, H, W, Cin, Cout, k, p):
+    """RLR_IM2COL_STEM: stem conv as one 64-deep GEMM k-block over gathered patches, weight gradient as a [Cout x 64] GEMM."""
+    import torch.nn.functional as F
+    torch.manual_seed(B + H + Cin)
+    x = torch.randn(B, H, W, Cin, device=DEV).to(BF)
+    w = (torch.randn(Cout, k, k, Cin, device=DEV) / (k * k * Cin) ** 0.5).to(BF)
+    bias = torch.randn(Cout, device=DEV) * 0.1
+    Ho, Wo = H + 2 * p - k + 1, W + 2 * p - k + 1
+    dy = torch.randn(B, Ho, Wo, Cout, device=DEV).to(BF)
+    old = nn.USE_IM2COL_STEM
+    nn.USE_IM2COL_STEM = True
+    try:
+        tag = ("stem-test", B, H, Cin, k, p)
+        y = torch.full((B, Ho, Wo, Cout), 7.0, device=DEV, dtype=BF)
+        ops.conv2d_fwd_sm100(x, w, bias, y, 1, p, True, None, tag=tag)
+        gw = torch.zeros(Cout, k, k, Cin, device=DEV)
+        gb = torch.zeros(Cout, device=DEV)
+        ops.conv2d_wgrad_sm100(x, dy, gw, gb, 1, p, tag=tag)
+        torch.cuda.synchronize()
+    finally:
+        nn.USE_IM2COL_STEM = old
+    xf, wf = x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2)
+    ref = F.relu(F.conv2d(xf, wf, bias, 1, p)).permute(0, 2, 3, 1)
+    assert float((y.float() - ref).abs().max() / ref.abs().max()) < 1e-2
+    _, gw_ref, gb_ref = torch.ops.aten.convolution_backward(dy.float().permute(0, 3, 1, 2), xf, wf, [Cout], [1, 1], [p, p], [1, 1], False, [0, 0], 1,
+                                                            [False, True, True])
+    gw_ref = gw_ref.permute(0, 2, 3, 1)
+    assert float((gw - gw_ref).abs().max() / gw_ref.abs().max()) < 1e-2
+    torch.testing.assert_close(gb, gb_ref, rtol=1e-3, atol=1e-2 * (B * Ho * Wo) ** 0.5)
