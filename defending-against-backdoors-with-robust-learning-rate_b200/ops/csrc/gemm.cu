@@ -34,7 +34,8 @@ constexpr int kEpiThreads = 128;
 
 template <int BN, int kOcc = 2>
 struct TileCfg {
-    static constexpr int kStages = (BN == 64 && kOcc == 2) ? 4 : 3;   // kOcc = 3 (BN = 64 only): 3 x 24 KB ring, three CTAs per SM
+    // two CTAs per SM: 4 x 24 KB / 3 x 32 KB ring; three CTAs per SM (kOcc = 3): 3 x 24 KB / 2 x 32 KB ring
+    static constexpr int kStages = kOcc == 3 ? (BN == 64 ? 3 : 2) : (BN == 64 ? 4 : 3);
     static constexpr int kABytes = BM * BK * 2;
     static constexpr int kBBytes = BN * BK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
@@ -292,25 +293,28 @@ template <int BN>
 cudaError_t launch_persistent_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, int m_tiles, int num_sms,
                                  cudaStream_t st);
 
-static int g_occ3 = -1;         // -1: take RLR_CONV_OCC3 from the environment on first use (unset = on)
-void set_conv_occ3(int on) { g_occ3 = on ? 1 : 0; }
-static bool conv_occ3() {
-    if (g_occ3 < 0) { const char* e = getenv("RLR_CONV_OCC3"); g_occ3 = (!e || atoi(e) > 0) ? 1 : 0; }   // default on: -1.4 % / round
-    return g_occ3 == 1;
+// 0: two CTAs per SM for every tile | 1 (default, measured -1.4 % / round): three for the 64-wide tile | 2 (not yet measured): also
+// for the 128-wide tile (2-stage ring).  -1: take RLR_CONV_OCC3 from the environment on first use.
+static int g_occ3 = -1;
+void set_conv_occ3(int level) { g_occ3 = level < 0 ? 0 : (level > 2 ? 2 : level); }
+static int conv_occ3() {
+    if (g_occ3 < 0) { const char* e = getenv("RLR_CONV_OCC3"); set_conv_occ3(e ? atoi(e) : 1); }
+    return g_occ3;
 }
 
 // default (RLR_CONV_OCC3=0 disables): 64-wide tiles with a 3-stage ring at three CTAs per SM (three TMA producers / MMA issue threads per SM)
-static cudaError_t launch_bn64_occ3(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, int m_tiles, cudaStream_t st) {
-    using Cfg = TileCfg<64, 3>;
+template <int BN>
+static cudaError_t launch_bn_occ3(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, int m_tiles, cudaStream_t st) {
+    using Cfg = TileCfg<BN, 3>;
     static bool configured = false;
     if (!configured) {
-        RLR_CUDA_CHECK(cudaFuncSetAttribute(umma_conv_gemm_kernel<64, false, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-        RLR_CUDA_CHECK(cudaFuncSetAttribute(umma_conv_gemm_kernel<64, false, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        RLR_CUDA_CHECK(cudaFuncSetAttribute(umma_conv_gemm_kernel<BN, false, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        RLR_CUDA_CHECK(cudaFuncSetAttribute(umma_conv_gemm_kernel<BN, false, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         configured = true;
     }
-    dim3 grid(m_tiles, (p.N + 63) / 64);
-    if (p.b_mn) umma_conv_gemm_kernel<64, false, true, 3><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
-    else umma_conv_gemm_kernel<64, false, false, 3><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
+    dim3 grid(m_tiles, (p.N + BN - 1) / BN);
+    if (p.b_mn) umma_conv_gemm_kernel<BN, false, true, 3><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
+    else umma_conv_gemm_kernel<BN, false, false, 3><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
     return cudaGetLastError();
 }
 
@@ -333,7 +337,7 @@ static cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, con
     using Cfg = TileCfg<BN>;
     if (!p.stats && persistent_sms() > 0 && m_tiles * ((p.N + BN - 1) / BN) > persistent_sms())
         return launch_persistent_bn<BN>(tmA, tmB, p, m_tiles, persistent_sms(), st);
-    if (BN == 64 && !p.stats && conv_occ3()) return launch_bn64_occ3(tmA, tmB, p, m_tiles, st);
+    if (!p.stats && conv_occ3() >= (BN == 64 ? 1 : 2)) return launch_bn_occ3<BN>(tmA, tmB, p, m_tiles, st);
     static bool configured = false;
     if (!configured) {
         RLR_CUDA_CHECK(cudaFuncSetAttribute(umma_conv_gemm_kernel<BN, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));

@@ -37,8 +37,8 @@ cudaError_t launch_gemm_bf16(const void* A, const void* B, void* out, int M, int
                              const float* bias, int relu, int accumulate, float* stats, cudaStream_t st);
 // opt-in persistent tile scheduler for the generic conv / GEMM kernel (gemm_persistent.cu); default: RLR_PERSISTENT_CONV env
 void set_persistent_conv(int on);
-// 3-CTAs-per-SM variant of the 64-wide tile (default on; RLR_CONV_OCC3=0 or set_conv_occ3(0) selects the 2-CTA / 4-stage one)
-void set_conv_occ3(int on);
+// three CTAs per SM: level 0 never, 1 (default) for the 64-wide tile, 2 also for the 128-wide tile (RLR_CONV_OCC3 env)
+void set_conv_occ3(int level);
 cudaError_t launch_conv_bf16(const void* x, const void* w, void* out, int NB, int planes, int Hin, int Win, int Cin, int Ho, int Wo,
                              int Cout, int ldc, int ntaps, const int* dh, const int* dw, const int* dplane, const float* bias,
                              int relu, int accumulate, float* stats, cudaStream_t st, const int* wtap = nullptr, int w_taps_total = 0,

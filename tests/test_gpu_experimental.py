@@ -117,3 +117,29 @@ def test_im2col_stem_conv_and_wgrad(B, H, W, Cin, Cout, k, p):
     gw_ref = gw_ref.permute(0, 2, 3, 1)
     assert float((gw - gw_ref).abs().max() / gw_ref.abs().max()) < 1e-2
     torch.testing.assert_close(gb, gb_ref, rtol=1e-3, atol=1e-2 * (B * Ho * Wo) ** 0.5)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,s,p", [(128, 16, 16, 128, 128, 3, 1, 1), (256, 8, 8, 256, 256, 3, 1, 1), (128, 16, 16, 128, 256, 1, 2, 0)])
+def test_conv_occ3_level2_matches_two_cta_kernel(B, H, W, Cin, Cout, k, s, p):
+    """RLR_CONV_OCC3=2: 128-wide tiles at three CTAs per SM with a 2-stage ring -- bit-identical to the 2-CTA kernel."""
+    torch.manual_seed(B + H + Cin)
+    x = torch.randn(B, H, W, Cin, device=DEV).to(BF)
+    w = (torch.randn(Cout, k, k, Cin, device=DEV) / (k * k * Cin) ** 0.5).to(BF)
+    bias = torch.randn(Cout, device=DEV) * 0.1
+    Ho, Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    dy = torch.randn(B, Ho, Wo, Cout, device=DEV).to(BF)
+    base = torch.randn(B, H, W, Cin, device=DEV).to(BF)
+    outs = {}
+    try:
+        for level in (0, 2):
+            ops.ext().set_conv_occ3(level)
+            y = torch.full((B, Ho, Wo, Cout), 7.0, device=DEV, dtype=BF)
+            ops.conv2d_fwd_sm100(x, w, bias, y, s, p, True, None, tag=("occ3x", level, B, H, Cin, k, s))
+            dx = base.clone()
+            ops.conv2d_dgrad_sm100(dy, w, dx, s, p, True)
+            torch.cuda.synchronize()
+            outs[level] = (y, dx)
+    finally:
+        ops.ext().set_conv_occ3(1)
+    for a, b in zip(outs[0], outs[2]):
+        assert torch.equal(a, b)

@@ -330,7 +330,7 @@ def test_persistent_conv_matches_default(B, H, W, Cin, Cout, k, s, p):
     try:
         for on in (False, True, "occ3"):
             ops.ext().set_persistent_conv(on is True)
-            ops.ext().set_conv_occ3(on == "occ3")
+            ops.ext().set_conv_occ3(1 if on == "occ3" else 0)
             y = torch.full((B, Ho, Wo, Cout), 7.0, device=DEV, dtype=BF)
             ops.conv2d_fwd_sm100(x, w, bias, y, s, p, True, None, tag=("persist", on, B, H, Cin, k, s))
             dx0 = torch.full_like(base, 3.0)
@@ -344,7 +344,7 @@ def test_persistent_conv_matches_default(B, H, W, Cin, Cout, k, s, p):
             outs[on] = (y, dx0, dx1, g)
     finally:
         ops.ext().set_persistent_conv(False)
-        ops.ext().set_conv_occ3(False)
+        ops.ext().set_conv_occ3(1)       # the default level
     ref = F.relu(F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), bias, s, p)).permute(0, 2, 3, 1)
     assert _rel(outs[True][0], ref) < 1e-2
     assert _rel(outs[True][3], A.float() @ Bm.float().t()) < 1e-2
