@@ -343,7 +343,8 @@ class NativeNet:
         dx = self.G(op.x, B)
         gamma = self.pw[op.name + ".weight"]
         ops.bn_bwd(dy, y, x, gamma, op.saved["mean_rstd"], op.saved["dsum"], dx, dres,
-                   self.pg[op.name + ".weight"], self.pg[op.name + ".bias"], op.relu, self.impl["bn"], zero_dsum=False)
+                   self.pg[op.name + ".weight"], self.pg[op.name + ".bias"], op.relu, self.impl["bn"], zero_dsum=False,
+                   beta=self.pw[op.name + ".bias"])
 
     # ---- pooling ---------------------------------------------------------------------------------------------------
     def _fwd_maxpool(self, op, B, train):

@@ -68,13 +68,14 @@ cudaError_t launch_bn_finalize(const float* stats, int slots, float* mean_rstd, 
 cudaError_t launch_bn_apply(const __nv_bfloat16* x, const __nv_bfloat16* res, __nv_bfloat16* y, const float* gamma, const float* beta,
                             float* mean_rstd, long long M, int C, int relu, int fin_mode, const float* stats, int slots, float count,
                             float eps, float momentum, float* running_mean, float* running_var, int num_sms, cudaStream_t st);
-// dsum[0][c] = sum dz, dsum[1][c] = sum dz * xhat   (dz = dy * (y > 0) if relu)
+// dsum[0][c] = sum dz, dsum[1][c] = sum dz * xhat   (dz = dy * mask; relu 1: mask = (y > 0), relu 2: mask recomputed from x, gamma, beta)
 cudaError_t launch_bn_bwd_reduce(const __nv_bfloat16* dy, const __nv_bfloat16* y, const __nv_bfloat16* x, const float* mean_rstd,
-                                 float* dsum /*accumulates*/, long long M, int C, int relu, int num_sms, cudaStream_t st);
+                                 float* dsum /*accumulates*/, long long M, int C, int relu, int num_sms, cudaStream_t st,
+                                 const float* gamma = nullptr, const float* beta = nullptr);
 // dx = gamma * rstd * (dz - dsum0/M - xhat * dsum1/M); dres = dz; dgamma = dsum1, dbeta = dsum0
 cudaError_t launch_bn_bwd_apply(const __nv_bfloat16* dy, const __nv_bfloat16* y, const __nv_bfloat16* x, const float* gamma,
                                 const float* mean_rstd, const float* dsum, __nv_bfloat16* dx, __nv_bfloat16* dres, float* dgamma,
-                                float* dbeta, long long M, int C, int relu, int num_sms, cudaStream_t st);
+                                float* dbeta, long long M, int C, int relu, int num_sms, cudaStream_t st, const float* beta = nullptr);
 cudaError_t launch_relu_bwd(__nv_bfloat16* dy, const __nv_bfloat16* y, long long n, int num_sms, cudaStream_t st);
 cudaError_t launch_maxpool2_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, uint8_t* idx, int B, int H, int W, int C, cudaStream_t st);
 cudaError_t launch_maxpool2_bwd(const __nv_bfloat16* dy, const uint8_t* idx, __nv_bfloat16* dx, int B, int H, int W, int C, cudaStream_t st);

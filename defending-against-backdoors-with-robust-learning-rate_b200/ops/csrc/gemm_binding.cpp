@@ -173,6 +173,19 @@ void bn_bwd(at::Tensor dy, at::Tensor y, at::Tensor x, at::Tensor gamma, at::Ten
                                    const_cast<__nv_bfloat16*>(bfo(dres)), (float*)dgamma.data_ptr(), (float*)dbeta.data_ptr(), M, C, relu,
                                    num_sms(), cur_stream()), "bn_bwd_apply");
 }
+// BatchNorm + ReLU without a residual: the ReLU mask is recomputed from x (same expression as the forward), y is never read
+void bn_bwd_recompute(at::Tensor dy, at::Tensor x, at::Tensor gamma, at::Tensor beta, at::Tensor mean_rstd, at::Tensor dsum, at::Tensor dx,
+                      at::Tensor dgamma, at::Tensor dbeta, bool zero_dsum) {
+    c10::cuda::CUDAGuard g(x.device());
+    const int C = x.size(-1);
+    const long long M = x.numel() / C;
+    if (zero_dsum) check(cudaMemsetAsync(dsum.data_ptr(), 0, sizeof(float) * 2 * C, cur_stream()), "bn_bwd/memset");
+    check(rlr::launch_bn_bwd_reduce(bf(dy), nullptr, bf(x), f32(mean_rstd), f32(dsum), M, C, 2, num_sms(), cur_stream(),
+                                    (const float*)gamma.data_ptr(), (const float*)beta.data_ptr()), "bn_bwd_reduce(recompute)");
+    check(rlr::launch_bn_bwd_apply(bf(dy), nullptr, bf(x), (const float*)gamma.data_ptr(), f32(mean_rstd), f32(dsum), bfm(dx), nullptr,
+                                   (float*)dgamma.data_ptr(), (float*)dbeta.data_ptr(), M, C, 2, num_sms(), cur_stream(),
+                                   (const float*)beta.data_ptr()), "bn_bwd_apply(recompute)");
+}
 void relu_bwd(at::Tensor dy, at::Tensor y) {
     c10::cuda::CUDAGuard g(dy.device());
     check(rlr::launch_relu_bwd(bfm(dy), bf(y), dy.numel(), num_sms(), cur_stream()), "relu_bwd");
@@ -257,6 +270,7 @@ void register_gemm_bindings(py::module_& m) {
     m.def("bn_finalize", &bn_finalize);
     m.def("bn_apply", &bn_apply);
     m.def("bn_bwd", &bn_bwd);
+    m.def("bn_bwd_recompute", &bn_bwd_recompute);
     m.def("relu_bwd", &relu_bwd);
     m.def("maxpool2_fwd", &maxpool2_fwd);
     m.def("maxpool2_bwd", &maxpool2_bwd);

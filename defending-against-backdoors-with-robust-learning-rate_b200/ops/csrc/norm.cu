@@ -34,19 +34,26 @@ static inline bool chan_ok(int C) { return C >= 8 && C <= 2048 && (C % 8) == 0 &
 // per-channel reductions:  out[0][c] += sum_r a(r,c),  out[1][c] += sum_r b(r,c)
 // MODE 0: a = x, b = x^2 (forward statistics)     MODE 1: a = dz, b = dz * xhat (backward)
 // ---------------------------------------------------------------------------------------------------------------------
-template <int MODE>
+template <int MODE, bool kRecompute = false>
 __global__ void __launch_bounds__(256, MODE == 0 ? 4 : 3) channel_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
                                                                const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean_rstd,
-                                                               float* out, long long M, int C, int relu) {
+                                                               float* out, long long M, int C, int relu,
+                                                               const float* __restrict__ gamma = nullptr, const float* __restrict__ beta = nullptr) {
+    // relu: 0 none | 1 mask = (y > 0) from the stored output | 2 mask recomputed as (x * scale + shift > 0) with exactly the
+    // expression of bn_apply_kernel -- BatchNorm + ReLU without a residual: the output tensor is not read at all
     extern __shared__ float sh[];   // [rpi][2][C] per-row-slot partials (16 KB for every C)
     const int tpr = C / 8, rpi = 256 / tpr;
     const int cg = threadIdx.x % tpr, ry = threadIdx.x / tpr;
-    float a[8], b[8], mu[8], rs[8];
+    float a[8], b[8], mu[8], rs[8], msc[8], msh[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { a[i] = 0.f; b[i] = 0.f; mu[i] = 0.f; rs[i] = 1.f; }
+    for (int i = 0; i < 8; ++i) { a[i] = 0.f; b[i] = 0.f; mu[i] = 0.f; rs[i] = 1.f; msc[i] = 0.f; msh[i] = 1.f; }
     if (MODE == 1) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) { mu[i] = mean_rstd[cg * 8 + i]; rs[i] = mean_rstd[C + cg * 8 + i]; }
+        if (kRecompute) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { msc[i] = gamma[cg * 8 + i] * rs[i]; msh[i] = beta[cg * 8 + i] - mu[i] * msc[i]; }
+        }
     }
     // U rows per iteration with every load issued before the first use: one 16-byte load per thread in flight reaches only
     // ~20 % (forward statistics) / ~48 % (backward) of the HBM roofline (profiles/r1c_ncu_bn_kernels.md)
@@ -61,7 +68,7 @@ __global__ void __launch_bounds__(256, MODE == 0 ? 4 : 3) channel_reduce_kernel(
             xr[u] = *reinterpret_cast<const uint4*>(x + off);
             if (MODE == 1) {
                 dr[u] = *reinterpret_cast<const uint4*>(dy + off);
-                if (relu) yr[u] = *reinterpret_cast<const uint4*>(y + off);
+                if (!kRecompute && relu) yr[u] = *reinterpret_cast<const uint4*>(y + off);
             }
         }
 #pragma unroll
@@ -77,9 +84,12 @@ __global__ void __launch_bounds__(256, MODE == 0 ? 4 : 3) channel_reduce_kernel(
                     a[2 * i] += xv.x; a[2 * i + 1] += xv.y; b[2 * i] += xv.x * xv.x; b[2 * i + 1] += xv.y * xv.y;
                 } else {
                     float2 dz = __bfloat1622float2(dh[i]);
-                    if (relu) {
+                    if (!kRecompute && relu) {
                         const float2 yv = __bfloat1622float2(yh[i]);
                         dz.x = yv.x > 0.f ? dz.x : 0.f; dz.y = yv.y > 0.f ? dz.y : 0.f;
+                    } else if (kRecompute) {
+                        dz.x = (xv.x * msc[2 * i] + msh[2 * i]) > 0.f ? dz.x : 0.f;
+                        dz.y = (xv.y * msc[2 * i + 1] + msh[2 * i + 1]) > 0.f ? dz.y : 0.f;
                     }
                     a[2 * i] += dz.x; a[2 * i + 1] += dz.y;
                     b[2 * i] += dz.x * (xv.x - mu[2 * i]) * rs[2 * i]; b[2 * i + 1] += dz.y * (xv.y - mu[2 * i + 1]) * rs[2 * i + 1];
@@ -107,10 +117,14 @@ cudaError_t launch_channel_stats(const __nv_bfloat16* x, long long M, int C, flo
     return cudaGetLastError();
 }
 cudaError_t launch_bn_bwd_reduce(const __nv_bfloat16* dy, const __nv_bfloat16* y, const __nv_bfloat16* x, const float* mean_rstd,
-                                 float* dsum, long long M, int C, int relu, int num_sms, cudaStream_t st) {
-    if (!chan_ok(C)) return cudaErrorInvalidValue;
+                                 float* dsum, long long M, int C, int relu, int num_sms, cudaStream_t st, const float* gamma,
+                                 const float* beta) {
+    if (!chan_ok(C) || (relu == 2 && (!gamma || !beta)) || (relu == 1 && !y)) return cudaErrorInvalidValue;
     const int rpi = 256 / (C / 8);
-    channel_reduce_kernel<1><<<rows_grid(M, rpi * 8, num_sms, 2), 256, (size_t)rpi * 2 * C * sizeof(float), st>>>(x, dy, y, mean_rstd, dsum, M, C, relu);
+    const int grid = rows_grid(M, rpi * 8, num_sms, 2);
+    const size_t smem = (size_t)rpi * 2 * C * sizeof(float);
+    if (relu == 2) channel_reduce_kernel<1, true><<<grid, 256, smem, st>>>(x, dy, y, mean_rstd, dsum, M, C, relu, gamma, beta);
+    else channel_reduce_kernel<1, false><<<grid, 256, smem, st>>>(x, dy, y, mean_rstd, dsum, M, C, relu);
     return cudaGetLastError();
 }
 
@@ -206,20 +220,23 @@ cudaError_t launch_bn_apply(const __nv_bfloat16* x, const __nv_bfloat16* res, __
     return cudaGetLastError();
 }
 
+template <bool kRecompute>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
                                                              const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
                                                              const float* __restrict__ mean_rstd, const float* __restrict__ dsum,
                                                              __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dres,
-                                                             float* dgamma, float* dbeta, long long M, int C, int relu) {
+                                                             float* dgamma, float* dbeta, long long M, int C, int relu,
+                                                             const float* __restrict__ beta = nullptr) {
     const int tpr = C / 8, rpi = 256 / tpr;
     const int cg = threadIdx.x % tpr, ry = threadIdx.x / tpr;
-    float mu[8], rs[8], g[8], k1[8], k2[8];
+    float mu[8], rs[8], g[8], k1[8], k2[8], msh[8];
     const float invM = 1.0f / (float)M;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int c = cg * 8 + i;
         mu[i] = mean_rstd[c]; rs[i] = mean_rstd[C + c]; g[i] = gamma[c] * rs[i];
         k1[i] = dsum[c] * invM; k2[i] = dsum[C + c] * invM;
+        msh[i] = kRecompute ? beta[c] - mu[i] * g[i] : 0.f;     // g = gamma * rstd is bn_apply's scale, msh its shift
     }
     if (blockIdx.x == 0 && ry == 0) {
 #pragma unroll
@@ -228,13 +245,16 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* 
     for (long long r = (long long)blockIdx.x * rpi + ry; r < M; r += (long long)gridDim.x * rpi) {
         const size_t off = (size_t)r * C + cg * 8;
         bf8 dz = load8(dy + off);
-        if (relu) {
+        const bf8 xv = load8(x + off);
+        if (!kRecompute && relu) {
             const bf8 yv = load8(y + off);
 #pragma unroll
             for (int i = 0; i < 8; ++i) dz.v[i] = yv.v[i] > 0.f ? dz.v[i] : 0.f;
+        } else if (kRecompute) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dz.v[i] = (xv.v[i] * g[i] + msh[i]) > 0.f ? dz.v[i] : 0.f;
         }
         if (dres) store8(dres + off, dz);
-        const bf8 xv = load8(x + off);
         bf8 o;
 #pragma unroll
         for (int i = 0; i < 8; ++i) o.v[i] = g[i] * (dz.v[i] - k1[i] - (xv.v[i] - mu[i]) * rs[i] * k2[i]);
@@ -243,10 +263,12 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* 
 }
 cudaError_t launch_bn_bwd_apply(const __nv_bfloat16* dy, const __nv_bfloat16* y, const __nv_bfloat16* x, const float* gamma,
                                 const float* mean_rstd, const float* dsum, __nv_bfloat16* dx, __nv_bfloat16* dres, float* dgamma,
-                                float* dbeta, long long M, int C, int relu, int num_sms, cudaStream_t st) {
-    if (!chan_ok(C)) return cudaErrorInvalidValue;
+                                float* dbeta, long long M, int C, int relu, int num_sms, cudaStream_t st, const float* beta) {
+    if (!chan_ok(C) || (relu == 2 && !beta) || (relu == 1 && !y)) return cudaErrorInvalidValue;
     const int rpi = 256 / (C / 8);
-    bn_bwd_apply_kernel<<<rows_grid(M, rpi * 4, num_sms, 8), 256, 0, st>>>(dy, y, x, gamma, mean_rstd, dsum, dx, dres, dgamma, dbeta, M, C, relu);
+    const int grid = rows_grid(M, rpi * 4, num_sms, 8);
+    if (relu == 2) bn_bwd_apply_kernel<true><<<grid, 256, 0, st>>>(dy, y, x, gamma, mean_rstd, dsum, dx, dres, dgamma, dbeta, M, C, relu, beta);
+    else bn_bwd_apply_kernel<false><<<grid, 256, 0, st>>>(dy, y, x, gamma, mean_rstd, dsum, dx, dres, dgamma, dbeta, M, C, relu);
     return cudaGetLastError();
 }
 

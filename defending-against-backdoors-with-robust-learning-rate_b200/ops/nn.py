@@ -20,6 +20,9 @@ USE_STRIDED_TMA = bool(int(os.environ.get("RLR_STRIDED_TMA", "0")))
 # (im2col_small) and run the plain tcgen05 GEMM on it, instead of k*k k-blocks of a 64-channel zero-padded input; the weight
 # gradient is a [Cout x 64] GEMM over the same matrix.  Opt-in until measured on hardware (RLR_IM2COL_STEM=1).
 USE_IM2COL_STEM = bool(int(os.environ.get("RLR_IM2COL_STEM", "0")))
+# BatchNorm(+ReLU, no residual) backward without reading the layer output: the mask is recomputed from x with the forward's own
+# scale/shift expression.  Opt-in until measured on hardware (RLR_BN_RECOMPUTE=1).
+USE_BN_RECOMPUTE = bool(int(os.environ.get("RLR_BN_RECOMPUTE", "0")))
 
 
 def _stem_ok(k, stride, cin, cout):
@@ -283,9 +286,14 @@ def bn_fwd(x, y, res, gamma, beta, rm, rv, stats, mean_rstd, count, eps, momentu
     y.copy_(out.reshape(y.shape))
 
 
-def bn_bwd(dy, y, x, gamma, mean_rstd, dsum, dx, dres, dgamma, dbeta, relu, impl, zero_dsum=True):
+def bn_bwd(dy, y, x, gamma, mean_rstd, dsum, dx, dres, dgamma, dbeta, relu, impl, zero_dsum=True, beta=None):
     C = x.shape[-1]
     if impl == "sm100":
+        if USE_BN_RECOMPUTE and relu and dres is None and beta is not None:
+            # BN + ReLU without a residual: recompute the ReLU mask from x (needed anyway for xhat) instead of reading y -- one
+            # activation-sized read less in each of the two backward passes
+            _ext().bn_bwd_recompute(dy, x, gamma, beta, mean_rstd, dsum, dx, dgamma, dbeta, bool(zero_dsum))
+            return
         _ext().bn_bwd(dy, y, x, gamma, mean_rstd, dsum, dx, dres, dgamma, dbeta, bool(relu), bool(zero_dsum))
         return
     dz = dy.float().reshape(-1, C)

@@ -143,3 +143,36 @@ def test_conv_occ3_level2_matches_two_cta_kernel(B, H, W, Cin, Cout, k, s, p):
         ops.ext().set_conv_occ3(1)
     for a, b in zip(outs[0], outs[2]):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("C,M", [(64, 65536), (128, 16384), (512, 4100), (256, 999)])
+def test_bn_backward_with_recomputed_relu_mask(C, M):
+    """RLR_BN_RECOMPUTE: BN+ReLU (no residual) backward derives the ReLU mask from x instead of reading y; must equal the
+    y-based kernels up to the reduction order."""
+    torch.manual_seed(C + M)
+    x = (torch.randn(M, C, device=DEV) * 1.5 + 0.3).to(BF)
+    gamma = torch.rand(C, device=DEV) + 0.5
+    beta = torch.randn(C, device=DEV) * 0.2
+    rm, rv = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+    mean_rstd = torch.zeros(2, C, device=DEV)
+    y = torch.empty_like(x)
+    nn.bn_fwd(x, y, None, gamma, beta, rm, rv, None, mean_rstd, M, 1e-5, 0.1, True, True, "sm100")
+    dy = torch.randn(M, C, device=DEV).to(BF)
+    res = {}
+    old = nn.USE_BN_RECOMPUTE
+    try:
+        for mode in (False, True):
+            nn.USE_BN_RECOMPUTE = mode
+            dsum = torch.zeros(2, C, device=DEV)
+            dx = torch.empty_like(x)
+            dg, db = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+            nn.bn_bwd(dy, y, x, gamma, mean_rstd, dsum, dx, None, dg, db, True, "sm100", zero_dsum=True, beta=beta)
+            torch.cuda.synchronize()
+            res[mode] = (dx.float(), dg, db)
+    finally:
+        nn.USE_BN_RECOMPUTE = old
+    # masks agree except where the pre-activation is within rounding of 0; the channel sums differ by reduction order only
+    mism = (~torch.isclose(res[False][0], res[True][0], rtol=2e-2, atol=2e-2)).float().mean()
+    assert float(mism) < 1e-3, float(mism)
+    torch.testing.assert_close(res[True][1], res[False][1], rtol=2e-3, atol=2e-2 * M ** 0.5)
+    torch.testing.assert_close(res[True][2], res[False][2], rtol=2e-3, atol=2e-2 * M ** 0.5)
