@@ -14,6 +14,33 @@ namespace rlr {
 
 constexpr int kWarp = 32;
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------------------
+// Kernels launched through launch_kernel() with PDL enabled (RLR_PDL=1 / set_pdl) may start while their predecessor in the stream
+// is still draining: they run their prologue (barrier init, TMEM allocation, tensor-map prefetch, index arithmetic) and then block
+// in pdl_wait() until the predecessor grid has completed and its memory is visible.  Rules every such kernel follows: NO global
+// memory access before pdl_wait(); pdl_wait() is executed by every thread; pdl_trigger() (lets the successor start launching)
+// comes after it.  Without the launch attribute both instructions are no-ops, so the same kernels serve plain launches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+extern int g_pdl;             // -1: read RLR_PDL on first use (default off); defined in elementwise.cu
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    if (!pdl_enabled()) {
+        kernel<<<grid, block, smem, st>>>(static_cast<KArgs>(args)...);
+        return cudaGetLastError();
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

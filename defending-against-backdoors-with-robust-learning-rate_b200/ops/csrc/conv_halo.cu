@@ -90,6 +90,8 @@ umma_conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
     tc_fence_after();
     const uint32_t tmem_acc = sh->tmem_base;
     const int tiles_per_img = p.tiles_h * p.tiles_w;
+    pdl_wait();        // nothing above read or wrote global memory
+    pdl_trigger();
 
     if (warp == 0) {
         // ===================== producer: filter once, then one halo box per tile =====================================
@@ -277,10 +279,9 @@ cudaError_t launch_conv3x3_halo_bf16(const void* x, const void* w, void* out, in
     if (gx > p.num_tiles) gx = p.num_tiles;
     if (gx < 1) gx = 1;
     const dim3 grid(gx, n_tiles_n);
-    if (stats) umma_conv3x3_halo_kernel<true, false><<<grid, HL_THREADS, HL_SMEM, st>>>(tmX, tmW, p);
-    else if (accumulate) umma_conv3x3_halo_kernel<false, true><<<grid, HL_THREADS, HL_SMEM, st>>>(tmX, tmW, p);
-    else umma_conv3x3_halo_kernel<false, false><<<grid, HL_THREADS, HL_SMEM, st>>>(tmX, tmW, p);
-    return cudaGetLastError();
+    if (stats) return launch_kernel(umma_conv3x3_halo_kernel<true, false>, grid, dim3(HL_THREADS), HL_SMEM, st, tmX, tmW, p);
+    if (accumulate) return launch_kernel(umma_conv3x3_halo_kernel<false, true>, grid, dim3(HL_THREADS), HL_SMEM, st, tmX, tmW, p);
+    return launch_kernel(umma_conv3x3_halo_kernel<false, false>, grid, dim3(HL_THREADS), HL_SMEM, st, tmX, tmW, p);
 }
 
 }  // namespace rlr

@@ -5,7 +5,17 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#include <cstdlib>
+
 namespace rlr {
+
+// ---- programmatic dependent launch switch (common.cuh) -------------------------------------------------------------------------
+int g_pdl = -1;
+void set_pdl(int on) { g_pdl = on ? 1 : 0; }
+bool pdl_enabled() {
+    if (g_pdl < 0) { const char* e = getenv("RLR_PDL"); g_pdl = (e && atoi(e) > 0) ? 1 : 0; }
+    return g_pdl > 0;
+}
 
 // ------------------------------------------------------------------------------------------------------------
 // batch = normalize(dataset[perm[cursor : cursor+B]])   (uint8/float NHWC  ->  fp32/bf16, NCHW or padded NHWC)

@@ -102,6 +102,8 @@ umma_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_acc = tail->tmem_base;
+    pdl_wait();        // everything above touched only parameters, shared memory and TMEM
+    pdl_trigger();
 
     if (warp == 0) {
         // ================================ TMA producer =====================================================================
@@ -313,9 +315,8 @@ static cudaError_t launch_bn_occ3(const CUtensorMap& tmA, const CUtensorMap& tmB
         configured = true;
     }
     dim3 grid(m_tiles, (p.N + BN - 1) / BN);
-    if (p.b_mn) umma_conv_gemm_kernel<BN, false, true, 3><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
-    else umma_conv_gemm_kernel<BN, false, false, 3><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
-    return cudaGetLastError();
+    if (p.b_mn) return launch_kernel(umma_conv_gemm_kernel<BN, false, true, 3>, grid, dim3(kThreads), Cfg::kSmemBytes, st, tmA, tmB, p);
+    return launch_kernel(umma_conv_gemm_kernel<BN, false, false, 3>, grid, dim3(kThreads), Cfg::kSmemBytes, st, tmA, tmB, p);
 }
 
 static int g_persistent = -1;   // -1: take RLR_PERSISTENT_CONV from the environment on first use
@@ -346,10 +347,9 @@ static cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, con
         configured = true;
     }
     dim3 grid(m_tiles, (p.N + BN - 1) / BN);
-    if (p.b_mn) umma_conv_gemm_kernel<BN, false, true><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
-    else if (p.stats) umma_conv_gemm_kernel<BN, true, false><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
-    else umma_conv_gemm_kernel<BN, false, false><<<grid, kThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
-    return cudaGetLastError();
+    if (p.b_mn) return launch_kernel(umma_conv_gemm_kernel<BN, false, true>, grid, dim3(kThreads), Cfg::kSmemBytes, st, tmA, tmB, p);
+    if (p.stats) return launch_kernel(umma_conv_gemm_kernel<BN, true, false>, grid, dim3(kThreads), Cfg::kSmemBytes, st, tmA, tmB, p);
+    return launch_kernel(umma_conv_gemm_kernel<BN, false, false>, grid, dim3(kThreads), Cfg::kSmemBytes, st, tmA, tmB, p);
 }
 
 static int pick_bn(int N) { return (N % 128 == 0) ? 128 : 64; }

@@ -42,6 +42,8 @@ __global__ void __launch_bounds__(256, MODE == 0 ? 4 : 3) channel_reduce_kernel(
     // relu: 0 none | 1 mask = (y > 0) from the stored output | 2 mask recomputed as (x * scale + shift > 0) with exactly the
     // expression of bn_apply_kernel -- BatchNorm + ReLU without a residual: the output tensor is not read at all
     extern __shared__ float sh[];   // [rpi][2][C] per-row-slot partials (16 KB for every C)
+    pdl_wait();
+    pdl_trigger();
     const int tpr = C / 8, rpi = 256 / tpr;
     const int cg = threadIdx.x % tpr, ry = threadIdx.x / tpr;
     float a[8], b[8], mu[8], rs[8], msc[8], msh[8];
@@ -113,8 +115,8 @@ __global__ void __launch_bounds__(256, MODE == 0 ? 4 : 3) channel_reduce_kernel(
 cudaError_t launch_channel_stats(const __nv_bfloat16* x, long long M, int C, float* stats, int num_sms, cudaStream_t st) {
     if (!chan_ok(C)) return cudaErrorInvalidValue;
     const int rpi = 256 / (C / 8);
-    channel_reduce_kernel<0><<<rows_grid(M, rpi * 8, num_sms, 2), 256, (size_t)rpi * 2 * C * sizeof(float), st>>>(x, nullptr, nullptr, nullptr, stats, M, C, 0);
-    return cudaGetLastError();
+    return launch_kernel(channel_reduce_kernel<0, false>, dim3(rows_grid(M, rpi * 8, num_sms, 2)), dim3(256), (size_t)rpi * 2 * C * sizeof(float), st,
+                         x, nullptr, nullptr, nullptr, stats, M, C, 0, nullptr, nullptr);
 }
 cudaError_t launch_bn_bwd_reduce(const __nv_bfloat16* dy, const __nv_bfloat16* y, const __nv_bfloat16* x, const float* mean_rstd,
                                  float* dsum, long long M, int C, int relu, int num_sms, cudaStream_t st, const float* gamma,
@@ -123,9 +125,8 @@ cudaError_t launch_bn_bwd_reduce(const __nv_bfloat16* dy, const __nv_bfloat16* y
     const int rpi = 256 / (C / 8);
     const int grid = rows_grid(M, rpi * 8, num_sms, 2);
     const size_t smem = (size_t)rpi * 2 * C * sizeof(float);
-    if (relu == 2) channel_reduce_kernel<1, true><<<grid, 256, smem, st>>>(x, dy, y, mean_rstd, dsum, M, C, relu, gamma, beta);
-    else channel_reduce_kernel<1, false><<<grid, 256, smem, st>>>(x, dy, y, mean_rstd, dsum, M, C, relu);
-    return cudaGetLastError();
+    if (relu == 2) return launch_kernel(channel_reduce_kernel<1, true>, dim3(grid), dim3(256), smem, st, x, dy, y, mean_rstd, dsum, M, C, relu, gamma, beta);
+    return launch_kernel(channel_reduce_kernel<1, false>, dim3(grid), dim3(256), smem, st, x, dy, y, mean_rstd, dsum, M, C, relu, nullptr, nullptr);
 }
 
 __global__ void bn_finalize_kernel(const float* __restrict__ stats, int slots, float* __restrict__ mean_rstd, float* running_mean,
@@ -166,6 +167,8 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __re
                                                          __nv_bfloat16* __restrict__ y, const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, float* __restrict__ mean_rstd,
                                                          long long M, int C, int relu, BnFinalize fin) {
+    pdl_wait();
+    pdl_trigger();
     const int tpr = C / 8, rpi = 256 / tpr;
     const int cg = threadIdx.x % tpr, ry = threadIdx.x / tpr;
     float sc[8], sh[8];
@@ -216,8 +219,8 @@ cudaError_t launch_bn_apply(const __nv_bfloat16* x, const __nv_bfloat16* res, __
     if (!chan_ok(C)) return cudaErrorInvalidValue;
     const int rpi = 256 / (C / 8);
     BnFinalize fin{fin_mode, stats, slots, count, eps, momentum, running_mean, running_var};
-    bn_apply_kernel<<<rows_grid(M, rpi * 4, num_sms, 8), 256, 0, st>>>(x, res, y, gamma, beta, mean_rstd, M, C, relu, fin);
-    return cudaGetLastError();
+    return launch_kernel(bn_apply_kernel, dim3(rows_grid(M, rpi * 4, num_sms, 8)), dim3(256), (size_t)0, st, x, res, y, gamma, beta, mean_rstd, M, C,
+                         relu, fin);
 }
 
 template <bool kRecompute>
@@ -227,6 +230,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* 
                                                              __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dres,
                                                              float* dgamma, float* dbeta, long long M, int C, int relu,
                                                              const float* __restrict__ beta = nullptr) {
+    pdl_wait();
+    pdl_trigger();
     const int tpr = C / 8, rpi = 256 / tpr;
     const int cg = threadIdx.x % tpr, ry = threadIdx.x / tpr;
     float mu[8], rs[8], g[8], k1[8], k2[8], msh[8];
@@ -267,9 +272,11 @@ cudaError_t launch_bn_bwd_apply(const __nv_bfloat16* dy, const __nv_bfloat16* y,
     if (!chan_ok(C) || (relu == 2 && !beta) || (relu == 1 && !y)) return cudaErrorInvalidValue;
     const int rpi = 256 / (C / 8);
     const int grid = rows_grid(M, rpi * 4, num_sms, 8);
-    if (relu == 2) bn_bwd_apply_kernel<true><<<grid, 256, 0, st>>>(dy, y, x, gamma, mean_rstd, dsum, dx, dres, dgamma, dbeta, M, C, relu, beta);
-    else bn_bwd_apply_kernel<false><<<grid, 256, 0, st>>>(dy, y, x, gamma, mean_rstd, dsum, dx, dres, dgamma, dbeta, M, C, relu);
-    return cudaGetLastError();
+    if (relu == 2)
+        return launch_kernel(bn_bwd_apply_kernel<true>, dim3(grid), dim3(256), (size_t)0, st, dy, y, x, gamma, mean_rstd, dsum, dx, dres, dgamma, dbeta, M,
+                             C, relu, beta);
+    return launch_kernel(bn_bwd_apply_kernel<false>, dim3(grid), dim3(256), (size_t)0, st, dy, y, x, gamma, mean_rstd, dsum, dx, dres, dgamma, dbeta, M, C,
+                         relu, nullptr);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

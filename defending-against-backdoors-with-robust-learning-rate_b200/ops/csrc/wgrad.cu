@@ -91,6 +91,8 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_acc = sh->tmem_base;
+    pdl_wait();        // prologue above: parameters, shared memory, TMEM only
+    pdl_trigger();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -208,8 +210,7 @@ static cudaError_t launch_wg(const CUtensorMap& tmA, const CUtensorMap& tmB, Wgr
     p.kb_per_cta = (p.num_kb + splits - 1) / splits;
     splits = (p.num_kb + p.kb_per_cta - 1) / p.kb_per_cta;
     dim3 grid(co_tiles * p.ci_tiles, tap_groups, splits);
-    umma_wgrad_kernel<BNW><<<grid, WG_THREADS, WgCfg<BNW>::kSmem, st>>>(tmA, tmB, p);
-    return cudaGetLastError();
+    return launch_kernel(umma_wgrad_kernel<BNW>, grid, dim3(WG_THREADS), (size_t)WgCfg<BNW>::kSmem, st, tmA, tmB, p);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -268,6 +269,8 @@ umma_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_acc = sh->tmem_base;
+    pdl_wait();        // prologue above: parameters, shared memory, TMEM only
+    pdl_trigger();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -375,8 +378,7 @@ cudaError_t launch_conv_wgrad_halo_bf16(const void* dy, const void* x, float* dW
         const uint32_t b[4] = {64, 16, 18, 1};
         RLR_CUDA_CHECK(make_tmap_bf16(&tmB, x, 4, d, s, b));
     }
-    umma_wgrad_halo_kernel<<<dim3(co_tiles, 3, splits), WG_THREADS, WH_SMEM, st>>>(tmA, tmB, p);
-    return cudaGetLastError();
+    return launch_kernel(umma_wgrad_halo_kernel, dim3(co_tiles, 3, splits), dim3(WG_THREADS), (size_t)WH_SMEM, st, tmA, tmB, p);
 }
 
 static int pow2_ceil_(int x) { int q = 1; while (q < x) q <<= 1; return q; }

@@ -176,3 +176,46 @@ def test_bn_backward_with_recomputed_relu_mask(C, M):
     assert float(mism) < 1e-3, float(mism)
     torch.testing.assert_close(res[True][1], res[False][1], rtol=2e-3, atol=2e-2 * M ** 0.5)
     torch.testing.assert_close(res[True][2], res[False][2], rtol=2e-3, atol=2e-2 * M ** 0.5)
+
+
+def test_programmatic_dependent_launch_matches_plain_launches():
+    """RLR_PDL: hot kernels launched with programmatic stream serialization (prologue overlaps the predecessor's tail, then
+    griddepcontrol.wait).  Eager and CUDA-graph-captured ResNet-18 steps must reproduce the plain-launch results."""
+    from rlr_b200.models import get_layout
+    from rlr_b200.models.native import NativeNet
+    torch.manual_seed(0)
+    lay = get_layout("resnet18")
+    B = 64
+    w = lay.init_(torch.zeros(lay.n_total, device=DEV), 1)
+    x = torch.randn(B, 32, 32, 3, device=DEV).to(BF)
+    t = torch.randint(0, 10, (B,), device=DEV)
+    res = {}
+    try:
+        for mode in ("plain", "pdl", "pdl-graph"):
+            ops.ext().set_pdl(mode != "plain")
+            net = NativeNet(lay, DEV, B, impl="sm100")
+            wi, g = w.clone(), torch.zeros_like(w)
+            net.bind(wi, wi.to(BF), g)
+
+            def step():
+                logits = net.forward(x, True)
+                _, dl = ops.softmax_xent(logits, t)
+                net.backward(dl)
+                return logits
+
+            logits = step()                       # eager (also allocates every scratch buffer before a capture)
+            if mode == "pdl-graph":
+                torch.cuda.synchronize()
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr):
+                    logits = step()
+                wi.copy_(w)                      # the eager step advanced the BatchNorm running statistics: restore, then replay
+                gr.replay()
+            torch.cuda.synchronize()
+            res[mode] = (logits.float().clone(), g[: lay.n_vote].clone())
+    finally:
+        ops.ext().set_pdl(False)
+    for mode in ("pdl", "pdl-graph"):
+        assert float((res["plain"][0] - res[mode][0]).abs().max() / res["plain"][0].abs().max()) < 2e-2, mode
+        cos = torch.nn.functional.cosine_similarity(res["plain"][1].double(), res[mode][1].double(), dim=0)
+        assert float(cos) > 0.999, (mode, float(cos))
