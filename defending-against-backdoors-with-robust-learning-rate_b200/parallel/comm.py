@@ -16,6 +16,7 @@ class DistContext:
     local_rank: int = 0
     device: torch.device = torch.device("cpu")
     backend: str = "none"
+    single_node: bool = True      # every rank on one host: peer-mapped symmetric memory (NVLink / NVSwitch) is available
 
     @property
     def is_dist(self):
@@ -84,4 +85,7 @@ def init_distributed(device=None, backend: str | None = None) -> DistContext:
     if not dist.is_initialized():
         kw = {"device_id": dev} if be == "nccl" else {}
         dist.init_process_group(backend=be, rank=rank, world_size=world, **kw)
-    return DistContext(rank, world, local_rank, dev, be)
+    # The fused aggregation kernel addresses every peer's memory directly, which needs all ranks under one NVSwitch domain;
+    # jobs that span hosts fall back to the NCCL all-gather transport (FusedAggregator, backend "auto").
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    return DistContext(rank, world, local_rank, dev, be, single_node=(local_world >= world))

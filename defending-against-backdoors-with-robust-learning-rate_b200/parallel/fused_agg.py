@@ -31,6 +31,12 @@ class FusedAggregator:
         dev = ctx.device
         if backend == "auto":
             backend = "fused" if (dev.type == "cuda") else ("gloo" if ctx.is_dist else "local")
+            if backend == "fused" and ctx.is_dist and not getattr(ctx, "single_node", True):
+                backend = "nccl"       # ranks on several hosts: no common peer-memory domain -> all-gather transport + local kernel
+                if ctx.is_main:
+                    print("[parallel] ranks span several hosts: aggregation uses the NCCL all-gather transport")
+        if backend == "fused" and ctx.is_dist and not getattr(ctx, "single_node", True):
+            raise ValueError("backend=fused needs all ranks on one host (peer-mapped memory); use --backend nccl across hosts")
         if backend == "fused" and dev.type != "cuda":
             raise ValueError("backend=fused needs CUDA devices")
         self.backend = backend
