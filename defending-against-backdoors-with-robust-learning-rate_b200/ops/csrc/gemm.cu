@@ -319,6 +319,31 @@ static cudaError_t launch_bn_occ3(const CUtensorMap& tmA, const CUtensorMap& tmB
     return launch_kernel(umma_conv_gemm_kernel<BN, false, false, 3>, grid, dim3(kThreads), Cfg::kSmemBytes, st, tmA, tmB, p);
 }
 
+// gemm_2cta.cu (opt-in, RLR_CONV_2CTA=1): CTA pairs, tcgen05.mma.cta_group::2 with M = 256, half of the B tile per CTA
+template <int BN>
+cudaError_t launch_2cta_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, int m_tiles, cudaStream_t st);
+static int g_2cta = -1;
+void set_conv_2cta(int on) { g_2cta = on ? 1 : 0; }
+static int sm_count() {
+    static const int sms = [] {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 148;
+        return n;
+    }();
+    return sms;
+}
+// tile width of the CTA-pair kernel for an M-tiles x N problem, 0 = use the single-CTA kernels (flag off, shape not eligible, or
+// too few pairs to cover the SMs)
+static int pair_bn(int m_tiles, int N, bool eligible) {
+    if (g_2cta < 0) { const char* e = getenv("RLR_CONV_2CTA"); g_2cta = (e && atoi(e) > 0) ? 1 : 0; }
+    if (!g_2cta || !eligible || N % 128) return 0;
+    const int ctas_m = (m_tiles + 1) / 2 * 2;
+    int bn = (N % 256 == 0) ? 256 : 128;
+    if (bn == 256 && ctas_m * (N / 256) < sm_count()) bn = 128;
+    if (ctas_m * (N / bn) < sm_count()) return 0;
+    return bn;
+}
+
 static int g_persistent = -1;   // -1: take RLR_PERSISTENT_CONV from the environment on first use
 void set_persistent_conv(int on) { g_persistent = on ? 1 : 0; }
 
@@ -358,7 +383,9 @@ static int pick_bn(int N) { return (N % 128 == 0) ? 128 : 64; }
 cudaError_t launch_gemm_bf16(const void* A, const void* B, void* out, int M, int N, int K, int lda, int ldb, int ldc,
                              const float* bias, int relu, int accumulate, float* stats, cudaStream_t st) {
     if (K % BK || N % 8 || M <= 0) return cudaErrorInvalidValue;
-    const int bn = pick_bn(N);
+    const int m_tiles = (M + BM - 1) / BM;
+    const int bn2 = pair_bn(m_tiles, N, stats == nullptr);
+    const int bn = bn2 ? bn2 : pick_bn(N);
     CUtensorMap tmA, tmB;
     {
         const uint64_t d[2] = {(uint64_t)K, (uint64_t)M}, s[1] = {(uint64_t)lda * 2};
@@ -367,13 +394,13 @@ cudaError_t launch_gemm_bf16(const void* A, const void* B, void* out, int M, int
     }
     {
         const uint64_t d[2] = {(uint64_t)K, (uint64_t)N}, s[1] = {(uint64_t)ldb * 2};
-        const uint32_t b[2] = {BK, (uint32_t)bn};
+        const uint32_t b[2] = {BK, (uint32_t)(bn2 ? bn2 / 2 : bn)};       // CTA pair: each CTA stages half of the B tile
         RLR_CUDA_CHECK(make_tmap_bf16(&tmB, B, 2, d, s, b));
     }
     ConvGemmParams p{};
     p.M = M; p.N = N; p.num_kb = K / BK; p.mode = 0; p.in_stride = 1; p.out_stride = 1;
     p.out = out; p.ldc = ldc; p.bias = bias; p.stats = stats; p.relu = relu; p.accumulate = accumulate;
-    const int m_tiles = (M + BM - 1) / BM;
+    if (bn2) return bn2 == 256 ? launch_2cta_bn<256>(tmA, tmB, p, m_tiles, st) : launch_2cta_bn<128>(tmA, tmB, p, m_tiles, st);
     return bn == 128 ? launch_bn<128>(tmA, tmB, p, m_tiles, st) : launch_bn<64>(tmA, tmB, p, m_tiles, st);
 }
 
@@ -429,8 +456,10 @@ cudaError_t launch_conv_bf16(const void* x, const void* w, void* out, int NB, in
     } else {
         const uint64_t K = (uint64_t)ntaps * Cin;
         const uint64_t d[2] = {K, (uint64_t)Cout}, s[1] = {K * 2};
-        const uint32_t b[2] = {BK, (uint32_t)bn};
+        const int bn2 = pair_bn(m_tiles, Cout, stats == nullptr);
+        const uint32_t b[2] = {BK, (uint32_t)(bn2 ? bn2 / 2 : bn)};       // CTA pair: each CTA stages half of the filter tile
         RLR_CUDA_CHECK(make_tmap_bf16(&tmB, w, 2, d, s, b));
+        if (bn2) return bn2 == 256 ? launch_2cta_bn<256>(tmA, tmB, p, m_tiles, st) : launch_2cta_bn<128>(tmA, tmB, p, m_tiles, st);
     }
     return bn == 128 ? launch_bn<128>(tmA, tmB, p, m_tiles, st) : launch_bn<64>(tmA, tmB, p, m_tiles, st);
 }

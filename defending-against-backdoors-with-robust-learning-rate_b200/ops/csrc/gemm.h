@@ -37,6 +37,8 @@ cudaError_t launch_gemm_bf16(const void* A, const void* B, void* out, int M, int
                              const float* bias, int relu, int accumulate, float* stats, cudaStream_t st);
 // programmatic dependent launch for the hot kernels (common.cuh: launch_kernel / pdl_wait); default: RLR_PDL env, off
 void set_pdl(int on);
+// opt-in CTA-pair kernel (gemm_2cta.cu: tcgen05.mma.cta_group::2, M = 256, half a B tile per CTA); default: RLR_CONV_2CTA env, off
+void set_conv_2cta(int on);
 // opt-in persistent tile scheduler for the generic conv / GEMM kernel (gemm_persistent.cu); default: RLR_PERSISTENT_CONV env
 void set_persistent_conv(int on);
 // three CTAs per SM: level 0 never, 1 (default) for the 64-wide tile, 2 also for the 128-wide tile (RLR_CONV_OCC3 env)

@@ -257,6 +257,7 @@ void linear_small_bwd(at::Tensor x, at::Tensor dy, at::Tensor w, c10::optional<a
 void register_gemm_bindings(py::module_& m) {
     m.attr("STAT_SLOTS") = rlr::kStatSlots;
     m.def("set_persistent_conv", [](bool on) { rlr::set_persistent_conv(on ? 1 : 0); });
+    m.def("set_conv_2cta", [](bool on) { rlr::set_conv_2cta(on ? 1 : 0); });
     m.def("set_pdl", [](bool on) { rlr::set_pdl(on ? 1 : 0); });
     m.def("set_conv_occ3", [](int64_t level) { rlr::set_conv_occ3((int)level); });
     m.def("gemm_bf16", &gemm_bf16);

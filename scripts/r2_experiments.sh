@@ -1,20 +1,38 @@
 #!/bin/bash
-# Round-2 opener: one 1-GPU call that validates and measures every opt-in path written blind at the end of round 1.
-#   gpurun --timeout 600 -- 'bash scripts/r2_experiments.sh'
-# Outputs: gpurun_out/r2_exp_tests.txt, gpurun_out/r2_bench_<flag>.json
+# Round-2 opener: ONE 1-GPU call that validates and measures every opt-in path written blind at the end of round 1.
+#   gpurun --timeout 900 -- 'bash scripts/r2_experiments.sh'
+# Each experiment: its numerics test (own process, own timeout: a deadlocked kernel only loses that experiment), then -- only if
+# the test passed -- the headline bench with the flag on.  The default build is benched first and last (box drift).
+# Outputs: gpurun_out/r2_exp_<name>.txt, gpurun_out/r2_bench_<name>.json, summary in gpurun_out/r2_summary.txt
 mkdir -p gpurun_out
-RLR_EXPERIMENTAL=1 timeout 240 python -m pytest tests/test_gpu_experimental.py -m gpu -q -x > gpurun_out/r2_exp_tests.txt 2>&1
-echo "experimental tests exit $?" | tee -a gpurun_out/r2_exp_tests.txt
-tail -5 gpurun_out/r2_exp_tests.txt
-for flag in NONE RLR_PDL RLR_STRIDED_TMA RLR_IM2COL_STEM RLR_BN_RECOMPUTE RLR_CONV_OCC3; do
-    val=1; [ $flag = RLR_CONV_OCC3 ] && val=2
-    env $flag=$val timeout 120 python bench.py --steps 3 --warmup 3 --no_e2e > gpurun_out/r2_bench_$flag.json 2> gpurun_out/r2_bench_$flag.err
-    python - <<PY
-import json
+: > gpurun_out/r2_summary.txt
+bench() {   # name, env assignment
+    env $2 timeout 150 python bench.py --steps 3 --warmup 3 --no_e2e > gpurun_out/r2_bench_$1.json 2> gpurun_out/r2_bench_$1.err
+    python - "$1" <<'PY' | tee -a gpurun_out/r2_summary.txt
+import json, sys
+name = sys.argv[1]
 try:
-    d = json.loads(open("gpurun_out/r2_bench_$flag.json").read().strip().splitlines()[-1])
-    print("$flag", d["ms_per_step"], "ms/round", d["value"], "rounds/s")
+    d = json.loads(open(f"gpurun_out/r2_bench_{name}.json").read().strip().splitlines()[-1])
+    print(f"bench {name}: {d['ms_per_step']:.1f} ms/round  {d['value']:.4f} rounds/s")
 except Exception as e:
-    print("$flag", "FAILED", e)
+    print(f"bench {name}: FAILED ({e})")
 PY
-done
+}
+bench default_first NONE=1
+#            name          pytest -k expression                          flag
+while read -r name expr flag; do
+    [ -z "$name" ] && continue
+    RLR_EXPERIMENTAL=1 timeout 150 python -m pytest tests/test_gpu_experimental.py -m gpu -q -s -k "$expr" > gpurun_out/r2_exp_$name.txt 2>&1
+    rc=$?
+    echo "test $name: exit $rc ($(tail -1 gpurun_out/r2_exp_$name.txt))" | tee -a gpurun_out/r2_summary.txt
+    [ $rc -eq 0 ] && bench $name $flag
+done <<'LIST'
+strided      strided_tma                  RLR_STRIDED_TMA=1
+stem         im2col_stem                  RLR_IM2COL_STEM=1
+bnmask       recomputed_relu_mask         RLR_BN_RECOMPUTE=1
+occ3x        occ3_level2                  RLR_CONV_OCC3=2
+pdl          programmatic_dependent       RLR_PDL=1
+pair         cta_pair                     RLR_CONV_2CTA=1
+LIST
+bench default_last NONE=1
+cat gpurun_out/r2_summary.txt

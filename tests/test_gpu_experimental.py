@@ -219,3 +219,38 @@ def test_programmatic_dependent_launch_matches_plain_launches():
         assert float((res["plain"][0] - res[mode][0]).abs().max() / res["plain"][0].abs().max()) < 2e-2, mode
         cos = torch.nn.functional.cosine_similarity(res["plain"][1].double(), res[mode][1].double(), dim=0)
         assert float(cos) > 0.999, (mode, float(cos))
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,s,p", [(128, 16, 16, 128, 128, 3, 1, 1), (256, 8, 8, 256, 256, 3, 1, 1), (512, 8, 8, 256, 512, 3, 1, 1),
+                                                   (254, 8, 8, 256, 256, 3, 1, 1), (128, 32, 32, 64, 128, 3, 2, 1), (256, 16, 16, 128, 256, 1, 2, 0)])
+def test_conv_cta_pair_kernel_matches_single_cta(B, H, W, Cin, Cout, k, s, p):
+    """RLR_CONV_2CTA: tcgen05.mma.cta_group::2 (M = 256 per CTA pair, half a filter tile per CTA, multicast commits) against the
+    single-CTA kernel: forward with bias+ReLU, accumulate epilogue through the transposed-filter data gradient, plain GEMM."""
+    torch.manual_seed(B + H + Cin)
+    x = torch.randn(B, H, W, Cin, device=DEV).to(BF)
+    w = (torch.randn(Cout, k, k, Cin, device=DEV) / (k * k * Cin) ** 0.5).to(BF)
+    bias = torch.randn(Cout, device=DEV) * 0.1
+    Ho, Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    A = torch.randn(32768, 512, device=DEV).to(BF)
+    Bm = (torch.randn(Cout, 512, device=DEV) / 16).to(BF)
+    base = torch.randn(32768, Cout, device=DEV).to(BF)
+    outs = {}
+    try:
+        for on in (False, True):
+            ops.ext().set_conv_2cta(on)
+            y = torch.full((B, Ho, Wo, Cout), 7.0, device=DEV, dtype=BF)
+            ops.conv2d_fwd_sm100(x, w, bias, y, s, p, True, None, tag=("2cta", on, B, H, Cin, k, s))
+            g0 = torch.empty(32768, Cout, device=DEV, dtype=BF)
+            ops.ext().gemm_bf16(A, Bm, g0, bias, False, False, None)
+            g1 = base.clone()
+            ops.ext().gemm_bf16(A, Bm, g1, None, False, True, None)      # accumulate epilogue
+            torch.cuda.synchronize()
+            outs[on] = (y, g0, g1)
+    finally:
+        ops.ext().set_conv_2cta(False)
+    ref = torch.relu(torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), bias, s, p)).permute(0, 2, 3, 1)
+    assert float((outs[True][0].float() - ref).abs().max() / ref.abs().max()) < 1e-2
+    for name, a, b in zip(("conv", "gemm", "gemm+acc"), outs[False], outs[True]):
+        err = float((a.float() - b.float()).abs().max() / (a.float().abs().max() + 1e-6))
+        print(name, "identical" if torch.equal(a, b) else f"max rel diff {err:.2e}")
+        assert err < 4e-3, (name, err)
