@@ -102,6 +102,11 @@ cudaError_t launch_filter_transpose(const __nv_bfloat16* w, __nv_bfloat16* wt, i
 // small dense layers on CUDA cores (heads with N=10): y = x W^T + b ; dx = dy W ; dW = dy^T x ; db = sum dy
 cudaError_t launch_linear_small_fwd(const __nv_bfloat16* x, const __nv_bfloat16* w, const float* bias, __nv_bfloat16* y, int B, int K,
                                     int N, int relu, cudaStream_t st);
+// v2 head kernels (opt-in): more blocks / staged weights; bwd2 ACCUMULATES into dW, db (must be zero on entry)
+cudaError_t launch_linear_small_fwd2(const __nv_bfloat16* x, const __nv_bfloat16* w, const float* bias, __nv_bfloat16* y, int B, int K,
+                                     int N, int relu, cudaStream_t st);
+cudaError_t launch_linear_small_bwd2(const __nv_bfloat16* x, const __nv_bfloat16* dy, const __nv_bfloat16* w, __nv_bfloat16* dx,
+                                     float* dw, float* db, int B, int K, int N, int accumulate_dx, cudaStream_t st);
 cudaError_t launch_linear_small_bwd(const __nv_bfloat16* x, const __nv_bfloat16* dy, const __nv_bfloat16* w, __nv_bfloat16* dx,
                                     float* dw, float* db, int B, int K, int N, int accumulate_dx, cudaStream_t st);
 

@@ -252,6 +252,17 @@ void linear_small_bwd(at::Tensor x, at::Tensor dy, at::Tensor w, c10::optional<a
     check(rlr::launch_linear_small_bwd(bf(x), bf(dy), bf(w), const_cast<__nv_bfloat16*>(bfo(dx)), (float*)dw.data_ptr(), opt<float>(db),
                                        x.size(0), x.size(1), w.size(0), accumulate_dx, cur_stream()), "linear_small_bwd");
 }
+void linear_small_fwd2(at::Tensor x, at::Tensor w, c10::optional<at::Tensor> bias, at::Tensor y, bool relu) {
+    c10::cuda::CUDAGuard g(x.device());
+    check(rlr::launch_linear_small_fwd2(bf(x), bf(w), opt<const float>(bias), bfm(y), x.size(0), x.size(1), w.size(0), relu, cur_stream()), "linear_small_fwd2");
+}
+// dw / db are ACCUMULATED into (zero them first)
+void linear_small_bwd2(at::Tensor x, at::Tensor dy, at::Tensor w, c10::optional<at::Tensor> dx, at::Tensor dw, c10::optional<at::Tensor> db,
+                       bool accumulate_dx) {
+    c10::cuda::CUDAGuard g(x.device());
+    check(rlr::launch_linear_small_bwd2(bf(x), bf(dy), bf(w), const_cast<__nv_bfloat16*>(bfo(dx)), (float*)dw.data_ptr(), opt<float>(db),
+                                        x.size(0), x.size(1), w.size(0), accumulate_dx, cur_stream()), "linear_small_bwd2");
+}
 }  // namespace
 
 void register_gemm_bindings(py::module_& m) {
@@ -287,4 +298,6 @@ void register_gemm_bindings(py::module_& m) {
     m.def("filter_gather_transpose", &filter_gather_transpose);
     m.def("linear_small_fwd", &linear_small_fwd);
     m.def("linear_small_bwd", &linear_small_bwd);
+    m.def("linear_small_fwd2", &linear_small_fwd2);
+    m.def("linear_small_bwd2", &linear_small_bwd2);
 }

@@ -683,6 +683,118 @@ __global__ void __launch_bounds__(256) linear_small_bwd_kernel(const __nv_bfloat
         }
     }
 }
+// v2 (opt-in, RLR_HEAD_V2): the weight/bias gradient of the classifier head is spread over (K/64) x (B/16) blocks that stage their
+// 16 dy rows in shared memory and add their partial sums with float atomics -- dW/db must be ZERO on entry (the native plan zeroes
+// the flat gradient once per step).  v1 used K/64 blocks that each walked the whole batch (30 us for a 256 x 512 x 10 layer).
+__global__ void __launch_bounds__(256) linear_small_bwd2_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                                                                  const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ dx,
+                                                                  float* __restrict__ dw, float* __restrict__ db, int B, int K, int N,
+                                                                  int accumulate_dx, int kchunks, int bsplit) {
+    pdl_wait();
+    pdl_trigger();
+    __shared__ float sdy[16][32];
+    const int wblocks = kchunks * bsplit;
+    if ((int)blockIdx.x < wblocks) {
+        const int kc = blockIdx.x % kchunks, bs = blockIdx.x / kchunks;
+        const int b0 = bs * 16;
+        for (int i = threadIdx.x; i < 16 * 32; i += 256) {
+            const int r = i >> 5, n = i & 31;
+            sdy[r][n] = (b0 + r < B && n < N) ? __bfloat162float(dy[(size_t)(b0 + r) * N + n]) : 0.f;
+        }
+        __syncthreads();
+        // 256 threads = 64 columns x 4 row groups of 4 samples
+        const int kk = threadIdx.x & 63, rg = threadIdx.x >> 6, k = kc * 64 + kk;
+        float xv[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int b = b0 + rg * 4 + r;
+            xv[r] = (k < K && b < B) ? __bfloat162float(x[(size_t)b * K + k]) : 0.f;
+        }
+        if (k < K) {
+            for (int n = 0; n < N; ++n) {
+                float a = 0.f;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) a += xv[r] * sdy[rg * 4 + r][n];
+                atomicAdd(dw + (size_t)n * K + k, a);
+            }
+        }
+        if (kc == 0 && db && threadIdx.x < N) {
+            float a = 0.f;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) a += sdy[r][threadIdx.x];
+            atomicAdd(db + threadIdx.x, a);
+        }
+    } else if (dx) {                                       // dx[b][k] = sum_n dy[b][n] w[n][k], two columns per thread
+        const long long total2 = (long long)B * (K / 2);
+        const int nb = gridDim.x - wblocks;
+        for (long long t = (long long)(blockIdx.x - wblocks) * 256 + threadIdx.x; t < total2; t += (long long)nb * 256) {
+            const int b = (int)(t / (K / 2)), k = (int)(t % (K / 2)) * 2;
+            float a0 = 0.f, a1 = 0.f;
+            for (int n = 0; n < N; ++n) {
+                const float d = __bfloat162float(dy[(size_t)b * N + n]);
+                const float2 wv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(w + (size_t)n * K + k));
+                a0 += d * wv.x; a1 += d * wv.y;
+            }
+            __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(dx + (size_t)b * K + k);
+            if (accumulate_dx) { const float2 old = __bfloat1622float2(*o); a0 += old.x; a1 += old.y; }
+            *o = __floats2bfloat162_rn(a0, a1);
+        }
+    }
+}
+cudaError_t launch_linear_small_bwd2(const __nv_bfloat16* x, const __nv_bfloat16* dy, const __nv_bfloat16* w, __nv_bfloat16* dx,
+                                     float* dw, float* db, int B, int K, int N, int accumulate_dx, cudaStream_t st) {
+    if (N > 32 || (K & 1)) return cudaErrorInvalidValue;
+    const int kchunks = (K + 63) / 64, bsplit = (B + 15) / 16;
+    long long dxb = dx ? ((long long)B * (K / 2) + 255) / 256 : 0;
+    if (dxb > 592) dxb = 592;
+    return launch_kernel(linear_small_bwd2_kernel, dim3(kchunks * bsplit + (int)dxb), dim3(256), (size_t)0, st, x, dy, w, dx, dw, db, B, K, N,
+                         accumulate_dx, kchunks, bsplit);
+}
+
+// v2 forward: 8 samples per 256-thread block, one warp per sample, the whole weight matrix staged in shared memory once per block
+// (N * K bf16 <= 32 KB) and the k loop unrolled so the loads of a row are all in flight together.
+__global__ void __launch_bounds__(256) linear_small_fwd2_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+                                                                  const float* __restrict__ bias, __nv_bfloat16* __restrict__ y,
+                                                                  int B, int K, int N, int relu) {
+    pdl_wait();
+    pdl_trigger();
+    extern __shared__ __nv_bfloat16 sw[];                 // [N][K]
+    for (int i = threadIdx.x * 8; i < N * K; i += 256 * 8) *reinterpret_cast<uint4*>(sw + i) = *reinterpret_cast<const uint4*>(w + i);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * 8 + warp;
+    if (b >= B) return;
+    float acc[32];
+#pragma unroll
+    for (int n = 0; n < 32; ++n) acc[n] = 0.f;
+#pragma unroll 4
+    for (int k = lane * 2; k < K; k += 64) {
+        const float2 xv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(x + (size_t)b * K + k));
+#pragma unroll
+        for (int n = 0; n < 32; ++n)
+            if (n < N) {
+                const float2 wv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sw + (size_t)n * K + k));
+                acc[n] += xv.x * wv.x + xv.y * wv.y;
+            }
+    }
+#pragma unroll
+    for (int n = 0; n < 32; ++n) {
+        if (n < N) {
+            float v = warp_sum(acc[n]);
+            if (lane == 0) {
+                v += bias ? bias[n] : 0.f;
+                if (relu) v = fmaxf(v, 0.f);
+                y[(size_t)b * N + n] = __float2bfloat16(v);
+            }
+        }
+    }
+}
+cudaError_t launch_linear_small_fwd2(const __nv_bfloat16* x, const __nv_bfloat16* w, const float* bias, __nv_bfloat16* y, int B, int K,
+                                     int N, int relu, cudaStream_t st) {
+    if (N > 32 || (K & 1) || (N * K) % 8 || (size_t)N * K * 2 > 48 * 1024) return cudaErrorInvalidValue;
+    return launch_kernel(linear_small_fwd2_kernel, dim3((B + 7) / 8), dim3(256), (size_t)N * K * 2, st, x, w, bias, y, B, K, N, relu);
+}
+
 cudaError_t launch_linear_small_bwd(const __nv_bfloat16* x, const __nv_bfloat16* dy, const __nv_bfloat16* w, __nv_bfloat16* dx,
                                     float* dw, float* db, int B, int K, int N, int accumulate_dx, cudaStream_t st) {
     if (N > 32) return cudaErrorInvalidValue;

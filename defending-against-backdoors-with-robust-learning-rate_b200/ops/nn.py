@@ -23,6 +23,9 @@ USE_IM2COL_STEM = bool(int(os.environ.get("RLR_IM2COL_STEM", "0")))
 # BatchNorm(+ReLU, no residual) backward without reading the layer output: the mask is recomputed from x with the forward's own
 # scale/shift expression.  Opt-in until measured on hardware (RLR_BN_RECOMPUTE=1).
 USE_BN_RECOMPUTE = bool(int(os.environ.get("RLR_BN_RECOMPUTE", "0")))
+# Classifier-head kernels v2 (weights staged in shared memory, weight gradient spread over K/64 x B/16 blocks with float atomics).
+# Opt-in until measured on hardware (RLR_HEAD_V2=1).
+USE_HEAD_V2 = bool(int(os.environ.get("RLR_HEAD_V2", "0")))
 
 
 def _stem_ok(k, stride, cin, cout):
@@ -378,6 +381,9 @@ def linear_fwd(x, w, bias, y, relu, impl):
     N, K = w.shape
     if impl == "sm100":
         if N <= 32:
+            if USE_HEAD_V2 and K % 2 == 0 and (N * K) % 8 == 0 and N * K * 2 <= 48 * 1024:
+                _ext().linear_small_fwd2(x.contiguous(), w, bias, y, bool(relu))
+                return
             _ext().linear_small_fwd(x.contiguous(), w, bias, y, bool(relu))
             return
         if K % 64 == 0 and N % 64 == 0:
@@ -392,6 +398,13 @@ def linear_fwd(x, w, bias, y, relu, impl):
 def linear_bwd(x, dy, w, dx, dw, db, acc_dx, impl, zero=True):
     N, K = w.shape
     if impl == "sm100" and N <= 32:
+        if USE_HEAD_V2 and K % 2 == 0:
+            if zero:                  # v2 accumulates with atomics (the native plan passes zero=False: the flat gradient is pre-zeroed)
+                dw.zero_()
+                if db is not None:
+                    db.zero_()
+            _ext().linear_small_bwd2(x.contiguous(), dy.contiguous(), w, dx, dw, db, bool(acc_dx))
+            return
         _ext().linear_small_bwd(x.contiguous(), dy.contiguous(), w, dx, dw, db, bool(acc_dx))
         return
     dyf = dy.to(x.dtype)

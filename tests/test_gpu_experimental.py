@@ -254,3 +254,38 @@ def test_conv_cta_pair_kernel_matches_single_cta(B, H, W, Cin, Cout, k, s, p):
         err = float((a.float() - b.float()).abs().max() / (a.float().abs().max() + 1e-6))
         print(name, "identical" if torch.equal(a, b) else f"max rel diff {err:.2e}")
         assert err < 4e-3, (name, err)
+
+
+@pytest.mark.parametrize("B,K,N,relu", [(256, 512, 10, False), (100, 256, 10, False), (37, 128, 10, True), (256, 1024, 16, False)])
+def test_head_kernels_v2(B, K, N, relu):
+    """RLR_HEAD_V2 classifier-head kernels against fp32 references (forward, dX with/without accumulation, dW, db)."""
+    torch.manual_seed(B + K)
+    x = torch.randn(B, K, device=DEV).to(BF)
+    w = (torch.randn(N, K, device=DEV) / K ** 0.5).to(BF)
+    bias = torch.randn(N, device=DEV) * 0.1
+    dy = (torch.randn(B, N, device=DEV) / B).to(BF)
+    base = torch.randn(B, K, device=DEV).to(BF)
+    old = nn.USE_HEAD_V2
+    nn.USE_HEAD_V2 = True
+    try:
+        y = torch.empty(B, N, device=DEV, dtype=BF)
+        nn.linear_fwd(x, w, bias, y, relu, "sm100")
+        dx0, dx1 = torch.empty_like(x), base.clone()
+        dw, db = torch.full((N, K), 3.0, device=DEV), torch.full((N,), 3.0, device=DEV)
+        nn.linear_bwd(x, dy, w, dx0, dw, db, False, "sm100", zero=True)
+        dw2, db2 = torch.zeros(N, K, device=DEV), torch.zeros(N, device=DEV)
+        nn.linear_bwd(x, dy, w, dx1, dw2, db2, True, "sm100", zero=False)
+        torch.cuda.synchronize()
+    finally:
+        nn.USE_HEAD_V2 = old
+    ref = x.float() @ w.float().t() + bias
+    if relu:
+        ref = ref.clamp_min(0)
+    assert float((y.float() - ref).abs().max() / ref.abs().max()) < 1e-2
+    dxr = dy.float() @ w.float()
+    assert float((dx0.float() - dxr).abs().max() / dxr.abs().max()) < 1e-2
+    assert float((dx1.float() - (dxr + base.float())).abs().max() / (dxr + base.float()).abs().max()) < 1e-2
+    dwr, dbr = dy.float().t() @ x.float(), dy.float().sum(0)
+    for got_w, got_b in ((dw, db), (dw2, db2)):
+        torch.testing.assert_close(got_w, dwr, rtol=1e-3, atol=1e-4)
+        torch.testing.assert_close(got_b, dbr, rtol=1e-3, atol=1e-4)
