@@ -453,6 +453,8 @@ cudaError_t launch_conv_bf16(const void* x, const void* w, void* out, int NB, in
         const uint64_t d[2] = {cols, (uint64_t)Cin}, s[1] = {cols * 2};
         const uint32_t b[2] = {64, BK};
         RLR_CUDA_CHECK(make_tmap_bf16(&tmB, w, 2, d, s, b));
+        const int bn2 = pair_bn(m_tiles, Cout, true);      // CTA pair: each CTA loads the 64-wide groups of its half of the tile
+        if (bn2) return bn2 == 256 ? launch_2cta_bn<256>(tmA, tmB, p, m_tiles, st) : launch_2cta_bn<128>(tmA, tmB, p, m_tiles, st);
     } else {
         const uint64_t K = (uint64_t)ntaps * Cin;
         const uint64_t d[2] = {K, (uint64_t)Cout}, s[1] = {K * 2};

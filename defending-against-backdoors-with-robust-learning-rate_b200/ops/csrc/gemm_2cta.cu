@@ -14,7 +14,8 @@
 // "accumulator complete" arrivals to the barriers of both CTAs
 //               * TMEM is allocated / freed with the cta_group::2 forms by the same warp of both CTAs, with cluster barriers after
 // the mbarrier initialisation and before the deallocation.
-// K-major B operands only (forward convolutions, GEMM, data gradients through a transposed filter); no statistics epilogue.
+// B operands: K-major (forward convolutions, GEMM) or MN-major boxes of the un-transposed forward filter (data gradients, kBMN:
+// each CTA loads the 64-wide N groups of ITS half of the tile); no statistics epilogue.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -91,7 +92,7 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mas
                  ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
 }
 
-template <int BN>
+template <int BN, bool kBMN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CThreads, 2)
 umma_conv_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvGemmParams p) {
     using Cfg = CCfg<BN>;
@@ -146,21 +147,27 @@ umma_conv_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
                 uint8_t* sa = smem + stage * Cfg::kStageBytes;
                 uint8_t* sb = sa + Cfg::kABytes;
                 if (leader) mbar_expect_tx(&sh->full[stage], 2 * Cfg::kStageBytes);     // bytes of BOTH CTAs land on this barrier
+                const int tap = p.mode == 1 ? kb / p.cblocks : 0, cb = p.mode == 1 ? kb - tap * p.cblocks : 0;
                 if (p.mode == 1) {
-                    const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
                     tma_load_4d_pair(&tmA, &sh->full[stage], sa, cb * CBK, w0 * p.in_stride + p.dw[tap], h0 * p.in_stride + p.dh[tap],
                                      n0 + p.dn[tap]);
                 } else {
                     tma_load_2d_pair(&tmA, &sh->full[stage], sa, kb * CBK, tile_m * CBM);
                 }
-                tma_load_2d_pair(&tmB, &sh->full[stage], sb, kb * CBK, tile_n * BN + (int)cta_rank * (BN / 2));   // my half of the filter rows
+                const int n_half = tile_n * BN + (int)cta_rank * (BN / 2);          // first B row / column of MY half of the tile
+                if (kBMN) {
+                    for (int g = 0; g < BN / 128; ++g)
+                        tma_load_2d_pair(&tmB, &sh->full[stage], sb + g * 8192, p.wtap[tap] * p.wcols + n_half + g * 64, cb * CBK);
+                } else {
+                    tma_load_2d_pair(&tmB, &sh->full[stage], sb, kb * CBK, n_half);
+                }
                 if (++stage == CStages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
         // ================================ MMA issuer: one thread of the LEADER CTA =============================================
         if (leader && lane == 0) {
-            constexpr uint32_t idesc = idesc_bf16(2 * CBM, BN, 0, 0);          // M = 256 across the pair
+            constexpr uint32_t idesc = idesc_bf16(2 * CBM, BN, 0, kBMN ? 1 : 0);   // M = 256 across the pair
             int stage = 0;
             uint32_t phase = 0;
             for (int kb = 0; kb < p.num_kb; ++kb) {
@@ -172,7 +179,7 @@ umma_conv_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
                 for (int k = 0; k < CBK / 16; ++k) {
                     // descriptors are offsets in the issuing CTA's shared memory; the peer's operands sit at the same offsets
                     const uint64_t da = smem_desc_sw128(sa + k * 32, 16, 1024);
-                    const uint64_t db = smem_desc_sw128(sb + k * 32, 16, 1024);
+                    const uint64_t db = kBMN ? smem_desc_sw128(sb + k * 2048, 8192, 1024) : smem_desc_sw128(sb + k * 32, 16, 1024);
                     umma_bf16_pair(tmem_acc, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
                 }
                 umma_commit_pair(&sh->empty[stage], 0x3);      // stage free in both CTAs
@@ -250,17 +257,19 @@ umma_conv_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
 
 }  // namespace
 
-// tmB must have been encoded with a {64, BN/2} box.  Grid: M tiles rounded up to whole pairs x N tiles.
+// tmB must have been encoded with a {64, BN/2} box (K-major B) or the {64, 64} box of the forward filter view (b_mn).  Grid: M tiles rounded up to whole pairs x N tiles.
 template <int BN>
 cudaError_t launch_2cta_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, int m_tiles, cudaStream_t st) {
     using Cfg = CCfg<BN>;
     static bool configured = false;
     if (!configured) {
-        RLR_CUDA_CHECK(cudaFuncSetAttribute(umma_conv_gemm_2cta_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        RLR_CUDA_CHECK(cudaFuncSetAttribute(umma_conv_gemm_2cta_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        RLR_CUDA_CHECK(cudaFuncSetAttribute(umma_conv_gemm_2cta_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         configured = true;
     }
     const dim3 grid((m_tiles + 1) / 2 * 2, (p.N + BN - 1) / BN);
-    return launch_kernel(umma_conv_gemm_2cta_kernel<BN>, grid, dim3(CThreads), (size_t)Cfg::kSmemBytes, st, tmA, tmB, p);
+    if (p.b_mn) return launch_kernel(umma_conv_gemm_2cta_kernel<BN, true>, grid, dim3(CThreads), (size_t)Cfg::kSmemBytes, st, tmA, tmB, p);
+    return launch_kernel(umma_conv_gemm_2cta_kernel<BN, false>, grid, dim3(CThreads), (size_t)Cfg::kSmemBytes, st, tmA, tmB, p);
 }
 template cudaError_t launch_2cta_bn<128>(const CUtensorMap&, const CUtensorMap&, const ConvGemmParams&, int, cudaStream_t);
 template cudaError_t launch_2cta_bn<256>(const CUtensorMap&, const CUtensorMap&, const ConvGemmParams&, int, cudaStream_t);

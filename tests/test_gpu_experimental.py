@@ -244,13 +244,18 @@ def test_conv_cta_pair_kernel_matches_single_cta(B, H, W, Cin, Cout, k, s, p):
             ops.ext().gemm_bf16(A, Bm, g0, bias, False, False, None)
             g1 = base.clone()
             ops.ext().gemm_bf16(A, Bm, g1, None, False, True, None)      # accumulate epilogue
+            dy = (torch.arange(B * Ho * Wo * Cout, device=DEV).reshape(B, Ho, Wo, Cout) % 17 - 8).to(BF) / 8
+            dx0 = torch.full((B, H, W, Cin), 3.0, device=DEV, dtype=BF)
+            dx1 = torch.ones(B, H, W, Cin, device=DEV, dtype=BF)
+            ops.conv2d_dgrad_sm100(dy, w, dx0, s, p, False)             # MN-major B operand (forward filter) in pair mode
+            ops.conv2d_dgrad_sm100(dy, w, dx1, s, p, True)
             torch.cuda.synchronize()
-            outs[on] = (y, g0, g1)
+            outs[on] = (y, g0, g1, dx0, dx1)
     finally:
         ops.ext().set_conv_2cta(False)
     ref = torch.relu(torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), bias, s, p)).permute(0, 2, 3, 1)
     assert float((outs[True][0].float() - ref).abs().max() / ref.abs().max()) < 1e-2
-    for name, a, b in zip(("conv", "gemm", "gemm+acc"), outs[False], outs[True]):
+    for name, a, b in zip(("conv", "gemm", "gemm+acc", "dgrad", "dgrad+acc"), outs[False], outs[True]):
         err = float((a.float() - b.float()).abs().max() / (a.float().abs().max() + 1e-6))
         print(name, "identical" if torch.equal(a, b) else f"max rel diff {err:.2e}")
         assert err < 4e-3, (name, err)
