@@ -1,6 +1,10 @@
 """Layer primitives of the native executor (models/native.py), each with an ``sm100`` back-end (hand-written kernels
 of ops/csrc: gemm.cu = tcgen05/TMEM/TMA implicit-GEMM convolution + GEMM, norm.cu = NHWC bf16 layer kernels) and an
-``aten`` back-end (the same math through PyTorch library calls on the same buffers: CPU path + in-place oracle)."""
+``aten`` back-end (the same math through PyTorch library calls on the same buffers: CPU path + in-place oracle).
+
+Reference call sites these primitives replace: the ``nn.Conv2d`` / ``nn.Linear`` / ``max_pool2d`` /
+``Dropout2d`` layers of src/models.py:11-58 and their autograd backward inside ``loss.backward()`` (src/agent.py:47-48); the
+BatchNorm / residual / average-pool primitives serve ResNet-18 and VGG-11, which the reference does not have."""
 from __future__ import annotations
 
 import os

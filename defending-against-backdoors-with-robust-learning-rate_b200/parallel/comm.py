@@ -1,5 +1,8 @@
 """Process-group bootstrap.  ``torchrun`` (or any launcher that sets RANK / WORLD_SIZE / LOCAL_RANK / MASTER_*)
-starts one process per GPU; NCCL is used on GPUs, gloo on CPU (the plumbing config of BASELINE.json)."""
+starts one process per GPU; NCCL is used on GPUs, gloo on CPU (the plumbing config of BASELINE.json).
+
+The reference has no counterpart: it is one process on one device (``--device``, src/options.py:67-68) that trains its agents one
+after another (src/federated.py:68-72)."""
 from __future__ import annotations
 
 import os

@@ -11,6 +11,10 @@ GPU's HBM over NVLink, (iii) computes sign vote / aggregator / RLR flip / server
 slice into EVERY rank's ``w_global`` (+bf16 shadow) with NVLS multicast stores (or per-peer P2P stores), and (v)
 signals/awaits "slice landed".  No NCCL call, no host synchronisation, no materialised update vectors.
 
+Reference counterpart: the Python dict ``agent_updates_dict[agent_id] = update`` (src/federated.py:67-70), the ~30 elementwise
+fp64 passes of ``Aggregation.aggregate_updates`` (src/aggregation.py:19-75) and the per-agent
+``vector_to_parameters(copy.deepcopy(rnd_global_params), ...)`` "broadcast" (src/federated.py:72).
+
 With ``backend in {nccl, gloo}`` (the baseline transport) the slots are all-gathered and the same kernel runs on the
 gathered copies locally; on CPU it runs the fp64 oracle.
 """
