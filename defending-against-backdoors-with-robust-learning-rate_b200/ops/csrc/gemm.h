@@ -52,6 +52,10 @@ cudaError_t launch_conv_bf16(const void* x, const void* w, void* out, int NB, in
 cudaError_t launch_conv3x3_halo_bf16(const void* x, const void* w, void* out, int NB, int H, int W, int Cout, const float* bias, int relu,
                                      int accumulate, float* stats, int bo_mode, long long* dbg, int num_sms, cudaStream_t st);
 
+// ---- conv_halo3.cu (opt-in): the three taps of a filter row in ONE N = 192 MMA, column shift-add in the epilogue -----------------
+cudaError_t launch_conv3x3_halo3_bf16(const void* x, const void* w, void* out, int NB, int H, int W, int Cout, const float* bias, int relu,
+                                      int accumulate, int num_sms, cudaStream_t st);
+
 // ---- wgrad.cu: MN-major tcgen05 weight gradients (fp32, accumulated with red.add) -----------------------------------
 cudaError_t launch_conv_wgrad_bf16(const void* dy, const void* x, float* dW, int NB, int planes, int Hin, int Win, int Cin, int Cin_valid,
                                    int Ho, int Wo, int Cout, int ntaps, const int* dh, const int* dw, const int* dplane, int num_sms,

@@ -90,6 +90,15 @@ void conv3x3_halo_bf16(at::Tensor x, at::Tensor w, at::Tensor out, c10::optional
                                         accumulate, opt<float>(stats), (int)bo_mode, opt<long long>(dbg), num_sms(), cur_stream()), "conv3x3_halo_bf16");
 }
 
+// same contract as conv3x3_halo_bf16 without statistics; H % 16 == 0, any W
+void conv3x3_halo3_bf16(at::Tensor x, at::Tensor w, at::Tensor out, c10::optional<at::Tensor> bias, bool relu, bool accumulate) {
+    c10::cuda::CUDAGuard g(x.device());
+    TORCH_CHECK(x.dim() == 4 && x.size(3) == 64 && out.dim() == 4 && w.dim() == 2 && w.size(1) == 9 * 64 && w.size(0) == out.size(3));
+    TORCH_CHECK(out.size(0) == x.size(0) && out.size(1) == x.size(1) && out.size(2) == x.size(2));
+    check(rlr::launch_conv3x3_halo3_bf16(bf(x), bf(w), bfm(out), x.size(0), x.size(1), x.size(2), out.size(3), opt<const float>(bias), relu,
+                                         accumulate, num_sms(), cur_stream()), "conv3x3_halo3_bf16");
+}
+
 // dW[Cout][T][Cin_valid] (fp32, pre-zeroed) += wgrad(dy[NB,Ho,Wo,Cout], x[planes*NB,Hin,Win,Cin])
 void conv_wgrad_bf16(at::Tensor dy, at::Tensor x, at::Tensor dW, int64_t NB, int64_t planes, int64_t cin_valid, std::vector<int64_t> dh,
                      std::vector<int64_t> dw, std::vector<int64_t> dplane) {
@@ -276,6 +285,7 @@ void register_gemm_bindings(py::module_& m) {
     m.def("conv_bf16_strided", &conv_bf16_strided);
     m.def("conv_wgrad_bf16_strided", &conv_wgrad_bf16_strided);
     m.def("conv3x3_halo_bf16", &conv3x3_halo_bf16);
+    m.def("conv3x3_halo3_bf16", &conv3x3_halo3_bf16);
     m.def("conv_wgrad_bf16", &conv_wgrad_bf16);
     m.def("linear_wgrad_bf16", &linear_wgrad_bf16);
     m.def("conv_wgrad_halo_bf16", &conv_wgrad_halo_bf16);

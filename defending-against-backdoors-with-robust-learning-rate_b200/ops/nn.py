@@ -27,6 +27,9 @@ USE_IM2COL_STEM = bool(int(os.environ.get("RLR_IM2COL_STEM", "0")))
 # BatchNorm(+ReLU, no residual) backward without reading the layer output: the mask is recomputed from x with the forward's own
 # scale/shift expression.  Opt-in until measured on hardware (RLR_BN_RECOMPUTE=1).
 USE_BN_RECOMPUTE = bool(int(os.environ.get("RLR_BN_RECOMPUTE", "0")))
+# 3x3/s1/p1 convs with 64 input channels: three filter taps per N = 192 MMA with a lane shift-add epilogue (conv_halo3.cu) instead of
+# nine N = 64 MMAs per k-step.  Opt-in until measured on hardware (RLR_HALO3=1).
+USE_HALO3 = bool(int(os.environ.get("RLR_HALO3", "0")))
 # Classifier-head kernels v2 (weights staged in shared memory, weight gradient spread over K/64 x B/16 blocks with float atomics).
 # Opt-in until measured on hardware (RLR_HEAD_V2=1).
 USE_HEAD_V2 = bool(int(os.environ.get("RLR_HEAD_V2", "0")))
@@ -110,6 +113,9 @@ def conv2d_fwd_sm100(x, w, bias, y, stride, pad, relu, stats, tag="fwd", zero_st
         x, w, Cin = xp, wp, cp
     if _halo_ok(k, stride, pad, Cin, H, W):
         # persistent halo-reuse kernel (conv_halo.cu): 36 KB of L2 traffic per 128-pixel tile instead of 216 KB
+        if USE_HALO3 and stats is None:
+            e.conv3x3_halo3_bf16(x, w.reshape(Cout, 9 * 64), y, bias, bool(relu), False)
+            return y
         if stats is not None and zero_stats:
             stats.zero_()
         e.conv3x3_halo_bf16(x, w.reshape(Cout, 9 * 64), y, bias, bool(relu), False, stats, 0, None)
@@ -146,7 +152,10 @@ def conv2d_dgrad_sm100(dy, w, dx, stride, pad, accumulate):
     if _halo_ok(k, 1, k - 1 - pad, Cout, dy.shape[1], dy.shape[2]) and dx.shape[1:3] == dy.shape[1:3]:
         wt = scratch(("wt", w.data_ptr()), (Cin, k * k * Cout), w.dtype, w.device)   # resident-filter kernel wants K-major taps
         e.filter_transpose(w, wt, Cout, k * k, Cin)
-        e.conv3x3_halo_bf16(dy, wt, dx, None, False, bool(accumulate), None, 0, None)
+        if USE_HALO3:
+            e.conv3x3_halo3_bf16(dy, wt, dx, None, False, bool(accumulate))
+        else:
+            e.conv3x3_halo_bf16(dy, wt, dx, None, False, bool(accumulate), None, 0, None)
         return dx
     dh, dw, pl = _taps(k, 1, k - 1 - pad)
     if Cin % 64 == 0:

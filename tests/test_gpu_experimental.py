@@ -294,3 +294,29 @@ def test_head_kernels_v2(B, K, N, relu):
     for got_w, got_b in ((dw, db), (dw2, db2)):
         torch.testing.assert_close(got_w, dwr, rtol=1e-3, atol=1e-4)
         torch.testing.assert_close(got_b, dbr, rtol=1e-3, atol=1e-4)
+
+
+@pytest.mark.parametrize("B,H,W,Cout,acc", [(64, 32, 32, 64, False), (37, 16, 16, 64, True), (8, 32, 32, 128, False), (5, 16, 8, 32, False),
+                                            (256, 32, 32, 64, True), (3, 16, 24, 64, False)])
+def test_conv3x3_halo3_kernel(B, H, W, Cout, acc):
+    """RLR_HALO3: three filter taps per N = 192 MMA over one A view, column shift-add with warp shuffles in the epilogue, tiles
+    advancing by six columns -- against the fp32 reference (and the nine-MMA halo kernel for the error scale)."""
+    import torch.nn.functional as F
+    torch.manual_seed(B + H)
+    x = torch.randn(B, H, W, 64, device=DEV).to(BF)
+    w = (torch.randn(Cout, 3, 3, 64, device=DEV) / 24).to(BF)
+    bias = torch.randn(Cout, device=DEV) * 0.1
+    base = torch.randn(B, H, W, Cout, device=DEV).to(BF)
+    ref = F.relu(F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), bias, 1, 1)).permute(0, 2, 3, 1)
+    if acc:
+        ref = ref + base.float()
+    y3 = base.clone() if acc else torch.full_like(base, 5.0)
+    ops.ext().conv3x3_halo3_bf16(x, w.reshape(Cout, 576), y3, bias, True, acc)
+    y1 = base.clone() if acc else torch.full_like(base, 5.0)
+    if W % 8 == 0:
+        ops.ext().conv3x3_halo_bf16(x, w.reshape(Cout, 576), y1, bias, True, acc, None, 0, None)
+    torch.cuda.synchronize()
+    e3 = float((y3.float() - ref).abs().max() / ref.abs().max())
+    e1 = float((y1.float() - ref).abs().max() / ref.abs().max()) if W % 8 == 0 else float("nan")
+    print(f"halo3 rel err {e3:.2e} (nine-MMA halo kernel {e1:.2e})")
+    assert e3 < 1e-2
