@@ -1,14 +1,16 @@
 #!/bin/bash
 # Round-2 opener: ONE 1-GPU call that validates and measures every opt-in path written blind at the end of round 1.
-#   gpurun --timeout 900 -- 'bash scripts/r2_experiments.sh'
+#   gpurun --timeout 1500 -- 'bash scripts/r2_experiments.sh'
 # Each experiment: its numerics test (own process, own timeout: a deadlocked kernel only loses that experiment), then -- only if
-# the test passed -- the headline bench with the flag on.  The default build is benched first and last (box drift).
+# the test passed -- the headline bench with the flag on.  The default build is benched first and last (box drift); finally all
+# passing flags together.
 # Outputs: gpurun_out/r2_exp_<name>.txt, gpurun_out/r2_bench_<name>.json, summary in gpurun_out/r2_summary.txt
 mkdir -p gpurun_out
 : > gpurun_out/r2_summary.txt
-bench() {   # name, env assignment
-    env $2 timeout 150 python bench.py --steps 3 --warmup 3 --no_e2e > gpurun_out/r2_bench_$1.json 2> gpurun_out/r2_bench_$1.err
-    python - "$1" <<'PY' | tee -a gpurun_out/r2_summary.txt
+bench() {   # name, env assignments (one word each)
+    name=$1; shift
+    env "$@" timeout 150 python bench.py --steps 3 --warmup 3 --no_e2e > gpurun_out/r2_bench_$name.json 2> gpurun_out/r2_bench_$name.err
+    python - "$name" <<'PY' | tee -a gpurun_out/r2_summary.txt
 import json, sys
 name = sys.argv[1]
 try:
@@ -19,13 +21,17 @@ except Exception as e:
 PY
 }
 bench default_first NONE=1
-#            name          pytest -k expression                          flag
+good=""
+#   name          pytest -k expression          flag
 while read -r name expr flag; do
     [ -z "$name" ] && continue
     RLR_EXPERIMENTAL=1 timeout 150 python -m pytest tests/test_gpu_experimental.py -m gpu -q -s -k "$expr" > gpurun_out/r2_exp_$name.txt 2>&1
     rc=$?
     echo "test $name: exit $rc ($(tail -1 gpurun_out/r2_exp_$name.txt))" | tee -a gpurun_out/r2_summary.txt
-    [ $rc -eq 0 ] && bench $name $flag
+    if [ $rc -eq 0 ]; then
+        bench $name $flag
+        good="$good $flag"
+    fi
 done <<'LIST'
 strided      strided_tma                  RLR_STRIDED_TMA=1
 stem         im2col_stem                  RLR_IM2COL_STEM=1
@@ -36,5 +42,6 @@ halo3        halo3_kernel                 RLR_HALO3=1
 pdl          programmatic_dependent       RLR_PDL=1
 pair         cta_pair                     RLR_CONV_2CTA=1
 LIST
+[ -n "$good" ] && bench combined $good      # every experiment whose test passed, together
 bench default_last NONE=1
 cat gpurun_out/r2_summary.txt
