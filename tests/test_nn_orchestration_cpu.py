@@ -154,6 +154,33 @@ class FakeExt:
         self.calls.append("linear_wgrad_bf16")
         dW += dy.t() @ x
 
+    # ---- BatchNorm backward (contracts of bn_bwd / bn_bwd_recompute in gemm_binding.cpp) ---------------------------------
+    def _bn_bwd(self, dz, x, gamma, mean_rstd, dsum, dx, dres, dgamma, dbeta, zero_dsum):
+        C = x.shape[-1]
+        xf, dzf = x.reshape(-1, C), dz.reshape(-1, C)
+        M = xf.shape[0]
+        xhat = (xf - mean_rstd[0]) * mean_rstd[1]
+        if zero_dsum:
+            dsum.zero_()
+        d2 = dsum.view(2, C)
+        d2[0] += dzf.sum(0)
+        d2[1] += (dzf * xhat).sum(0)
+        if dres is not None:
+            dres.copy_(dzf.reshape(dres.shape))
+        dx.copy_((gamma * mean_rstd[1] * (dzf - d2[0] / M - xhat * d2[1] / M)).reshape(dx.shape))
+        dgamma.copy_(d2[1]); dbeta.copy_(d2[0])
+
+    def bn_bwd(self, dy, y, x, gamma, mean_rstd, dsum, dx, dres, dgamma, dbeta, relu, zero_dsum):
+        self.calls.append("bn_bwd")
+        dz = dy * (y > 0) if relu else dy
+        self._bn_bwd(dz, x, gamma, mean_rstd, dsum, dx, dres, dgamma, dbeta, zero_dsum)
+
+    def bn_bwd_recompute(self, dy, x, gamma, beta, mean_rstd, dsum, dx, dgamma, dbeta, zero_dsum):
+        self.calls.append("bn_bwd_recompute")
+        sc = gamma * mean_rstd[1]
+        mask = (x * sc + (beta - mean_rstd[0] * sc)) > 0              # the forward's own scale / shift expression
+        self._bn_bwd(dy * mask, x, gamma, mean_rstd, dsum, dx, None, dgamma, dbeta, zero_dsum)
+
     def channel_stats(self, x, st):
         self.calls.append("channel_stats")
         xf = x.reshape(-1, x.shape[-1])
@@ -240,3 +267,69 @@ def test_shared_parity_copy_is_made_once_per_forward(fake):
         nn.conv2d_fwd_sm100(x, w3, None, y, 2, 1, False, None, tag="a", s2d_epoch=epoch)
         nn.conv2d_fwd_sm100(x, w1, None, y, 2, 0, False, None, tag="b", s2d_epoch=epoch)
     assert fake.calls.count("space_to_depth") == 2
+
+
+@pytest.mark.parametrize("mode", ["default", "strided", "stem"])
+@pytest.mark.parametrize("model", ["resnet18", "cnn_cifar"])
+def test_native_plan_with_kernel_conv_paths_matches_library_convs(fake, monkeypatch, model, mode):
+    """Whole network on CPU: the executor's plan with the convolution wrappers of ops/nn.py (emulated kernels) against the same plan
+    with library convolutions -- catches wrong buffers / tags / accumulate flags in how models/native.py drives the conv paths."""
+    from rlr_b200.models import get_layout
+    from rlr_b200.models.native import NativeNet
+    from rlr_b200 import ops
+    monkeypatch.setattr(nn, "USE_STRIDED_TMA", mode == "strided")
+    monkeypatch.setattr(nn, "USE_IM2COL_STEM", mode == "stem")
+    torch.manual_seed(0)
+    lay = get_layout(model)
+    for nd in lay.nodes:
+        if nd.op == "dropout":
+            nd.attrs["p"] = 0.0
+    B = 4
+    w = lay.init_(torch.zeros(lay.n_total), 1)
+    C, H, W = lay.in_shape
+    x = torch.randn(B, H, W, C)
+    t = torch.randint(0, 10, (B,))
+    res = {}
+    for name, conv_impl in (("lib", "aten"), ("kern", "sm100")):
+        impl = dict(conv_fwd=conv_impl, conv_dgrad=conv_impl, conv_wgrad=conv_impl, bn="aten", pool="aten", linear="aten", dropout="aten")
+        net = NativeNet(lay, "cpu", B, impl=impl, act_dtype=torch.float32)
+        wi, g = w.clone(), torch.zeros_like(w)
+        net.bind(wi, wi.clone(), g)
+        logits = net.forward(x, True).clone()
+        _, dl = ops.softmax_xent(logits, t)
+        net.backward(dl)
+        res[name] = (logits, g[: lay.n_vote].clone())
+    torch.testing.assert_close(res["kern"][0], res["lib"][0], rtol=1e-3, atol=1e-3)
+    cos = F.cosine_similarity(res["kern"][1].double(), res["lib"][1].double(), dim=0)
+    assert float(cos) > 0.9999, float(cos)
+    assert "conv_bf16" in fake.calls or "conv_bf16_strided" in fake.calls or "gemm_bf16" in fake.calls
+
+
+@pytest.mark.parametrize("recompute", [False, True])
+@pytest.mark.parametrize("relu,with_res", [(True, False), (True, True), (False, False)])
+def test_bn_backward_wrapper_paths(fake, monkeypatch, recompute, relu, with_res):
+    """nn.bn_bwd: the y-based kernels vs the mask-recomputing variant (only legal for BN+ReLU without a residual) vs the library
+    formulation, all on the same saved statistics."""
+    monkeypatch.setattr(nn, "USE_BN_RECOMPUTE", recompute)
+    torch.manual_seed(3)
+    M, C = 96, 16
+    x = torch.randn(M, C) * 1.5 + 0.2
+    gamma, beta = torch.rand(C) + 0.5, torch.randn(C) * 0.3
+    mean, var = x.mean(0), x.var(0, unbiased=False)
+    mean_rstd = torch.stack([mean, torch.rsqrt(var + 1e-5)])
+    res = torch.randn(M, C) if with_res else None
+    pre = (x - mean) * mean_rstd[1] * gamma + beta + (res if with_res else 0)
+    y = pre.clamp_min(0) if relu else pre
+    dy = torch.randn(M, C)
+    outs = {}
+    for impl in ("aten", "sm100"):
+        dsum, dx = torch.zeros(2, C), torch.empty(M, C)
+        dres = torch.empty(M, C) if with_res else None
+        dg, db = torch.zeros(C), torch.zeros(C)
+        nn.bn_bwd(dy, y, x, gamma, mean_rstd, dsum, dx, dres, dg, db, relu, impl, zero_dsum=True, beta=beta)
+        outs[impl] = (dx, dg, db, dres)
+    for a, b in zip(outs["aten"], outs["sm100"]):
+        if a is not None:
+            torch.testing.assert_close(b, a, rtol=1e-4, atol=1e-5)
+    used = "bn_bwd_recompute" in fake.calls
+    assert used == (recompute and relu and not with_res)
