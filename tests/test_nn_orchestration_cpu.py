@@ -333,3 +333,36 @@ def test_bn_backward_wrapper_paths(fake, monkeypatch, recompute, relu, with_res)
             torch.testing.assert_close(b, a, rtol=1e-4, atol=1e-5)
     used = "bn_bwd_recompute" in fake.calls
     assert used == (recompute and relu and not with_res)
+
+
+def test_halo3_tile_algorithm_emulation():
+    """Scalar emulation of conv_halo3.cu's arithmetic: 8 x 18 pixel boxes advancing by 6 columns, one accumulator block per dx tap
+    over a single A view per filter row, out = D_1 + shfl_up(D_0) + shfl_down(D_2) inside 32-lane warps, lanes 1..6 of each 8-lane
+    group valid -- must reproduce a padded 3x3 convolution exactly (geometry, shift directions, masks)."""
+    torch.manual_seed(0)
+    NB, H, W, Cin, Cout = 2, 16, 20, 4, 8
+    x = torch.randn(NB, H, W, Cin)
+    w = torch.randn(Cout, 9, Cin)
+    ref = F.conv2d(x.permute(0, 3, 1, 2), w.reshape(Cout, 3, 3, Cin).permute(0, 3, 1, 2), None, 1, 1).permute(0, 2, 3, 1)
+    out = torch.full((NB, H, W, Cout), float("nan"))
+    xp = F.pad(x, (0, 0, 8, 8, 1, 1))                                    # zero fill = TMA out-of-bounds behaviour (cols +-8, rows +-1)
+    m = torch.arange(128)
+    hl, wl = m // 8, m % 8
+    lane = m % 32
+    for n in range(NB):
+        for th in range(H // 16):
+            for tw in range((W + 5) // 6):
+                h0, c0, oc0 = th * 16, tw * 6 - 1, tw * 6
+                D = torch.zeros(128, 3, Cout)
+                for dy in range(3):
+                    a = xp[n, h0 + hl + dy - 1 + 1, c0 + wl + 8]          # A view of filter row dy: box rows (h + dy), all 8 columns
+                    for j in range(3):
+                        D[:, j] += a @ w[:, dy * 3 + j, :].t()
+                up = torch.where((lane >= 1)[:, None], D[(m - 1).clamp(0), 0], D[:, 0])          # __shfl_up_sync(d0, 1)
+                dn = torch.where((lane <= 30)[:, None], D[(m + 1).clamp(max=127), 2], D[:, 2])   # __shfl_down_sync(d2, 1)
+                val = D[:, 1] + up + dn
+                c = oc0 + wl - 1
+                ok = (wl >= 1) & (wl <= 6) & (h0 + hl < H) & (c < W)
+                out[n, (h0 + hl)[ok], c[ok]] = val[ok]
+    assert not torch.isnan(out).any()
+    torch.testing.assert_close(out, ref, rtol=1e-4, atol=1e-4)
