@@ -48,3 +48,20 @@ def test_bench_reference_arm_reports_unavailable_or_runs_without_gpu():
     r = _run(["bench.py", "--impl", "reference", "--steps", "1", "--warmup", "1"])
     assert r.returncode == 0, r.stderr[-1000:]
     assert '"impl": "reference"' in r.stdout
+
+
+def test_bench_prints_one_json_line_with_the_contract_fields():
+    """bench.py's output contract (one JSON line on stdout with the driver's keys), exercised on CPU with a tiny config."""
+    import json
+    r = _run(["bench.py", "--model", "cnn_mnist", "--data", "fmnist", "--train_size", "256", "--bs", "64", "--steps", "1", "--warmup", "3"],
+             timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.strip().splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+                "data", "config", "clocks", "e2e", "gpu_launches"):
+        assert key in d, key
+    assert d["metric"] == "fl_rounds_per_sec" and d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 3 and d["higher_is_better"] is True
+    assert d["value"] > 0 and abs(d["value"] - 1000.0 / d["ms_per_step"]) < 1e-6 * d["value"] + 1e-9
+    assert d["config"]["model"] == "cnn_mnist" and d["data"] == "synthetic"
