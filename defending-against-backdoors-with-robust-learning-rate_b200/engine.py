@@ -85,7 +85,8 @@ class FLEngine:
             backend = "local"
         if backend == "auto" and ctx.is_dist and ctx.backend == "gloo":
             backend = "gloo"
-        self.fused = FusedAggregator(ctx, self.layout.n_total, self.layout.n_vote, max_slots, backend)
+        self.fused = FusedAggregator(ctx, self.layout.n_total, self.layout.n_vote, max_slots, backend,
+                                     transport=getattr(args, "agg_transport", "auto"))
         init = torch.zeros(self.layout.n_total, dtype=torch.float32)
         self.layout.init_(init, args.seed)
         self.fused.w_global.copy_(init.to(dev))

@@ -195,6 +195,47 @@ def aggregate_oracle(w_global, w_agents, weights, mode="avg", theta=0, server_lr
     return new.float(), flipped
 
 
+def aggregate_partials(w_global, w_local_agents, local_weights, n_vote=None, scales=None):
+    """This rank's share of the server step for the additive aggregators: ``(vote, wsum)`` with
+    ``vote = sum_k sign(w_k - w_g)`` (float32: small integers) and ``wsum = sum_k n_k (w_k - w_g)`` (float64) over the LOCAL
+    participants.  Summed over ranks (all_reduce) they are exactly the ``signs`` and ``mean * sum(n)`` of ``aggregate_oracle``."""
+    g = w_global.double()
+    vote = torch.zeros_like(w_global, dtype=torch.float32)
+    wsum = torch.zeros_like(g)
+    for i, (w, nk) in enumerate(zip(w_local_agents, local_weights)):
+        u = w.double() - g
+        if scales is not None:
+            u = u * float(scales[i])
+        vote += torch.sign(u).float()
+        wsum += float(nk) * u
+    return vote, wsum
+
+
+def aggregate_from_partials(w_global, vote, wsum, total_weight, mode="avg", theta=0, server_lr=1.0, noise=None, n_vote=None):
+    """Finish the server step from globally reduced partials (same formulas and order as ``aggregate_oracle``; avg / sign only)."""
+    if mode not in ("avg", "sign"):
+        raise ValueError(f"aggregate_from_partials: mode {mode!r} is not additive (coordinate median needs every update)")
+    g = w_global.double()
+    n = g.numel()
+    n_vote = n if n_vote is None else int(n_vote)
+    mean = wsum / float(total_weight)
+    signs = vote.double()
+    agg = mean.clone() if mode == "avg" else torch.sign(signs)
+    if noise is not None:
+        agg = agg + noise.double()
+    lr = torch.full_like(g, float(server_lr))
+    flipped = 0
+    if theta > 0:
+        neg = signs.abs() < theta
+        neg[n_vote:] = False
+        lr[neg] = -float(server_lr)
+        flipped = int(neg.sum())
+    new = g + lr * agg
+    if n_vote < n:
+        new[n_vote:] = g[n_vote:] + mean[n_vote:]
+    return new.float(), flipped
+
+
 class PtrTable:
     """Device int64 table of raw pointers (kept with the tensors it points into, so they stay alive)."""
 

@@ -54,6 +54,10 @@ def build_parser() -> argparse.ArgumentParser:
                    help="activation/GEMM-operand dtype on GPU (master params, updates, aggregation stay fp32)")
     p.add_argument("--backend", type=str, default="auto", choices=("auto", "fused", "nccl", "gloo", "local"),
                    help="aggregation transport: fused = P2P/multicast sm_100a kernel; nccl/gloo = all_gather + kernel")
+    p.add_argument("--agg_transport", type=str, default="auto", choices=("auto", "gather", "reduce"),
+                   help="nccl/gloo back-ends only: gather = all_gather every participant's parameters (needed for comed); reduce = "
+                        "all_reduce per-coordinate vote / weighted-sum partials (avg, sign, RLR: O(N) traffic per rank); "
+                        "auto = reduce when the ranks span several hosts")
     p.add_argument("--trainer", type=str, default="auto", choices=("auto", "native", "torch"),
                    help="local-training executor: native = sm_100a kernels, torch = autograd oracle (CPU / baseline)")
     p.add_argument("--class_per_agent", type=int, default=10,

@@ -29,8 +29,13 @@ FLAG_BYTES = 4096
 
 
 class FusedAggregator:
-    def __init__(self, ctx, n_total: int, n_vote: int, max_slots: int, backend: str = "auto", with_bf16: bool = True):
+    def __init__(self, ctx, n_total: int, n_vote: int, max_slots: int, backend: str = "auto", with_bf16: bool = True,
+                 transport: str = "auto"):
         self.ctx = ctx
+        # nccl / gloo back-ends: "gather" all-gathers every participant's parameters and runs the kernel on the copies (any
+        # aggregator); "reduce" all-reduces per-coordinate partial sums (vote, weighted update sum) -- O(N) instead of O(K N)
+        # traffic per rank, avg / sign / RLR only (coordinate median falls back to gather).  auto = reduce across hosts.
+        self.transport = transport if transport in ("gather", "reduce") else ("gather" if getattr(ctx, "single_node", True) else "reduce")
         self.n, self.n_vote, self.max_slots = int(n_total), int(n_vote), int(max_slots)
         dev = ctx.device
         if backend == "auto":
@@ -107,7 +112,11 @@ class FusedAggregator:
                 self.begin, self.end, self.n_vote, ops.MODE_IDS[mode], int(theta), float(server_lr), float(noise_std),
                 int(seed), int(rnd), self.flipped, self.flag_ptrs.tensor, self.local_sync, ctx.rank, ctx.world, self.epoch)
             return
-        # ---- baseline transports / single process: gather participant params, run the kernel locally ------------
+        # ---- baseline transports / single process ------------------------------------------------------------------
+        if ctx.is_dist and self.transport == "reduce" and mode in ("avg", "sign"):
+            self._aggregate_reduce(weights, mode, theta, server_lr, noise_std, seed, rnd, scales)
+            return
+        # gather participant params, run the kernel locally
         if ctx.is_dist:
             mine = torch.stack(self.slots, 0)                       # [max_slots, n]
             allp = ctx.all_gather(mine)                             # [world, max_slots, n]
@@ -116,6 +125,29 @@ class FusedAggregator:
             agents = [self.slots[j] for j in range(n_part)]
         ops.fused_aggregate(self.w_global, agents, weights, mode, theta, server_lr, noise_std, seed, rnd, self.n_vote,
                             scales, out=self.w_global, out_bf16=self.w_bf16, flipped=self.flipped)
+
+    def _aggregate_reduce(self, weights, mode, theta, server_lr, noise_std, seed, rnd, scales):
+        """All-reduce transport: every rank folds its local participants into (vote, weighted sum), two all_reduce calls make them
+        global, and every rank finishes the identical server step locally (ops.aggregate_from_partials).  The noise vector is
+        drawn from a torch generator seeded like the CPU oracle on every rank (same stream everywhere; it is NOT the Philox
+        stream of the fused kernel)."""
+        ctx, n_part = self.ctx, len(weights)
+        mine = [j for j in range(n_part) if self.slot_owner(j)[0] == ctx.rank]
+        vote, wsum = ops.aggregate_partials(self.w_global, [self.slots[self.slot_owner(j)[1]] for j in mine], [weights[j] for j in mine],
+                                            self.n_vote, [scales[j] for j in mine] if scales is not None else None)
+        ctx.all_reduce_sum(vote)
+        ctx.all_reduce_sum(wsum)
+        noise = None
+        if noise_std > 0:
+            gen = torch.Generator().manual_seed(int(seed) * 1000003 + int(rnd))
+            noise = (torch.randn(self.n, generator=gen, dtype=torch.float64) * noise_std).to(self.w_global.device)
+            noise[self.n_vote:] = 0
+        new, nflip = ops.aggregate_from_partials(self.w_global, vote, wsum, sum(float(x) for x in weights), mode, theta, server_lr,
+                                                 noise, self.n_vote)
+        self.w_global.copy_(new)
+        if self.w_bf16 is not None:
+            self.w_bf16.copy_(new.to(torch.bfloat16))
+        self.flipped += nflip
 
     def update_norms(self, n_part: int):
         """||w_j - w_global|| for every participant (float64 [n_part]), computed where the slot lives."""

@@ -49,3 +49,51 @@ def test_gloo_ranks_agree_and_match_single_process(tmp_path, world, agents):
     for r in range(1, 3):
         solo.run_round(r)
     assert abs(solo.evaluate(2)["val_acc"] - outs[0]["val_acc"]) < 0.25
+
+
+def _transport_worker(rank, world, port, outdir, cases):
+    """Unit-level: fill the slots with known vectors, aggregate with both transports, save the results."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.set_num_threads(2)
+    from rlr_b200.parallel import FusedAggregator, init_distributed
+    ctx = init_distributed("cpu")
+    out = {}
+    for ci, (n, n_vote, n_part, mode, theta, noise) in enumerate(cases):
+        max_slots = (n_part + world - 1) // world
+        res = {}
+        for transport in ("gather", "reduce"):
+            fa = FusedAggregator(ctx, n, n_vote, max_slots, "gloo", transport=transport)
+            g = torch.Generator().manual_seed(100 + ci)
+            w0 = torch.randn(n, generator=g)
+            agents = [w0 + 0.1 * torch.randn(n, generator=g) for _ in range(n_part)]
+            fa.w_global.copy_(w0)
+            for j, a in enumerate(agents):
+                r, s = fa.slot_owner(j)
+                if r == rank:
+                    fa.slots[s].copy_(a)
+            weights = [float(10 + 3 * j) for j in range(n_part)]
+            fa.aggregate(weights, mode, theta, 1.0 if mode != "sign" else 0.01, noise, seed=5, rnd=2)
+            res[transport] = (fa.w_global.clone(), int(fa.flipped))
+            fa.close()
+        out[ci] = res
+    torch.save(out, os.path.join(outdir, f"t{rank}.pt"))
+    import torch.distributed as dist
+    dist.barrier(); dist.destroy_process_group()
+
+
+def test_reduce_transport_matches_gather_transport(tmp_path):
+    """--agg_transport reduce (all_reduce of vote / weighted-sum partials, for jobs that span hosts) must give the gathered
+    result for the additive aggregators, with and without RLR, noise and BatchNorm-style tail coordinates; all ranks identical."""
+    world = 3
+    cases = [(4096, 4096, 5, "avg", 0, 0.0), (4096, 4000, 7, "avg", 3, 0.0), (8192, 8192, 4, "sign", 2, 0.0), (4096, 4032, 6, "avg", 2, 0.05),
+             (4096, 4096, 5, "comed", 2, 0.0)]
+    mp.spawn(_transport_worker, args=(world, _free_port(), str(tmp_path), cases), nprocs=world, join=True)
+    outs = [torch.load(tmp_path / f"t{r}.pt") for r in range(world)]
+    for ci in range(len(cases)):
+        wg, fg = outs[0][ci]["gather"]
+        wr, fr = outs[0][ci]["reduce"]
+        torch.testing.assert_close(wr, wg, rtol=1e-6, atol=1e-6)
+        assert fr == fg
+        for o in outs[1:]:
+            assert torch.equal(o[ci]["reduce"][0], wr) and torch.equal(o[ci]["gather"][0], wg)
