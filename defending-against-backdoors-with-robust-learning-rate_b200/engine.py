@@ -114,6 +114,26 @@ class FLEngine:
         rs = np.random.RandomState((self.args.seed * 1_000_003 + rnd) % (2 ** 31))
         return [int(a) for a in rs.choice(self.args.num_agents, self.n_part, replace=False)]
 
+    def place_participants(self, chosen):
+        """Order the round's participants so that the static participant -> (rank, slot) map (j % world, j // world) balances the
+        local-training time of the ranks.  With equal shards (the FMNIST / CIFAR-10 partitions) the sampled order is kept; with
+        skewed shards (Fed-EMNIST clients differ ~10x) the participants are sorted by their number of local steps and dealt to the
+        ranks in serpentine order, which keeps equal slot counts per rank and evens out the step sums.  Deterministic, identical
+        on every rank; aggregation is order-independent, so only the floating-point summation order changes."""
+        world = self.ctx.world
+        if world <= 1 or len(chosen) <= world:
+            return list(chosen)
+        bs, ep = self.args.bs, self.args.local_ep
+        cost = {a: ep * ((self.agents[a].n_data + bs - 1) // bs) for a in chosen}
+        if max(cost.values()) == min(cost.values()):
+            return list(chosen)
+        by_cost = sorted(chosen, key=lambda a: (-cost[a], a))
+        out = []
+        for row in range(0, len(by_cost), world):
+            chunk = by_cost[row:row + world]
+            out.extend(chunk if (row // world) % 2 == 0 else chunk[::-1])
+        return out
+
     # ---- end-to-end input streaming (bench "e2e"): shards come from pinned host memory every round ----------
     def enable_input_streaming(self):
         """End-to-end mode: every agent's shard is kept in pinned host memory and ``run_round(stream_inputs=True)`` uploads the
@@ -147,7 +167,7 @@ class FLEngine:
 
     # ---- one federated round (src/federated.py:66-74) --------------------------------------------------------
     def run_round(self, rnd: int, stream_inputs: bool = False):
-        chosen = self.sample_agents(rnd)
+        chosen = self.place_participants(self.sample_agents(rnd))
         ctx, fused = self.ctx, self.fused
         self.round_loss.zero_()
         steps = 0

@@ -153,3 +153,29 @@ def test_h5dataset_container_and_conversion():
     assert len(ab) == 4 and ab.targets.tolist() == [1, 2, 3, 4]
     dd = ab.as_device_dataset()
     assert dd.data.shape == (4, 28, 28, 1) and dd.name == "fedemnist"
+
+
+def test_participant_placement_balances_skewed_shards():
+    """place_participants: same multiset, equal slot counts per rank, smaller maximum per-rank step sum than the sampled order for
+    skewed shard sizes; untouched for equal shards and for a single process."""
+    from types import SimpleNamespace
+    from rlr_b200.engine import FLEngine
+    import random
+    rs = random.Random(0)
+    sizes = [rs.choice([20, 40, 80, 160, 400, 900]) for _ in range(40)]
+    fake = SimpleNamespace(ctx=SimpleNamespace(world=8), args=SimpleNamespace(bs=64, local_ep=2),
+                           agents=[SimpleNamespace(n_data=n) for n in sizes])
+    chosen = list(range(40)); rs.shuffle(chosen); chosen = chosen[:33]
+    placed = FLEngine.place_participants(fake, chosen)
+    assert sorted(placed) == sorted(chosen)
+    steps = lambda a: 2 * ((sizes[a] + 63) // 64)
+    load = lambda order: max(sum(steps(a) for a in order[r::8]) for r in range(8))
+    assert load(placed) < load(chosen)
+    ideal = sum(steps(a) for a in chosen) / 8
+    assert load(placed) <= 1.35 * ideal
+    assert FLEngine.place_participants(fake, placed) == FLEngine.place_participants(fake, chosen)      # deterministic, order-free
+    fake.agents = [SimpleNamespace(n_data=100) for _ in sizes]
+    assert FLEngine.place_participants(fake, chosen) == chosen                                           # equal shards: sampled order
+    fake.ctx.world = 1
+    fake.agents = [SimpleNamespace(n_data=n) for n in sizes]
+    assert FLEngine.place_participants(fake, chosen) == chosen
