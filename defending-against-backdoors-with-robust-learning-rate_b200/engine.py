@@ -95,6 +95,13 @@ class FLEngine:
         self.w_global = self.fused.w_global
 
         self.trainer = make_trainer(args.trainer, self.layout, args, dev, max_shard)
+        # Several agents per GPU and round can be trained concurrently: trainer i (own parameters, activations, CUDA graphs) runs
+        # on stream i.  The small reference CNNs are launch-latency bound at batch 256, so two to four agents in flight fill the GPU.
+        n_flight = max(1, int(getattr(args, "agents_in_flight", 1))) if dev.type == "cuda" else 1
+        n_flight = min(n_flight, max_slots)
+        self.trainers = [self.trainer] + [make_trainer(args.trainer, self.layout, args, dev, max_shard) for _ in range(n_flight - 1)]
+        self.streams = [torch.cuda.Stream(dev) for _ in range(n_flight)] if n_flight > 1 else None
+        self._loss_parts = [torch.zeros(1, dtype=torch.float32, device=dev) for _ in range(n_flight)]
         self.logger = MetricLogger(args, enabled=ctx.is_main and bool(args.log_dir))
         self.aggregator = Aggregation(self.agent_data_sizes, self.layout.n_params, self.poisoned_val, args,
                                       self.logger, self.layout, self.fused)
@@ -173,16 +180,36 @@ class FLEngine:
         steps = 0
         h2d = 0
         self.timer.start("local_train")
+        concurrent = self.streams is not None and not stream_inputs     # streamed inputs share one staging buffer: sequential
+        if concurrent:
+            cur = torch.cuda.current_stream(ctx.device)
+            for st_ in self.streams:
+                st_.wait_stream(cur)                                     # w_global of this round is ready
+            for part in self._loss_parts:
+                part.zero_()
+        k = 0
         for j, aid in enumerate(chosen):
             r, s = fused.slot_owner(j)
             if r != ctx.rank:
                 continue
             agent = self.agents[aid]
-            if stream_inputs:
-                h2d += self._upload_shard(agent)
-            st = agent.local_train(self.trainer, self.w_global, fused.slots[s], rnd)
-            self.round_loss += st["loss_sum"]
+            if concurrent:
+                i = k % len(self.trainers)
+                with torch.cuda.stream(self.streams[i]):
+                    st = agent.local_train(self.trainers[i], self.w_global, fused.slots[s], rnd)
+                    self._loss_parts[i] += st["loss_sum"]
+            else:
+                if stream_inputs:
+                    h2d += self._upload_shard(agent)
+                st = agent.local_train(self.trainer, self.w_global, fused.slots[s], rnd)
+                self.round_loss += st["loss_sum"]
             steps += st["steps"]
+            k += 1
+        if concurrent:
+            for st_ in self.streams:
+                cur.wait_stream(st_)                                     # every slot is final before the aggregation kernel
+            for part in self._loss_parts:
+                self.round_loss += part
         self.timer.stop("local_train")
         self.timer.start("aggregate")
         self.aggregator.aggregate_slots(chosen, rnd)

@@ -54,6 +54,9 @@ def build_parser() -> argparse.ArgumentParser:
                    help="activation/GEMM-operand dtype on GPU (master params, updates, aggregation stay fp32)")
     p.add_argument("--backend", type=str, default="auto", choices=("auto", "fused", "nccl", "gloo", "local"),
                    help="aggregation transport: fused = P2P/multicast sm_100a kernel; nccl/gloo = all_gather + kernel")
+    p.add_argument("--agents_in_flight", type=int, default=1,
+                   help="agents a GPU trains CONCURRENTLY when it hosts several per round (one trainer + CUDA stream each); helps the "
+                        "small launch-bound CNNs, costs one set of activation buffers per extra agent")
     p.add_argument("--agg_transport", type=str, default="auto", choices=("auto", "gather", "reduce"),
                    help="nccl/gloo back-ends only: gather = all_gather every participant's parameters (needed for comed); reduce = "
                         "all_reduce per-coordinate vote / weighted-sum partials (avg, sign, RLR: O(N) traffic per rank); "

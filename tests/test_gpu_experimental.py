@@ -320,3 +320,25 @@ def test_conv3x3_halo3_kernel(B, H, W, Cout, acc):
     e1 = float((y1.float() - ref).abs().max() / ref.abs().max()) if W % 8 == 0 else float("nan")
     print(f"halo3 rel err {e3:.2e} (nine-MMA halo kernel {e1:.2e})")
     assert e3 < 1e-2
+
+
+def test_agents_in_flight_matches_sequential_training():
+    """--agents_in_flight 2: two agents of a round train concurrently on one GPU (own trainer and CUDA stream each); the aggregated
+    parameters must match the sequential schedule up to float-atomic ordering."""
+    from rlr_b200.engine import FLEngine
+    from rlr_b200.options import make_args
+    res = {}
+    for n_flight in (1, 2):
+        args = make_args(data="cifar10", model="resnet18", num_agents=4, local_ep=1, bs=64, synthetic=1024, synthetic_val=128, log_dir="",
+                         device=DEV, seed=2, agents_in_flight=n_flight, robustLR_threshold=2)
+        eng = FLEngine(args, verbose=False)
+        assert len(eng.trainers) == n_flight
+        for r in (1, 2):
+            eng.run_round(r)
+        loss, _ = eng.round_result()
+        torch.cuda.synchronize()
+        res[n_flight] = (eng.w_global[: eng.layout.n_vote].clone(), loss)
+        eng.close()
+    cos = torch.nn.functional.cosine_similarity(res[1][0].double(), res[2][0].double(), dim=0)
+    assert float(cos) > 0.999, float(cos)
+    assert abs(res[1][1] - res[2][1]) < 0.05 * abs(res[1][1]) + 1e-3
