@@ -44,6 +44,10 @@ def parse():
     p.add_argument("--backend", type=str, default="auto")
     p.add_argument("--dtype", type=str, default="bf16")
     p.add_argument("--no_e2e", action="store_true")
+    p.add_argument("--agents", type=int, default=0,
+                   help="number of FL agents (default 0 = one per GPU, the headline config); more agents than GPUs are time-multiplexed "
+                        "-- e.g. --agents 10 --gpus 1 is the reference README's FMNIST setting")
+    p.add_argument("--agents_in_flight", type=int, default=1, help="agents a GPU trains concurrently (ours only)")
     return p.parse_args()
 
 
@@ -91,11 +95,13 @@ class ClockSampler:
 
 
 def config_dict(a, n, impl):
-    return {"model": a.model, "dataset": f"{a.data} (synthetic, {a.train_size} train images)", "num_agents": n,
-            "agents_per_gpu": 1 if impl == "ours" else n, "global_batch": a.bs * n if impl == "ours" else a.bs,
+    k = a.agents or n                     # agents: one per GPU unless --agents
+    return {"model": a.model, "dataset": f"{a.data} (synthetic, {a.train_size} train images)", "num_agents": k,
+            "agents_per_gpu": (k + n - 1) // n if impl == "ours" else k, "agents_in_flight": a.agents_in_flight if impl == "ours" else 1,
+            "global_batch": a.bs * n if impl == "ours" else a.bs,
             "local_batch": a.bs, "local_ep": a.local_ep, "aggr": a.aggr, "robustLR_threshold": a.theta,
             "num_corrupt": a.num_corrupt, "seq_len": None,
-            "parallelism": f"agent-parallel: {n} agent(s) on {n} GPU(s)" if impl == "ours" else f"{n} agent(s) sequential on 1 GPU (reference design)",
+            "parallelism": f"agent-parallel: {k} agent(s) on {n} GPU(s)" if impl == "ours" else f"{k} agent(s) sequential on 1 GPU (reference design)",
             "l2_policy": "inputs larger than L2: each step streams a fresh batch from the 150 MB device-resident dataset plus "
                          "4x45 MB flat parameter/grad/momentum buffers and >100 MB of activations (L2 = 126 MB)",
             "timed_region": "local training of all agents + aggregation + parameter hand-off; evaluation excluded"}
@@ -118,7 +124,7 @@ def run_reference(a):
         return
     clocks = ClockSampler(0)
     t0 = time.time()
-    res = rr.run(data=a.data, model=a.model, num_agents=a.gpus, local_ep=a.local_ep, bs=a.bs, aggr=a.aggr,
+    res = rr.run(data=a.data, model=a.model, num_agents=a.agents or a.gpus, local_ep=a.local_ep, bs=a.bs, aggr=a.aggr,
                  train_size=a.train_size, steps=a.steps, warmup=a.warmup, theta=a.theta, num_corrupt=a.num_corrupt,
                  poison_frac=a.poison_frac, device="cuda:0")
     ck = clocks.stop()
@@ -146,7 +152,8 @@ def run_ours(a):
     if n != a.gpus and ctx.is_main:
         print(f"[bench] warning: --gpus {a.gpus} but WORLD_SIZE={n}; using {n}", file=sys.stderr)
     def make_engine(trainer):
-        args = make_args(data=a.data, model=a.model, num_agents=n, local_ep=a.local_ep, bs=a.bs, aggr=a.aggr,
+        args = make_args(data=a.data, model=a.model, num_agents=a.agents or n, agents_in_flight=a.agents_in_flight, local_ep=a.local_ep, bs=a.bs,
+                         aggr=a.aggr,
                          robustLR_threshold=a.theta, num_corrupt=a.num_corrupt, poison_frac=a.poison_frac,
                          synthetic=a.train_size, synthetic_val=1000, snap=10 ** 9, rounds=10 ** 9, log_dir="",
                          trainer=trainer, backend=a.backend, dtype=a.dtype, seed=0)

@@ -46,10 +46,12 @@ LIST
 # concurrency of several agents per GPU (the reference's README workload: FMNIST CNN, 10 agents on one GPU)
 RLR_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_gpu_experimental.py -m gpu -q -s -k agents_in_flight > gpurun_out/r2_exp_inflight.txt 2>&1
 echo "test inflight: exit $? ($(tail -1 gpurun_out/r2_exp_inflight.txt))" | tee -a gpurun_out/r2_summary.txt
+readme="--model cnn_mnist --data fmnist --train_size 60000 --agents 10 --steps 3 --warmup 3 --no_e2e"
+timeout 600 python bench.py --impl reference $readme > gpurun_out/r2_readme_reference.json 2> gpurun_out/r2_readme_reference.err
+echo "README workload (FMNIST CNN, 10 agents, 1 GPU) reference: $(tail -1 gpurun_out/r2_readme_reference.json | cut -c1-160)" | tee -a gpurun_out/r2_summary.txt
 for nf in 1 2 4; do
-    timeout 200 python federated.py --data=fmnist --num_agents=10 --local_ep=2 --bs=256 --rounds=6 --snap=100 --synthetic=60000 --synthetic_val=1000 \
-        --log_dir= --no_tensorboard --profile_phases --agents_in_flight=$nf > gpurun_out/r2_inflight_$nf.txt 2>&1
-    echo "fmnist 10 agents, agents_in_flight=$nf: $(grep -o "'ms_local_train': [0-9.]*" gpurun_out/r2_inflight_$nf.txt | tail -1)" | tee -a gpurun_out/r2_summary.txt
+    timeout 200 python bench.py $readme --agents_in_flight $nf > gpurun_out/r2_readme_ours_$nf.json 2> gpurun_out/r2_readme_ours_$nf.err
+    echo "README workload ours, agents_in_flight=$nf: $(tail -1 gpurun_out/r2_readme_ours_$nf.json | cut -c1-160)" | tee -a gpurun_out/r2_summary.txt
 done
 bench default_last NONE=1
 cat gpurun_out/r2_summary.txt
