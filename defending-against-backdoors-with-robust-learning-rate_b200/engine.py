@@ -16,6 +16,7 @@ aggregation + parameter hand-off), evaluation excluded -- BASELINE.md section 2.
 """
 from __future__ import annotations
 
+import contextlib
 import math
 import random
 
@@ -97,10 +98,10 @@ class FLEngine:
         self.trainer = make_trainer(args.trainer, self.layout, args, dev, max_shard)
         # Several agents per GPU and round can be trained concurrently: trainer i (own parameters, activations, CUDA graphs) runs
         # on stream i.  The small reference CNNs are launch-latency bound at batch 256, so two to four agents in flight fill the GPU.
-        n_flight = max(1, int(getattr(args, "agents_in_flight", 1))) if dev.type == "cuda" else 1
-        n_flight = min(n_flight, max_slots)
+        n_flight = min(max(1, int(getattr(args, "agents_in_flight", 1))), max_slots)
         self.trainers = [self.trainer] + [make_trainer(args.trainer, self.layout, args, dev, max_shard) for _ in range(n_flight - 1)]
-        self.streams = [torch.cuda.Stream(dev) for _ in range(n_flight)] if n_flight > 1 else None
+        # (on CPU the extra trainers are still used round-robin -- same bookkeeping, no overlap)
+        self.streams = [torch.cuda.Stream(dev) for _ in range(n_flight)] if (n_flight > 1 and dev.type == "cuda") else None
         self._loss_parts = [torch.zeros(1, dtype=torch.float32, device=dev) for _ in range(n_flight)]
         self.logger = MetricLogger(args, enabled=ctx.is_main and bool(args.log_dir))
         self.aggregator = Aggregation(self.agent_data_sizes, self.layout.n_params, self.poisoned_val, args,
@@ -180,13 +181,14 @@ class FLEngine:
         steps = 0
         h2d = 0
         self.timer.start("local_train")
-        concurrent = self.streams is not None and not stream_inputs     # streamed inputs share one staging buffer: sequential
+        concurrent = len(self.trainers) > 1 and not stream_inputs       # streamed inputs share one staging buffer: sequential
         if concurrent:
-            cur = torch.cuda.current_stream(ctx.device)
-            for st_ in self.streams:
-                st_.wait_stream(cur)                                     # w_global of this round is ready
             for part in self._loss_parts:
                 part.zero_()
+            if self.streams is not None:
+                cur = torch.cuda.current_stream(ctx.device)
+                for st_ in self.streams:
+                    st_.wait_stream(cur)                                 # w_global of this round is ready
         k = 0
         for j, aid in enumerate(chosen):
             r, s = fused.slot_owner(j)
@@ -195,7 +197,7 @@ class FLEngine:
             agent = self.agents[aid]
             if concurrent:
                 i = k % len(self.trainers)
-                with torch.cuda.stream(self.streams[i]):
+                with (torch.cuda.stream(self.streams[i]) if self.streams is not None else contextlib.nullcontext()):
                     st = agent.local_train(self.trainers[i], self.w_global, fused.slots[s], rnd)
                     self._loss_parts[i] += st["loss_sum"]
             else:
@@ -206,8 +208,9 @@ class FLEngine:
             steps += st["steps"]
             k += 1
         if concurrent:
-            for st_ in self.streams:
-                cur.wait_stream(st_)                                     # every slot is final before the aggregation kernel
+            if self.streams is not None:
+                for st_ in self.streams:
+                    cur.wait_stream(st_)                                 # every slot is final before the aggregation kernel
             for part in self._loss_parts:
                 self.round_loss += part
         self.timer.stop("local_train")

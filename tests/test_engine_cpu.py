@@ -179,3 +179,21 @@ def test_participant_placement_balances_skewed_shards():
     fake.ctx.world = 1
     fake.agents = [SimpleNamespace(n_data=n) for n in sizes]
     assert FLEngine.place_participants(fake, chosen) == chosen
+
+
+def test_agents_in_flight_bookkeeping_matches_sequential():
+    """--agents_in_flight: the agents of a rank are spread round-robin over several trainers (concurrent CUDA streams on a GPU); on
+    CPU the schedule is still sequential, so the aggregated parameters and the round loss must equal the single-trainer run exactly
+    for a dropout-free model."""
+    res = {}
+    for nf in (1, 3):
+        eng = _engine(data="cifar10", model="resnet18", synthetic=160, synthetic_val=40, num_agents=5, local_ep=1, bs=16, agents_in_flight=nf,
+                      robustLR_threshold=2)
+        assert len(eng.trainers) == nf and eng.streams is None
+        info = eng.run_round(1)
+        loss, _ = eng.round_result()
+        res[nf] = (eng.w_global.clone(), loss, info["steps"])
+        eng.close()
+    assert res[1][2] == res[3][2]
+    torch.testing.assert_close(res[3][0], res[1][0], rtol=0, atol=0)
+    assert abs(res[1][1] - res[3][1]) < 1e-4 * abs(res[1][1])          # per-trainer partial sums: float summation order only
