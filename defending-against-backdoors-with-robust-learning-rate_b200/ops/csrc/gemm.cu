@@ -385,7 +385,11 @@ cudaError_t launch_gemm_bf16(const void* A, const void* B, void* out, int M, int
     if (K % BK || N % 8 || M <= 0) return cudaErrorInvalidValue;
     const int m_tiles = (M + BM - 1) / BM;
     const int bn2 = pair_bn(m_tiles, N, stats == nullptr);
-    const int bn = bn2 ? bn2 : pick_bn(N);
+    int bn = bn2 ? bn2 : pick_bn(N);
+    {   // opt-in (RLR_GEMM_SMALL_BN64=1, not yet measured): small-batch linear layers (M = 256: two M tiles) get twice the CTAs
+        static const int small64 = [] { const char* e = getenv("RLR_GEMM_SMALL_BN64"); return e ? atoi(e) : 0; }();
+        if (small64 && !bn2 && bn == 128 && m_tiles * (N / 128) < sm_count()) bn = 64;
+    }
     CUtensorMap tmA, tmB;
     {
         const uint64_t d[2] = {(uint64_t)K, (uint64_t)M}, s[1] = {(uint64_t)lda * 2};

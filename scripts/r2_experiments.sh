@@ -46,6 +46,10 @@ LIST
 # concurrency of several agents per GPU (the reference's README workload: FMNIST CNN, 10 agents on one GPU)
 RLR_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_gpu_experimental.py -m gpu -q -s -k agents_in_flight > gpurun_out/r2_exp_inflight.txt 2>&1
 echo "test inflight: exit $? ($(tail -1 gpurun_out/r2_exp_inflight.txt))" | tee -a gpurun_out/r2_summary.txt
+for v in 0 1; do
+    RLR_GEMM_SMALL_BN64=$v RLR_EXPERIMENTAL=1 timeout 120 python -m pytest tests/test_gpu_experimental.py -m gpu -q -s -k small_batch_gemm 2>&1 \
+        | grep "gemm \|passed\|failed" | sed "s/^/RLR_GEMM_SMALL_BN64=$v  /" | tee -a gpurun_out/r2_summary.txt
+done
 readme="--model cnn_mnist --data fmnist --train_size 60000 --agents 10 --steps 3 --warmup 3 --no_e2e"
 timeout 600 python bench.py --impl reference $readme > gpurun_out/r2_readme_reference.json 2> gpurun_out/r2_readme_reference.err
 echo "README workload (FMNIST CNN, 10 agents, 1 GPU) reference: $(tail -1 gpurun_out/r2_readme_reference.json | cut -c1-160)" | tee -a gpurun_out/r2_summary.txt

@@ -342,3 +342,23 @@ def test_agents_in_flight_matches_sequential_training():
     cos = torch.nn.functional.cosine_similarity(res[1][0].double(), res[2][0].double(), dim=0)
     assert float(cos) > 0.999, float(cos)
     assert abs(res[1][1] - res[2][1]) < 0.05 * abs(res[1][1]) + 1e-3
+
+
+def test_small_batch_gemm_shapes():
+    """Linear layers of the small CNNs as the tcgen05 GEMM sees them (M = 256): correctness at these shapes with whatever tile
+    heuristic is active (run with RLR_GEMM_SMALL_BN64=1 to cover the 64-wide choice); prints the device time of each."""
+    for M, N, K in [(256, 128, 9216), (256, 128, 1024), (256, 256, 128), (64, 128, 9216)]:
+        torch.manual_seed(K)
+        A = torch.randn(M, K, device=DEV).to(BF)
+        Bm = (torch.randn(N, K, device=DEV) / K ** 0.5).to(BF)
+        bias = torch.randn(N, device=DEV) * 0.1
+        out = torch.empty(M, N, device=DEV, dtype=BF)
+        ops.ext().gemm_bf16(A, Bm, out, bias, True, False, None)
+        ref = torch.relu(A.float() @ Bm.float().t() + bias)
+        assert float((out.float() - ref).abs().max() / ref.abs().max()) < 1e-2
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            ops.ext().gemm_bf16(A, Bm, out, bias, True, False, None)
+        e1.record(); torch.cuda.synchronize()
+        print(f"gemm {M}x{N}x{K}: {e0.elapsed_time(e1) / 20 * 1000:.1f} us")
