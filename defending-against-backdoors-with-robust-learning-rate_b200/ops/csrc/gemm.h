@@ -37,6 +37,10 @@ cudaError_t launch_gemm_bf16(const void* A, const void* B, void* out, int M, int
                              const float* bias, int relu, int accumulate, float* stats, cudaStream_t st);
 // programmatic dependent launch for the hot kernels (common.cuh: launch_kernel / pdl_wait); default: RLR_PDL env, off
 void set_pdl(int on);
+// gemm_splitk.cu (opt-in): small-M / deep-K GEMM, grid.z CTAs share a tile's k range and add fp32 partials into `ws` ([M][N], zero on
+// entry and left zero), then one finishing pass applies bias / ReLU and packs bf16
+cudaError_t launch_gemm_splitk_bf16(const void* A, const void* B, void* out, float* ws, int M, int N, int K, const float* bias, int relu,
+                                    int num_sms, cudaStream_t st);
 // opt-in CTA-pair kernel (gemm_2cta.cu: tcgen05.mma.cta_group::2, M = 256, half a B tile per CTA); default: RLR_CONV_2CTA env, off
 void set_conv_2cta(int on);
 // opt-in persistent tile scheduler for the generic conv / GEMM kernel (gemm_persistent.cu); default: RLR_PERSISTENT_CONV env

@@ -56,6 +56,15 @@ void conv_bf16(at::Tensor x, at::Tensor w, at::Tensor out, int64_t NB, int64_t p
                                 (int)w_taps_total), "conv_bf16");
 }
 
+// out[M][N] = act(A[M][K] @ B[N][K]^T + bias) with split-K partial sums in ws ([M][N] fp32, zero on entry, left zero)
+void gemm_splitk_bf16(at::Tensor A, at::Tensor B, at::Tensor out, at::Tensor ws, c10::optional<at::Tensor> bias, bool relu) {
+    c10::cuda::CUDAGuard g(A.device());
+    const int M = A.size(0), K = A.size(1), N = B.size(0);
+    TORCH_CHECK(B.size(1) == K && out.size(0) == M && out.size(1) == N && ws.numel() == (int64_t)M * N);
+    check(rlr::launch_gemm_splitk_bf16(bf(A), bf(B), bfm(out), f32(ws), M, N, K, opt<const float>(bias), relu, num_sms(), cur_stream()),
+          "gemm_splitk_bf16");
+}
+
 // Strided variant without parity-split copies: x [NB,Hin,Win,Cin] is the ORIGINAL input, read through a TMA box with element
 // strides (in_stride, 2 for stride-2 forward convs); `out` [NB,OutH,OutW,Cout] is the FULL output image and this launch fills the
 // pixels (out_stride*h + out_ph, out_stride*w + out_pw) of it (out_stride 2 = one parity plane of a stride-2 data gradient).
@@ -281,6 +290,7 @@ void register_gemm_bindings(py::module_& m) {
     m.def("set_pdl", [](bool on) { rlr::set_pdl(on ? 1 : 0); });
     m.def("set_conv_occ3", [](int64_t level) { rlr::set_conv_occ3((int)level); });
     m.def("gemm_bf16", &gemm_bf16);
+    m.def("gemm_splitk_bf16", &gemm_splitk_bf16);
     m.def("conv_bf16", &conv_bf16);
     m.def("conv_bf16_strided", &conv_bf16_strided);
     m.def("conv_wgrad_bf16_strided", &conv_wgrad_bf16_strided);

@@ -30,6 +30,9 @@ USE_BN_RECOMPUTE = bool(int(os.environ.get("RLR_BN_RECOMPUTE", "0")))
 # 3x3/s1/p1 convs with 64 input channels: three filter taps per N = 192 MMA with a lane shift-add epilogue (conv_halo3.cu) instead of
 # nine N = 64 MMAs per k-step.  Opt-in until measured on hardware (RLR_HALO3=1).
 USE_HALO3 = bool(int(os.environ.get("RLR_HALO3", "0")))
+# Dense layers with few output tiles and a deep reduction (FMNIST CNN fc1: 256 x 128 x 9216): split-K GEMM with an fp32 workspace
+# (gemm_splitk.cu).  Opt-in until measured on hardware (RLR_SPLITK=1).
+USE_SPLITK = bool(int(os.environ.get("RLR_SPLITK", "0")))
 # Classifier-head kernels v2 (weights staged in shared memory, weight gradient spread over K/64 x B/16 blocks with float atomics).
 # Opt-in until measured on hardware (RLR_HEAD_V2=1).
 USE_HEAD_V2 = bool(int(os.environ.get("RLR_HEAD_V2", "0")))
@@ -400,6 +403,11 @@ def linear_fwd(x, w, bias, y, relu, impl):
             _ext().linear_small_fwd(x.contiguous(), w, bias, y, bool(relu))
             return
         if K % 64 == 0 and N % 64 == 0:
+            M = x.shape[0]
+            if USE_SPLITK and K >= 1024 and ((M + 127) // 128) * ((N + 127) // 128) <= 16:
+                ws = scratch(("splitk_ws", y.data_ptr()), (M, N), torch.float32, x.device)     # zero at creation, left zero by the kernel
+                _ext().gemm_splitk_bf16(x.contiguous(), w, y, ws, bias, bool(relu))
+                return
             _ext().gemm_bf16(x.contiguous(), w, y, bias, bool(relu), False, None)
             return
     out = F.linear(x, w.to(x.dtype), bias.to(x.dtype) if bias is not None else None)

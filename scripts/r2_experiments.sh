@@ -38,6 +38,7 @@ stem         im2col_stem                  RLR_IM2COL_STEM=1
 bnmask       recomputed_relu_mask         RLR_BN_RECOMPUTE=1
 occ3x        occ3_level2                  RLR_CONV_OCC3=2
 head         head_kernels_v2              RLR_HEAD_V2=1
+splitk       splitk_gemm                  RLR_SPLITK=1
 halo3        halo3_kernel                 RLR_HALO3=1
 pdl          programmatic_dependent       RLR_PDL=1
 pair         cta_pair                     RLR_CONV_2CTA=1

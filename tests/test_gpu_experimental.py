@@ -362,3 +362,29 @@ def test_small_batch_gemm_shapes():
             ops.ext().gemm_bf16(A, Bm, out, bias, True, False, None)
         e1.record(); torch.cuda.synchronize()
         print(f"gemm {M}x{N}x{K}: {e0.elapsed_time(e1) / 20 * 1000:.1f} us")
+
+
+@pytest.mark.parametrize("M,N,K,relu", [(256, 128, 9216, True), (64, 128, 9216, False), (256, 256, 1024, True), (100, 192, 2048, False)])
+def test_splitk_gemm(M, N, K, relu):
+    """RLR_SPLITK: grid.z CTAs share a tile's k range and add fp32 partials into a workspace; finish pass applies bias / ReLU, packs
+    bf16 and re-zeroes the workspace (second call must give the same result)."""
+    torch.manual_seed(M + K)
+    A = torch.randn(M, K, device=DEV).to(BF)
+    Bm = (torch.randn(N, K, device=DEV) / K ** 0.5).to(BF)
+    bias = torch.randn(N, device=DEV) * 0.1
+    ws = torch.zeros(M, N, device=DEV)
+    ref = A.float() @ Bm.float().t() + bias
+    if relu:
+        ref = ref.clamp_min(0)
+    for _ in range(2):
+        out = torch.full((M, N), 9.0, device=DEV, dtype=BF)
+        ops.ext().gemm_splitk_bf16(A, Bm, out, ws, bias, relu)
+        torch.cuda.synchronize()
+        assert float((out.float() - ref).abs().max() / ref.abs().max()) < 1e-2
+        assert float(ws.abs().max()) == 0.0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        ops.ext().gemm_splitk_bf16(A, Bm, out, ws, bias, relu)
+    e1.record(); torch.cuda.synchronize()
+    print(f"split-K gemm {M}x{N}x{K}: {e0.elapsed_time(e1) / 20 * 1000:.1f} us (two kernels)")
