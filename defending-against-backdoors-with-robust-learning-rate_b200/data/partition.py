@@ -10,8 +10,6 @@ from __future__ import annotations
 
 from collections import defaultdict
 
-import torch
-
 
 def distribute_data(dataset, args=None, n_classes: int = 10, class_per_agent: int = 10, num_agents: int | None = None):
     """Return ``{agent_id: list[int]}`` of sample indices."""

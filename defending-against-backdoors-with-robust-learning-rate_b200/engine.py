@@ -23,7 +23,6 @@ import random
 import numpy as np
 import torch
 
-from . import ops
 from .agent import Agent
 from .aggregation import Aggregation
 from .data import distribute_data, get_datasets, make_poisoned_val
