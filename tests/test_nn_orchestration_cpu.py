@@ -366,3 +366,72 @@ def test_halo3_tile_algorithm_emulation():
                 out[n, (h0 + hl)[ok], c[ok]] = val[ok]
     assert not torch.isnan(out).any()
     torch.testing.assert_close(out, ref, rtol=1e-4, atol=1e-4)
+
+
+def _pow2_ceil(x):
+    p = 1
+    while p < x:
+        p <<= 1
+    return p
+
+
+def _simulate_conv_kernel_indexing(x, w2d, NB, Ho, Wo, Cout, dh, dw, in_stride, out_stride, ph, pw):
+    """Python transcription of the index arithmetic of launch_conv_bf16 + umma_conv_gemm_kernel (ops/csrc/gemm.cu): tile shape
+    TW x TH x TN = 128 output pixels, tile origin, per-row global output index `gi`, and the TMA box of tap t starting at
+    (w0 * in_stride + dw[t], h0 * in_stride + dh[t], n0) with element strides (in_stride, in_stride) and zero fill out of bounds."""
+    Hin, Win, Cin = x.shape[1], x.shape[2], x.shape[3]
+    TW = min(_pow2_ceil(Wo), 128)
+    TH = _pow2_ceil(Ho)
+    if TW * TH > 128:
+        TH = 128 // TW
+    TN = 128 // (TW * TH)
+    tiles_w, tiles_h, tiles_n = -(-Wo // TW), -(-Ho // TH), -(-NB // TN)
+    OutH, OutW = Ho * out_stride, Wo * out_stride
+    out = torch.full((NB * OutH * OutW, Cout), float("nan"))
+    for tile_m in range(tiles_w * tiles_h * tiles_n):
+        w0, h0, n0 = (tile_m % tiles_w) * TW, ((tile_m // tiles_w) % tiles_h) * TH, (tile_m // (tiles_w * tiles_h)) * TN
+        r = torch.arange(128)
+        tw, th, tn = r % TW, (r // TW) % TH, r // (TW * TH)
+        w_, h_, n_ = w0 + tw, h0 + th, n0 + tn
+        valid = (w_ < Wo) & (h_ < Ho) & (n_ < NB)
+        gi = (n_ * OutH + h_ * out_stride + ph) * OutW + w_ * out_stride + pw
+        acc = torch.zeros(128, Cout)
+        for t in range(len(dh)):
+            cw, ch = w0 * in_stride + dw[t] + tw * in_stride, h0 * in_stride + dh[t] + th * in_stride     # box element (tw, th)
+            inb = (cw >= 0) & (cw < Win) & (ch >= 0) & (ch < Hin) & (n_ < NB)
+            a = x[n_.clamp(max=NB - 1), ch.clamp(0, Hin - 1), cw.clamp(0, Win - 1)] * inb[:, None]
+            acc += a @ w2d[:, t * Cin:(t + 1) * Cin].t()
+        out[gi[valid]] = acc[valid]
+    return out.view(NB, OutH, OutW, Cout)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,p", [(3, 8, 8, 8, 16, 3, 1), (2, 16, 16, 8, 8, 1, 0), (5, 4, 4, 8, 8, 3, 1), (1, 32, 32, 8, 8, 3, 1)])
+def test_kernel_index_arithmetic_for_strided_input_and_output(B, H, W, Cin, Cout, k, p):
+    """The two additions to the generic conv kernel's index math -- strided TMA boxes for stride-2 forward convolutions and strided
+    output rows for the parity planes of stride-2 data gradients -- reproduce PyTorch when transcribed literally."""
+    torch.manual_seed(B + H)
+    x = torch.randn(B, H, W, Cin)
+    w = torch.randn(Cout, k, k, Cin)
+    Ho, Wo = (H + 2 * p - k) // 2 + 1, (W + 2 * p - k) // 2 + 1
+    dh = [d - p for d in range(k) for _ in range(k)]
+    dw = [d - p for _ in range(k) for d in range(k)]
+    y = _simulate_conv_kernel_indexing(x, w.reshape(Cout, -1), B, Ho, Wo, Cout, dh, dw, 2, 1, 0, 0)
+    ref = F.conv2d(x.permute(0, 3, 1, 2), w.permute(0, 3, 1, 2), None, 2, p).permute(0, 2, 3, 1)
+    torch.testing.assert_close(y, ref, rtol=1e-4, atol=1e-4)
+    # data gradient: plane (pi, pj) of dX is a stride-1 conv of dY with the taps of matching parity, stored at (2a+pi, 2b+pj)
+    dy = torch.randn(B, Ho, Wo, Cout)
+    dx = torch.zeros(B, H, W, Cin)
+    wt = w.permute(1, 2, 0, 3).reshape(k * k, Cout, Cin)                  # per tap: [Cout][Cin]
+    for pi in range(2):
+        for pj in range(2):
+            taps = [(fy, fx) for fy in range(k) for fx in range(k) if (pi + p - fy) % 2 == 0 and (pj + p - fx) % 2 == 0]
+            if not taps:
+                continue
+            w_plane = torch.cat([wt[fy * k + fx].t() for fy, fx in taps], dim=1)          # [Cin][ntaps * Cout] == K-major "filter" of this conv
+            plane = _simulate_conv_kernel_indexing(dy, w_plane, B, H // 2, W // 2, Cin, [(pi + p - fy) // 2 for fy, _ in taps],
+                                                   [(pj + p - fx) // 2 for _, fx in taps], 1, 2, pi, pj)
+            m = ~torch.isnan(plane)
+            dx[m] = plane[m]
+    xn = x.permute(0, 3, 1, 2).clone().requires_grad_(True)
+    F.conv2d(xn, w.permute(0, 3, 1, 2), None, 2, p).backward(dy.permute(0, 3, 1, 2))
+    torch.testing.assert_close(dx, xn.grad.permute(0, 2, 3, 1), rtol=1e-4, atol=1e-4)
