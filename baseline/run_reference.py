@@ -5,7 +5,7 @@ What is the reference's and what is ours:
   ``Agent`` (DataLoader, local_train), ``Aggregation.aggregate_updates``, ``models.get_model`` (for its own CNNs).
 * shims (ours): ``utils.get_datasets`` -> synthetic torchvision-style dataset (the reference downloads, no network
   here), the 6-line round loop of src/federated.py:65-74 (the reference's is module-level script code that cannot be
-  imported), and -- only for ``--model resnet18|vgg11`` -- ``models.get_model`` -> baseline/torch_models.py because the
+  imported), and -- only for ``--model resnet18|resnet34|vgg11|vgg16`` -- ``models.get_model`` -> baseline/torch_models.py because the
   reference has no such architectures.
 Timed region = src/federated.py:66-74 (local training of every sampled agent + restore + aggregation), no evaluation.
 """
@@ -95,10 +95,11 @@ def run(data="cifar10", model="resnet18", num_agents=1, local_ep=2, bs=256, aggr
             tf = transforms.Compose([transforms.ToTensor(), transforms.Normalize(mean=[0.2860], std=[0.3530])])
         train_dataset = _synthetic_vision_dataset(data, train_size, seed, tf)
         ref_utils.get_datasets = lambda _d: (train_dataset, None)          # shim #1 (documented above)
-        if model in ("resnet18", "vgg11"):                                 # shim #3: architectures the reference lacks
+        if model in ("resnet18", "resnet34", "vgg11", "vgg16"):                                 # shim #3: architectures the reference lacks
             sys.path.insert(0, HERE)
             import torch_models
-            ctor = torch_models.ResNet18 if model == "resnet18" else torch_models.VGG11
+            ctor = {"resnet18": torch_models.ResNet18, "resnet34": torch_models.ResNet34, "vgg11": torch_models.VGG11,
+                    "vgg16": torch_models.VGG16}[model]
             ref_models.get_model = lambda _d: ctor()
 
         user_groups = ref_utils.distribute_data(train_dataset, args)

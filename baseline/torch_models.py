@@ -28,13 +28,15 @@ class BasicBlock(nn.Module):
 
 
 class ResNet18(nn.Module):
+    BLOCKS = (2, 2, 2, 2)
+
     def __init__(self, num_classes=10):
         super().__init__()
         self.conv1 = nn.Conv2d(3, 64, 3, 1, 1, bias=False)
         self.bn1 = nn.BatchNorm2d(64)
         layers, cin = [], 64
-        for cout, stride in [(64, 1), (128, 2), (256, 2), (512, 2)]:
-            layers += [BasicBlock(cin, cout, stride), BasicBlock(cout, cout, 1)]
+        for (cout, stride), nb in zip([(64, 1), (128, 2), (256, 2), (512, 2)], self.BLOCKS):
+            layers += [BasicBlock(cin, cout, stride)] + [BasicBlock(cout, cout, 1) for _ in range(nb - 1)]
             cin = cout
         self.layers = nn.Sequential(*layers)
         self.fc = nn.Linear(512, num_classes)
@@ -46,11 +48,17 @@ class ResNet18(nn.Module):
         return self.fc(x)
 
 
+class ResNet34(ResNet18):
+    BLOCKS = (3, 4, 6, 3)
+
+
 class VGG11(nn.Module):
+    CFG = [64, "M", 128, "M", 256, 256, "M", 512, 512, "M", 512, 512, "M"]
+
     def __init__(self, num_classes=10):
         super().__init__()
         mods, cin = [], 3
-        for v in [64, "M", 128, "M", 256, 256, "M", 512, 512, "M", 512, 512, "M"]:
+        for v in self.CFG:
             if v == "M":
                 mods.append(nn.MaxPool2d(2, 2))
             else:
@@ -61,3 +69,7 @@ class VGG11(nn.Module):
 
     def forward(self, x):
         return self.classifier(self.features(x).flatten(1))
+
+
+class VGG16(VGG11):
+    CFG = [64, 64, "M", 128, 128, "M", 256, 256, 256, "M", 512, 512, 512, "M", 512, 512, 512, "M"]

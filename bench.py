@@ -136,7 +136,7 @@ def run_reference(a):
                    "d2h_bytes_per_step": 0, "note": "wall clock of the same rounds; the reference copies every batch from pageable host memory"},
            "gpu_launches": 0,
            "note": ("unmodified reference Agent/Aggregation loop on 1 GPU"
-                    + ("; ResNet-18/VGG-11 are not in the reference: plain torch.nn definition from baseline/torch_models.py" if a.model in ("resnet18", "vgg11") else "")),
+                    + ("; ResNet / VGG are not in the reference: plain torch.nn definition from baseline/torch_models.py" if a.model in ("resnet18", "resnet34", "vgg11", "vgg16") else "")),
            "wall_s_total": time.time() - t0}
     print(json.dumps(out))
 

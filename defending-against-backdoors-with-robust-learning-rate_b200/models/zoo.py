@@ -3,7 +3,8 @@
 ``cnn_mnist`` / ``cnn_cifar`` are the reference's two networks (src/models.py:11-31, :33-58), layer for layer.
 ``resnet18`` / ``vgg11`` are NOT in the reference: they are the CIFAR variants named by
 BASELINE.json -- ResNet-18 with a 3x3 stem and no max-pool (11,173,962 parameters) and VGG-11-BN with a single
-``Linear(512,10)`` head (9,231,114 parameters).
+``Linear(512,10)`` head (9,231,114 parameters).  ``resnet34`` / ``vgg16`` are the deeper members of the same two
+families (same layer types, hence the same kernels).
 """
 from __future__ import annotations
 
@@ -34,11 +35,11 @@ def cnn_cifar():
     return n, (3, 32, 32)
 
 
-def resnet18(num_classes=10):
+def _resnet(blocks, num_classes=10):
     n = [Node("conv", "conv1", attrs=dict(cin=3, cout=64, k=3, pad=1, bias=False)), Node("bn", "bn1", attrs=dict(c=64)), Node("relu")]
     cin = 64
     for li, (cout, stride) in enumerate([(64, 1), (128, 2), (256, 2), (512, 2)], 1):
-        for bi in range(2):
+        for bi in range(blocks[li - 1]):
             s = stride if bi == 0 else 1
             pre = f"layer{li}.{bi}"
             n.append(Node("save", out="id"))
@@ -56,9 +57,23 @@ def resnet18(num_classes=10):
     return n, (3, 32, 32)
 
 
-def vgg11(num_classes=10):
+def resnet18(num_classes=10):
+    """CIFAR ResNet-18 (BasicBlock x [2,2,2,2], 3x3 stem, no max-pool): 11,173,962 parameters."""
+    return _resnet((2, 2, 2, 2), num_classes)
+
+
+def resnet34(num_classes=10):
+    """CIFAR ResNet-34 (BasicBlock x [3,4,6,3]): same layer types as ResNet-18, so every layer runs on the same kernels."""
+    return _resnet((3, 4, 6, 3), num_classes)
+
+
+_VGG = {"vgg11": [64, "M", 128, "M", 256, 256, "M", 512, 512, "M", 512, 512, "M"],
+        "vgg16": [64, 64, "M", 128, 128, "M", 256, 256, 256, "M", 512, 512, 512, "M", 512, 512, 512, "M"]}
+
+
+def _vgg(cfg, num_classes=10):
     n, cin, i = [], 3, 0
-    for v in [64, "M", 128, "M", 256, 256, "M", 512, 512, "M", 512, 512, "M"]:
+    for v in _VGG[cfg]:
         if v == "M":
             n.append(Node("maxpool"))
         else:
@@ -71,4 +86,14 @@ def vgg11(num_classes=10):
     return n, (3, 32, 32)
 
 
-ZOO = {"cnn_mnist": cnn_mnist, "cnn_cifar": cnn_cifar, "resnet18": resnet18, "vgg11": vgg11}
+def vgg11(num_classes=10):
+    """VGG-11-BN with a single Linear(512, 10) head: 9,231,114 parameters."""
+    return _vgg("vgg11", num_classes)
+
+
+def vgg16(num_classes=10):
+    """VGG-16-BN, same head."""
+    return _vgg("vgg16", num_classes)
+
+
+ZOO = {"cnn_mnist": cnn_mnist, "cnn_cifar": cnn_cifar, "resnet18": resnet18, "resnet34": resnet34, "vgg11": vgg11, "vgg16": vgg16}

@@ -14,7 +14,7 @@ import torch
 DATASETS = ("fmnist", "fedemnist", "cifar10")
 AGGREGATORS = ("avg", "comed", "sign")
 PATTERNS = ("plus", "square", "copyright", "apple")
-MODELS = ("auto", "cnn_mnist", "cnn_cifar", "resnet18", "vgg11")
+MODELS = ("auto", "cnn_mnist", "cnn_cifar", "resnet18", "resnet34", "vgg11", "vgg16")
 
 
 def _default_device():

@@ -47,6 +47,8 @@ LIST
 # concurrency of several agents per GPU (the reference's README workload: FMNIST CNN, 10 agents on one GPU)
 RLR_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_gpu_experimental.py -m gpu -q -s -k agents_in_flight > gpurun_out/r2_exp_inflight.txt 2>&1
 echo "test inflight: exit $? ($(tail -1 gpurun_out/r2_exp_inflight.txt))" | tee -a gpurun_out/r2_summary.txt
+RLR_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_gpu_experimental.py -m gpu -q -s -k deeper_family > gpurun_out/r2_exp_family.txt 2>&1
+echo "test resnet34/vgg16 on native kernels: exit $? ($(grep "logit rel" gpurun_out/r2_exp_family.txt | tr '\n' ';') $(tail -1 gpurun_out/r2_exp_family.txt))" | tee -a gpurun_out/r2_summary.txt
 for v in 0 1; do
     RLR_GEMM_SMALL_BN64=$v RLR_EXPERIMENTAL=1 timeout 120 python -m pytest tests/test_gpu_experimental.py -m gpu -q -s -k small_batch_gemm 2>&1 \
         | grep "gemm \|passed\|failed" | sed "s/^/RLR_GEMM_SMALL_BN64=$v  /" | tee -a gpurun_out/r2_summary.txt

@@ -388,3 +388,31 @@ def test_splitk_gemm(M, N, K, relu):
         ops.ext().gemm_splitk_bf16(A, Bm, out, ws, bias, relu)
     e1.record(); torch.cuda.synchronize()
     print(f"split-K gemm {M}x{N}x{K}: {e0.elapsed_time(e1) / 20 * 1000:.1f} us (two kernels)")
+
+
+@pytest.mark.parametrize("model,B", [("resnet34", 32), ("vgg16", 32)])
+def test_deeper_family_members_on_native_kernels(model, B):
+    """ResNet-34 / VGG-16 (same layer types and shapes as ResNet-18 / VGG-11): kernels vs library calls through the same plan."""
+    import torch.nn.functional as F
+    from rlr_b200.models import get_layout
+    from rlr_b200.models.native import NativeNet, native_supported
+    torch.manual_seed(0)
+    lay = get_layout(model)
+    assert native_supported(lay)
+    w = lay.init_(torch.zeros(lay.n_total, device=DEV), 1)
+    C, H, W = lay.in_shape
+    x = torch.randn(B, H, W, C, device=DEV).to(BF)
+    y = torch.randint(0, 10, (B,), device=DEV)
+    res = {}
+    for impl in ("aten", "sm100"):
+        net = NativeNet(lay, DEV, B, impl=impl)
+        wi, g = w.clone(), torch.zeros_like(w)
+        net.bind(wi, wi.to(BF), g)
+        logits = net.forward(x, True).clone()
+        _, dl = ops.softmax_xent(logits, y)
+        net.backward(dl)
+        res[impl] = (logits.float(), g[: lay.n_vote].clone())
+    rel = float((res["sm100"][0] - res["aten"][0]).abs().max() / res["aten"][0].abs().max())
+    cos = float(F.cosine_similarity(res["sm100"][1].double(), res["aten"][1].double(), dim=0))
+    print(model, "logit rel", rel, "grad cos", cos)
+    assert rel < 8e-2 and cos > 0.9

@@ -6,7 +6,8 @@ from rlr_b200.models import get_layout, get_model
 
 
 @pytest.mark.parametrize("name,n_params,shape", [("cnn_mnist", 1_199_882, (1, 28, 28)), ("cnn_cifar", 537_610, (3, 32, 32)),
-                                                 ("resnet18", 11_173_962, (3, 32, 32)), ("vgg11", 9_231_114, (3, 32, 32))])
+                                                 ("resnet18", 11_173_962, (3, 32, 32)), ("vgg11", 9_231_114, (3, 32, 32)),
+                                                 ("resnet34", 21_282_122, (3, 32, 32)), ("vgg16", 14_728_266, (3, 32, 32))])
 def test_param_counts_and_forward_backward(name, n_params, shape):
     net = get_model(name, seed=1)
     lay = net.layout
