@@ -137,3 +137,26 @@ def test_more_participants_than_the_kernel_limit_uses_exact_fallback():
         ops.fused_aggregate(w0, ws, wt, mode, 40, 1.0, out=out, flipped=flipped)
         torch.testing.assert_close(out, ref)
         assert int(flipped) == nflip
+
+
+@settings(max_examples=40, deadline=None)
+@given(K=st.integers(1, 9), splits=st.integers(1, 4), theta=st.integers(0, 9), seed=st.integers(0, 1000), aggr=st.sampled_from(["avg", "sign"]),
+       tail=st.integers(0, 16))
+def test_property_partial_sums_reproduce_the_oracle(K, splits, theta, seed, aggr, tail):
+    """The all-reduce transport's algebra: splitting the participants over any number of ranks, summing their (vote, weighted sum)
+    partials and finishing with aggregate_from_partials equals the oracle on the full list (weights, zeros, RLR, BN-style tail)."""
+    n = 64
+    w0, ws = _mk(K, n, seed, zeros=0.3)
+    wt = [1.0 + (i * 7 % 5) for i in range(K)]
+    ref, nflip = ops.aggregate_oracle(w0, ws, wt, aggr, theta, 0.5, None, n - tail)
+    vote, wsum = torch.zeros(n), torch.zeros(n, dtype=torch.float64)
+    for r in range(splits):
+        mine = list(range(r, K, splits))
+        v, s = ops.aggregate_partials(w0, [ws[j] for j in mine], [wt[j] for j in mine])
+        vote += v
+        wsum += s
+    out, nf = ops.aggregate_from_partials(w0, vote, wsum, sum(wt), aggr, theta, 0.5, None, n - tail)
+    torch.testing.assert_close(out, ref, atol=1e-6, rtol=1e-6)
+    assert nf == nflip
+    with pytest.raises(ValueError):
+        ops.aggregate_from_partials(w0, vote, wsum, sum(wt), "comed", theta, 0.5)
