@@ -54,15 +54,20 @@ class Aggregation:
         weights = [float(self.agent_data_sizes[i]) for i in participants]
         scales = None
         norms = None
-        if self._server_clip or self.args.diagnostics:
+        diag = bool(self.args.diagnostics)
+        if self._server_clip or diag:
             norms = self.fused.update_norms(len(participants))
         if self._server_clip:
             scales = self._clip_scales(norms)
+        if diag:   # the sign-agreement analysis needs the pre-step global parameters and every participant's parameters
+            prev = self.fused.w_global.clone()
+            ws = [w.clone() for w in self.fused.gather_participants(len(participants))]
         self.fused.aggregate(weights, self.args.aggr, self.args.robustLR_threshold, self.server_lr,
                              self.args.noise * self.args.clip, self.args.seed, cur_round, scales)
         self.last_flipped = self.fused.flipped
-        if self.args.diagnostics and norms is not None:
+        if diag:
             self.plot_norms(dict(zip(participants, norms.tolist())), cur_round)
+            self.plot_sign_agreement(prev, self.fused.w_global, ws, participants, cur_round)
 
     @property
     def _server_clip(self):

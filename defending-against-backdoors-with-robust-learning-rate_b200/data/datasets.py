@@ -234,8 +234,8 @@ def get_datasets(data: str, data_dir: str = "../data", synthetic: int = 0, synth
     """Train/validation datasets (reference ``get_datasets``, src/utils.py:95-124), device resident.
 
     Real data is read from ``data_dir`` in torchvision's on-disk layout *without* downloading (the
-    reference downloads, src/utils.py:102-103; there is no network here).  ``synthetic>0`` or missing
-    files -> synthetic data of the same shape.
+    reference downloads, src/utils.py:102-103; there is no network here).  ``synthetic>0`` -> synthetic data of
+    the same shape; missing files raise (no silent substitution).
     """
     if data not in DATASET_META:
         raise ValueError(f"unknown dataset {data!r}")
@@ -248,9 +248,10 @@ def get_datasets(data: str, data_dir: str = "../data", synthetic: int = 0, synth
         return h5_to_device_dataset(tr, device), h5_to_device_dataset(te, device)
     try:
         (xtr, ytr), (xte, yte) = _load_torchvision(data, data_dir)
-    except Exception as e:  # noqa: BLE001 - any failure means "not on disk"
-        meta = DATASET_META[data]
-        print(f"[data] {data} not found under {data_dir!r} ({type(e).__name__}); using synthetic data of the same shape")
-        return make_synthetic(data, meta.n_train, meta.n_val, seed, device)
+    except Exception as e:  # noqa: BLE001
+        # never substitute synthetic data silently: accuracy / poison numbers of a run must not look like real-data results
+        raise FileNotFoundError(
+            f"{data} not readable under data_dir={data_dir!r} ({type(e).__name__}: {e}). There is no download here; put the torchvision "
+            f"on-disk files there or pass --synthetic N (N > 0) to train on synthetic data of the same shape.") from e
     return (DeviceDataset(data, xtr.to(device), ytr.to(device)),
             DeviceDataset(data, xte.to(device), yte.to(device)))

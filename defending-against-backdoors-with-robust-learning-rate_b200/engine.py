@@ -219,9 +219,18 @@ class FLEngine:
         return {"chosen": chosen, "steps": steps, "h2d_bytes": h2d}
 
     def round_result(self):
-        """Device->host read of the round's result: (mean local training loss on this rank, flipped-coordinate count)."""
-        vals = torch.cat([self.round_loss.double(), self.fused.flipped.double()]).cpu()
-        return float(vals[0]), int(vals[1])
+        """Device->host read of the round's result: (summed local training loss on this rank, number of REAL coordinates whose
+        learning rate was flipped this round).  On the fused multi-GPU back-end every rank counts only its own coordinate slice, so
+        the count is all-reduced; the always-zero alignment padding below ``n_vote`` (vote 0 < theta) is taken out, so the count is
+        over ``layout.n_params`` coordinates whatever the transport."""
+        flipped = self.fused.flipped.double()
+        if self.fused.flipped_is_partial:
+            flipped = self.ctx.all_reduce_sum(flipped.clone())
+        vals = torch.cat([self.round_loss.double(), flipped]).cpu()
+        n_flip = int(vals[1])
+        if self.args.robustLR_threshold > 0:
+            n_flip = max(0, n_flip - (self.layout.n_vote - self.layout.n_params))
+        return float(vals[0]), n_flip
 
     # ---- evaluation (src/federated.py:78-92) ---------------------------------------------------------------
     def evaluate(self, rnd: int):
@@ -269,7 +278,7 @@ class FLEngine:
                 rec.update({k: v for k, v in ev.items() if k != "per_class_acc"})
             loss, flipped = self.round_result()
             rec["train_loss"] = loss / max(1, info["steps"])
-            rec["frac_flipped"] = flipped / max(1, self.layout.n_vote)
+            rec["frac_flipped"] = flipped / max(1, self.layout.n_params)
             rec.update({f"ms_{k}": v for k, v in self.timer.elapsed().items()})
             if args.profile_phases and self.verbose:
                 print({k: round(v, 3) for k, v in rec.items() if k.startswith("ms_")})

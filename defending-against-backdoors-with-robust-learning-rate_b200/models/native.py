@@ -30,6 +30,15 @@ from .graph import FlatLayout
 ACT = torch.bfloat16   # default activation / GEMM-operand dtype on GPU (tests may run the plan in fp32 on CPU)
 
 
+def dropout_stream_base(seed: int, agent_id: int, rnd: int) -> int:
+    """First Philox step-counter value of (agent, round): a splitmix64 hash kept below 2^62 so that the per-step increments of
+    one local training run (< 2^20) can neither overflow nor realistically meet another agent's range."""
+    z = (int(seed) * 0x9E3779B97F4A7C15 + (int(agent_id) + 1) * 0xBF58476D1CE4E5B9 + (int(rnd) + 1) * 0x94D049BB133111EB) & (2 ** 64 - 1)
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & (2 ** 64 - 1)
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & (2 ** 64 - 1)
+    return (z ^ (z >> 31)) & (2 ** 62 - 1)
+
+
 def native_supported(layout: FlatLayout) -> bool:
     return all(nd.op in ("conv", "bn", "relu", "maxpool", "avgpool", "flatten", "dropout", "linear", "save", "add")
                for nd in layout.nodes)
@@ -459,6 +468,10 @@ class NativeTrainer:
             full = self._get_graph(dataset, bs, w_global) if n >= bs else None
             tail = self._get_graph(dataset, n % bs, w_global) if n % bs else None
         ops.round_init(w_global, self.w, self.wb, self.m)
+        # dropout Philox stream = (seed, step counter, node): start every (agent, round) at its own counter so agents trained in
+        # the same round -- on different GPUs or one after another -- draw independent masks, as the reference's agents do from
+        # one sequential RNG (src/federated.py:68-72); the captured graphs increment the device counter once per step
+        self.net.step_counter.fill_(dropout_stream_base(args.seed, agent.id, rnd))
         steps = 0
         for ep in range(args.local_ep):
             idx = agent.epoch_indices(args.seed, rnd, ep)

@@ -108,10 +108,12 @@ def build(verbose: bool = False, force: bool = False) -> str:
         with open(os.path.join(OBJ, name + ".log"), "w") as fh:
             fh.write(out)
     if jobs or force or not os.path.exists(TARGET):
-        link = ["g++", "-shared", "-o", TARGET, *objs, f"-L{torch_lib}", "-L/usr/local/cuda/lib64",
+        tmp = TARGET + ".tmp"       # link to a temporary name and rename: a gpurun snapshot taken meanwhile never sees half a file
+        link = ["g++", "-shared", "-o", tmp, *objs, f"-L{torch_lib}", "-L/usr/local/cuda/lib64",
                 "-lc10", "-ltorch_cpu", "-ltorch", "-ltorch_python", "-lc10_cuda", "-ltorch_cuda", "-lcudart",
                 f"-Wl,-rpath,{torch_lib}", "-Wl,-rpath,/usr/local/cuda/lib64"]
         _run(link)
+        os.replace(tmp, TARGET)
         if verbose:
             print(f"[build] linked {TARGET}")
     return TARGET

@@ -62,6 +62,7 @@ class FusedAggregator:
         self.w_bf16 = self.buf.tensor(self.off_wb, n, torch.bfloat16) if self.with_bf16 else None
         self.slots = [self.buf.tensor(self.off_slots + 4 * n * j, n, torch.float32) for j in range(self.max_slots)]
         self.flipped = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.flipped_is_partial = False   # True after a launch in which every rank counted only its own coordinate slice
         self.epoch = 0
         self._tables = {}
         if use_symm:
@@ -102,7 +103,9 @@ class FusedAggregator:
         n_part = len(weights)
         ctx, dev = self.ctx, self.ctx.device
         self.flipped.zero_()
+        self.flipped_is_partial = False
         if self.backend == "fused" and ctx.is_dist and n_part <= ops.MAX_FUSED_AGENTS:
+            self.flipped_is_partial = True
             self.epoch += 1
             wt = torch.as_tensor(weights, dtype=torch.float64).to(dev)
             sc = torch.as_tensor(scales, dtype=torch.float32).to(dev) if scales is not None else None
@@ -148,6 +151,15 @@ class FusedAggregator:
         if self.w_bf16 is not None:
             self.w_bf16.copy_(new.to(torch.bfloat16))
         self.flipped += nflip
+
+    def gather_participants(self, n_part: int):
+        """Every participant's flat parameter vector on THIS rank (list of ``n_part`` tensors; remote slots are copied through an
+        all_gather).  Off the hot path: used by the ``--diagnostics`` analyses and by bench.py's post-run aggregation check."""
+        ctx = self.ctx
+        if not ctx.is_dist:
+            return [self.slots[j] for j in range(n_part)]
+        allp = ctx.all_gather(torch.stack(self.slots, 0))            # [world, max_slots, n]
+        return [allp[j % ctx.world, j // ctx.world] for j in range(n_part)]
 
     def update_norms(self, n_part: int):
         """||w_j - w_global|| for every participant (float64 [n_part]), computed where the slot lives."""

@@ -18,6 +18,10 @@ from . import ops
 from .models.graph import GraphNet
 
 
+def _agent_round_seed(seed: int, agent_id: int, rnd: int) -> int:
+    return (int(seed) * 1_000_003 + (int(agent_id) + 1) * 7_919 + int(rnd) * 104_729) % (2 ** 63 - 1)
+
+
 class TorchTrainer:
     name = "torch"
 
@@ -98,6 +102,9 @@ class TorchTrainer:
             full = self._get_graph(dataset, bs, w_global) if n >= bs else None
             tail = self._get_graph(dataset, n % bs, w_global) if n % bs else None
         ops.round_init(w_global, self.w, None, self.m)
+        # independent dropout masks per (agent, round): the reference draws them from one sequential RNG (src/federated.py:68-72);
+        # here agents of a round run on different ranks that were all seeded alike at start-up
+        torch.manual_seed(_agent_round_seed(args.seed, agent.id, rnd))
         for ep in range(args.local_ep):
             idx = agent.epoch_indices(args.seed, rnd, ep)
             if graphs:

@@ -37,7 +37,8 @@ def test_local_step_matches_reference_agent_math():
     params = [p for p in net.parameters()]
     opt = torch.optim.SGD(params, lr=0.1, momentum=0.9)
     net.train()
-    torch.manual_seed(11)
+    from rlr_b200.trainers import _agent_round_seed
+    torch.manual_seed(_agent_round_seed(eng.args.seed, agent.id, 1))     # train_agent seeds the dropout stream per (agent, round)
     idx = agent.epoch_indices(eng.args.seed, 1, 0)
     for s in range(0, agent.n_data, 32):
         x, y = agent.dataset.batch(idx[s:s + 32])
