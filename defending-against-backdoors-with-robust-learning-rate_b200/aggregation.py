@@ -36,7 +36,8 @@ class Aggregation:
         ids = list(agent_params.keys())
         ws = [agent_params[i] for i in ids]
         weights = [float(self.agent_data_sizes[i]) for i in ids]
-        scales = self._clip_scales(ops.update_norms(w_global, ws)) if self._server_clip else None
+        nv = n_vote if n_vote is not None else (self.layout.n_vote if self.layout else None)
+        scales = self._clip_scales(ops.update_norms(w_global, ws, nv)) if self._server_clip else None
         prev = w_global.clone() if self.args.diagnostics else None
         flipped = torch.zeros(1, dtype=torch.int64, device=w_global.device)
         ops.fused_aggregate(w_global, ws, weights, self.args.aggr, self.args.robustLR_threshold, self.server_lr,
@@ -45,7 +46,7 @@ class Aggregation:
                             scales, out=w_global, flipped=flipped)
         self.last_flipped = flipped
         if self.args.diagnostics:
-            self.plot_norms(dict(zip(ids, ops.update_norms(prev, ws).tolist())), cur_round)
+            self.plot_norms(dict(zip(ids, ops.update_norms(prev, ws, nv).tolist())), cur_round)
             self.plot_sign_agreement(prev, w_global, ws, ids, cur_round)
         return
 

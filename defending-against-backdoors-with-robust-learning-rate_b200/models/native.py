@@ -261,22 +261,34 @@ class NativeNet:
     def forward(self, x_nhwc, train: bool):
         """``x_nhwc``: [B,H,W,C] bf16 (channels of the first conv, un-padded).  Returns fp32 logits [B,classes]."""
         B = x_nhwc.shape[0]
+        out = self.forward_raw(x_nhwc, train)
+        self.logits[:B].copy_(out)
+        return self.logits[:B]
+
+    def forward_raw(self, x_nhwc, train: bool):
+        """Forward pass; returns the head's output [B,classes] in the activation dtype, in place in its activation buffer (the
+        training step hands it straight to the loss kernel -- no fp32 staging copy)."""
+        B = x_nhwc.shape[0]
         self._x, self._B, self._train = x_nhwc, B, train
         self._epoch = getattr(self, "_epoch", 0) + 1     # forward-pass id: lets stride-2 convs share their parity-split input copy
         if train:
-            self.stats_arena.zero_()
+            ops.zero_(self.stats_arena)
         for op in self.plan:
             getattr(self, "_fwd_" + op.kind)(op, B, train)
-        out = self.T(self.out_tid, B)
-        self.logits[:B].copy_(out.reshape(B, -1))
-        return self.logits[:B]
+        return self.T(self.out_tid, B).reshape(B, -1)
+
+    def dlogits_buffer(self, B):
+        """Gradient buffer of the head's output ([B,classes], activation dtype): the loss kernel writes into it directly."""
+        return self.G(self.out_tid, B).reshape(B, -1)
 
     def backward(self, dlogits):
         """``dlogits`` [B,classes] (already scaled by 1/B).  Fills the flat gradient buffer."""
         B = dlogits.shape[0]
-        self.G(self.out_tid, B).copy_(dlogits.reshape(self.G(self.out_tid, B).shape))
-        self.g.zero_()           # tcgen05 weight gradients are split-K reductions (red.add) into the flat buffer
-        self.dsum_arena.zero_()
+        gout = self.G(self.out_tid, B)
+        if dlogits.data_ptr() != gout.data_ptr():
+            gout.copy_(dlogits.reshape(gout.shape))
+        ops.zero_(self.g)        # tcgen05 weight gradients are split-K reductions (red.add) into the flat buffer
+        ops.zero_(self.dsum_arena)
         for op in reversed(self.plan):
             getattr(self, "_bwd_" + op.kind)(op, B)
 
@@ -291,6 +303,8 @@ class NativeNet:
         if self.impl["conv_fwd"] == "sm100" and ops.conv_supported(op.in_shape, a, "fwd"):
             ops.conv2d_fwd_sm100(x, self.pwb[op.name + ".weight"], bias, y, a.get("stride", 1), a.get("pad", 0), op.relu, stats, tag=(id(self), op.name), zero_stats=False, s2d_epoch=self._epoch)
             return
+        if self.impl["conv_fwd"] == "sm100":
+            ops.note_fallback("conv_fwd", f"{op.name} in={op.in_shape} {a}")
         wt = self.pwb[op.name + ".weight"].permute(0, 3, 1, 2)
         out = F.conv2d(x.permute(0, 3, 1, 2), wt, bias.to(self.act_dtype) if bias is not None else None, a.get("stride", 1), a.get("pad", 0))
         if op.relu:
@@ -311,6 +325,8 @@ class NativeNet:
         if self.impl["conv_wgrad"] == "sm100" and ops.conv_supported(op.in_shape, a, "wgrad"):
             ops.conv2d_wgrad_sm100(x, dy, gw, gb, s, p, tag=(id(self), op.name), zero=False)
         else:
+            if self.impl["conv_wgrad"] == "sm100":
+                ops.note_fallback("conv_wgrad", f"{op.name} in={op.in_shape} {a}")
             _, dw, db = torch.ops.aten.convolution_backward(
                 dy.permute(0, 3, 1, 2), x.permute(0, 3, 1, 2), self.pwb[name].permute(0, 3, 1, 2),
                 [a["cout"]] if gb is not None else None, [s, s], [p, p], [1, 1], False, [0, 0], 1, [False, True, gb is not None])
@@ -323,6 +339,8 @@ class NativeNet:
         if self.impl["conv_dgrad"] == "sm100" and ops.conv_supported(op.in_shape, a, "dgrad"):
             ops.conv2d_dgrad_sm100(dy, self.pwb[name], dx, s, p, op.acc_dx)
             return
+        if self.impl["conv_dgrad"] == "sm100":
+            ops.note_fallback("conv_dgrad", f"{op.name} in={op.in_shape} {a}")
         di, _, _ = torch.ops.aten.convolution_backward(
             dy.permute(0, 3, 1, 2), x.permute(0, 3, 1, 2), self.pwb[name].permute(0, 3, 1, 2), None, [s, s], [p, p], [1, 1],
             False, [0, 0], 1, [True, False, False])
@@ -411,7 +429,7 @@ class NativeTrainer:
         self.bs = args.bs
         self.net = NativeNet(layout, device, self.bs, impl, seed=args.seed)
         self.net.bind(self.w, self.wb, self.g)
-        self.opt = ops.FlatSGD(n, device, args.client_lr, args.client_moment, 10.0, args.clip)
+        self.opt = ops.FlatSGD(n, device, args.client_lr, args.client_moment, 10.0, args.clip, n_pgd=layout.n_vote)
         self.loss_sum = torch.zeros(1, dtype=torch.float32, device=device)
         self.use_graphs = not args.no_graphs
         self.max_shard = max_shard
@@ -427,12 +445,11 @@ class NativeTrainer:
         meta = dataset.meta
         ops.gather_normalize(dataset.data, self.perm, meta.mean, meta.std, out=self.x[:B], nhwc=True, cursor=self.cursor,
                              targets=dataset.targets, out_labels=self.y, batch=B)
-        ops.ext().advance_cursor(self.cursor, B)
-        logits = self.net.forward(self.x[:B], True)
-        _, dl = ops.softmax_xent(logits, self.y[:B], True, self.loss_sum)
+        logits = self.net.forward_raw(self.x[:B], True)                       # bf16 [B,classes], in the head's activation buffer
+        _, dl = ops.softmax_xent(logits, self.y[:B], True, self.loss_sum, dlogits=self.net.dlogits_buffer(B))
         self.net.backward(dl)
         self.opt.step(self.w, self.g, self.m, w0=w0, w_bf16=self.wb)
-        self.net.step_counter += 1
+        ops.ext().advance_cursor(self.cursor, B, self.net.step_counter)       # next batch; next Philox step for the dropout masks
 
     def _get_graph(self, dataset, B, w0):
         key = (B, dataset.data.data_ptr(), w0.data_ptr())

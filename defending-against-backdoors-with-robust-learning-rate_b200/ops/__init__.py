@@ -55,6 +55,37 @@ def launch_calls() -> int:
     return _Counter.calls
 
 
+# ---- library fall-throughs ---------------------------------------------------------------------------------------------
+# The sm100 back-end of a layer primitive may meet a shape no kernel of ours covers and fall through to a PyTorch library call
+# (cuBLAS / cuDNN / ATen).  Every such fall-through is recorded here by call site; ``RLR_STRICT=1`` turns it into an error.  The
+# bench prints the counters (``library_fallbacks``) and tests/test_gpu_native.py asserts they stay empty for every zoo model.
+_fallbacks: dict = {}
+
+
+def note_fallback(site: str, detail: str = ""):
+    _fallbacks[site] = _fallbacks.get(site, 0) + 1
+    if os.environ.get("RLR_STRICT", "0") == "1":
+        raise RuntimeError(f"RLR_STRICT=1: sm100 back-end fell through to a library call at {site} {detail}")
+
+
+def fallback_calls() -> dict:
+    """{call site: count} of library fall-throughs of the sm100 back-end since the last reset (empty = none)."""
+    return dict(_fallbacks)
+
+
+def reset_fallbacks():
+    _fallbacks.clear()
+
+
+def zero_(t):
+    """Zero a tensor: a memset node on CUDA (no ATen fill kernel inside captured steps), ``zero_()`` on CPU."""
+    if t.is_cuda and t.is_contiguous():
+        ext().memset_zero(t)
+    else:
+        t.zero_()
+    return t
+
+
 def native_available() -> bool:
     """True if the compiled extension can be imported (it may still be unusable without a GPU)."""
     try:
@@ -298,15 +329,17 @@ def fused_aggregate(w_global, w_agents, weights, mode="avg", theta=0, server_lr=
     return out
 
 
-def update_norms(w_global, w_agents):
+def update_norms(w_global, w_agents, n=None):
     """L2 norms of the agents' updates ``||w_k - w_global||`` (server clipping, src/aggregation.py:77-81, and the
-    Norms/* diagnostic, :83-100) -> float64 tensor [K]."""
+    Norms/* diagnostic, :83-100) -> float64 tensor [K].  ``n``: only the first ``n`` coordinates count (the model parameters:
+    BatchNorm running statistics stored behind ``n_vote`` are not part of the reference's parameter vector)."""
+    n = w_global.numel() if n is None else int(n)
     if not w_global.is_cuda:
-        return torch.stack([(w.double() - w_global.double()).norm() for w in w_agents])
+        return torch.stack([(w[:n].double() - w_global[:n].double()).norm() for w in w_agents])
     dev = w_global.device
     tab = PtrTable([w.data_ptr() for w in w_agents], dev, w_agents)
     out = torch.zeros(len(w_agents), dtype=torch.float64, device=dev)
-    ext().update_sqnorm(tab.tensor, w_global.data_ptr(), w_global.numel(), out)
+    ext().update_sqnorm(tab.tensor, w_global.data_ptr(), n, out)
     return out.sqrt()
 
 
@@ -334,30 +367,34 @@ class FlatSGD:
     for ``max(1, norm/clip)``); the whole step is 2 kernels (+2 with PGD) regardless of the number of tensors.
     """
 
-    def __init__(self, n, device, lr, momentum, max_grad_norm=10.0, pgd_clip=0.0):
+    def __init__(self, n, device, lr, momentum, max_grad_norm=10.0, pgd_clip=0.0, n_pgd=None):
         self.lr, self.momentum, self.max_grad_norm, self.pgd_clip = float(lr), float(momentum), float(max_grad_norm), float(pgd_clip)
+        # the PGD ball is measured and projected over the model parameters [0, n_pgd) only (layout.n_vote): BatchNorm running
+        # statistics behind them are not in the reference's parameters_to_vector() (src/agent.py:54-60)
+        self.n_pgd = int(n if n_pgd is None else n_pgd)
         self.norms = torch.zeros(2, dtype=torch.float64, device=device)  # [||g||^2, ||w-w0||^2]
 
     def step(self, w, g, m, w0=None, w_bf16=None):
         if w.is_cuda:
             e = ext()
-            self.norms.zero_()
+            e.memset_zero(self.norms)
             e.sqnorm(g, self.norms[0:1])
             pgd = self.pgd_clip > 0
             e.sgd_step(w, g, m, w0 if pgd else None, w_bf16, self.lr, self.momentum, self.max_grad_norm,
-                       self.norms[0:1], self.norms[1:2] if pgd else None)
+                       self.norms[0:1], self.norms[1:2] if pgd else None, self.n_pgd)
             if pgd:
-                e.pgd_project(w, w0, w_bf16, self.pgd_clip, self.norms[1:2])
+                e.pgd_project(w, w0, w_bf16, self.pgd_clip, self.norms[1:2], self.n_pgd)
             return
         gn = g.double().norm()
         coef = min(1.0, self.max_grad_norm / (float(gn) + 1e-6)) if self.max_grad_norm > 0 else 1.0
         m.mul_(self.momentum).add_(g, alpha=coef)
         w.add_(m, alpha=-self.lr)
         if self.pgd_clip > 0:
-            d = w - w0
+            k = self.n_pgd
+            d = w[:k] - w0[:k]
             denom = max(1.0, float(d.double().norm()) / self.pgd_clip)
             if denom > 1.0:
-                w.copy_(w0 + d / denom)
+                w[:k].copy_(w0[:k] + d / denom)
         if w_bf16 is not None:
             w_bf16.copy_(w.to(torch.bfloat16))
 
@@ -365,12 +402,13 @@ class FlatSGD:
 # =====================================================================================================================
 # loss / evaluation
 # =====================================================================================================================
-def softmax_xent(logits, labels, want_grad=True, loss_sum=None, correct=None):
+def softmax_xent(logits, labels, want_grad=True, loss_sum=None, correct=None, dlogits=None):
     """Fused softmax cross-entropy (mean reduction) forward + backward: returns ``(loss_sum_tensor, dlogits)`` where
-    ``dlogits = (softmax - onehot) / B``."""
+    ``dlogits = (softmax - onehot) / B``.  ``dlogits``: optional pre-allocated output of the logits' dtype and
+    shape (the native executor passes its gradient buffer, so the loss kernel writes the head's gradient in place)."""
     B = logits.shape[0]
     if logits.is_cuda:
-        dl = torch.empty_like(logits) if want_grad else None
+        dl = (dlogits if dlogits is not None else torch.empty_like(logits)) if want_grad else None
         if loss_sum is None:
             loss_sum = torch.zeros(1, dtype=torch.float32, device=logits.device)
         ext().softmax_xent(logits.contiguous(), labels, dl, loss_sum, correct, 1.0 / B)
@@ -382,6 +420,9 @@ def softmax_xent(logits, labels, want_grad=True, loss_sum=None, correct=None):
     if want_grad:
         dl = (lsm.exp() - torch.nn.functional.one_hot(labels, lf.shape[1]).float()) / B
         dl = dl.to(logits.dtype)
+        if dlogits is not None:
+            dlogits.copy_(dl)
+            dl = dlogits
     if loss_sum is None:
         loss_sum = torch.zeros(1)
     loss_sum += loss

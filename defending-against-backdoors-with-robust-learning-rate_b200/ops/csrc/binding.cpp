@@ -103,11 +103,38 @@ void stamp_pixels(at::Tensor data, at::Tensor sel, at::Tensor rows, at::Tensor c
                                    data.size(3), (int)mode, cur_stream()), "stamp_pixels");
 }
 
-void advance_cursor(at::Tensor cursor, int64_t delta) {
+void advance_cursor(at::Tensor cursor, int64_t delta, c10::optional<at::Tensor> step) {
     CHECK_CUDA(cursor);
     TORCH_CHECK(cursor.scalar_type() == at::kInt);
+    TORCH_CHECK(!(step.has_value() && step->defined()) || step->scalar_type() == at::kLong, "step counter must be int64");
     c10::cuda::CUDAGuard guard(cursor.device());
-    check(rlr::launch_advance_cursor(cursor.data_ptr<int>(), (int)delta, cur_stream()), "advance_cursor");
+    check(rlr::launch_advance_cursor(cursor.data_ptr<int>(), (int)delta, reinterpret_cast<long long*>(ptr_or_null<int64_t>(step)),
+                                     cur_stream()), "advance_cursor");
+}
+
+// zero a contiguous tensor with a memset node on the current stream (no fill kernel inside captured steps)
+void memset_zero(at::Tensor t) {
+    CHECK_CUDA(t);
+    c10::cuda::CUDAGuard guard(t.device());
+    check(cudaMemsetAsync(t.data_ptr(), 0, (size_t)t.numel() * t.element_size(), cur_stream()), "memset_zero");
+}
+
+void pad_rows(at::Tensor src, at::Tensor dst) {
+    CHECK_CUDA(src); CHECK_CUDA(dst);
+    TORCH_CHECK(src.scalar_type() == at::kBFloat16 && dst.scalar_type() == at::kBFloat16 && src.dim() == 2 && dst.dim() == 2 &&
+                src.size(0) == dst.size(0), "pad_rows: bf16 [R,K] -> [R,Kp]");
+    c10::cuda::CUDAGuard guard(src.device());
+    check(rlr::launch_pad_rows(reinterpret_cast<const __nv_bfloat16*>(src.data_ptr()), reinterpret_cast<__nv_bfloat16*>(dst.data_ptr()),
+                               src.size(0), (int)src.size(1), (int)dst.size(1), num_sms(), cur_stream()), "pad_rows");
+}
+
+void unpad_add(at::Tensor src, at::Tensor dst) {
+    CHECK_CUDA(src); CHECK_CUDA(dst);
+    TORCH_CHECK(src.scalar_type() == at::kFloat && dst.scalar_type() == at::kFloat && src.dim() == 2 && dst.dim() == 2 &&
+                src.size(0) == dst.size(0), "unpad_add: fp32 [R,Kp] -> [R,K]");
+    c10::cuda::CUDAGuard guard(src.device());
+    check(rlr::launch_unpad_add(src.data_ptr<float>(), dst.data_ptr<float>(), src.size(0), (int)dst.size(1), (int)src.size(1), num_sms(),
+                                cur_stream()), "unpad_add");
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -128,7 +155,7 @@ void sqnorm(at::Tensor x, at::Tensor out) {
 
 void sgd_step(at::Tensor w, at::Tensor g, at::Tensor m, c10::optional<at::Tensor> w0, c10::optional<at::Tensor> w_bf16,
               double lr, double momentum, double max_grad_norm, c10::optional<at::Tensor> g_sqnorm,
-              c10::optional<at::Tensor> d_sqnorm) {
+              c10::optional<at::Tensor> d_sqnorm, int64_t n_pgd) {
     CHECK_CUDA(w); CHECK_CUDA(g); CHECK_CUDA(m);
     TORCH_CHECK(w.numel() == g.numel() && w.numel() == m.numel());
     TORCH_CHECK(!(d_sqnorm.has_value() && d_sqnorm->defined()) || (w0.has_value() && w0->defined()), "PGD needs w0");
@@ -136,14 +163,14 @@ void sgd_step(at::Tensor w, at::Tensor g, at::Tensor m, c10::optional<at::Tensor
     check(rlr::launch_sgd_step(w.data_ptr<float>(), g.data_ptr<float>(), m.data_ptr<float>(), ptr_or_null<const float>(w0),
                                ptr_or_null<__nv_bfloat16>(w_bf16), w.numel(), (float)lr, (float)momentum,
                                (float)max_grad_norm, ptr_or_null<const double>(g_sqnorm), ptr_or_null<double>(d_sqnorm),
-                               num_sms(), cur_stream()), "sgd_step");
+                               num_sms(), cur_stream(), n_pgd), "sgd_step");
 }
 
-void pgd_project(at::Tensor w, at::Tensor w0, c10::optional<at::Tensor> w_bf16, double clip, at::Tensor d_sqnorm) {
+void pgd_project(at::Tensor w, at::Tensor w0, c10::optional<at::Tensor> w_bf16, double clip, at::Tensor d_sqnorm, int64_t n_pgd) {
     CHECK_CUDA(w); CHECK_CUDA(w0); CHECK_CUDA(d_sqnorm);
     c10::cuda::CUDAGuard guard(w.device());
     check(rlr::launch_pgd_project(w.data_ptr<float>(), w0.data_ptr<float>(), ptr_or_null<__nv_bfloat16>(w_bf16), w.numel(),
-                                  (float)clip, d_sqnorm.data_ptr<double>(), num_sms(), cur_stream()), "pgd_project");
+                                  (float)clip, d_sqnorm.data_ptr<double>(), num_sms(), cur_stream(), n_pgd), "pgd_project");
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -210,11 +237,16 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("update_sqnorm", &update_sqnorm);
     m.def("gather_normalize", &gather_normalize);
     m.def("stamp_pixels", &stamp_pixels);
-    m.def("advance_cursor", &advance_cursor);
+    m.def("advance_cursor", &advance_cursor, py::arg("cursor"), py::arg("delta"), py::arg("step") = py::none());
+    m.def("memset_zero", &memset_zero);
+    m.def("pad_rows", &pad_rows);
+    m.def("unpad_add", &unpad_add);
     m.def("round_init", &round_init);
     m.def("sqnorm", &sqnorm);
-    m.def("sgd_step", &sgd_step);
-    m.def("pgd_project", &pgd_project);
+    m.def("sgd_step", &sgd_step, py::arg("w"), py::arg("g"), py::arg("m"), py::arg("w0"), py::arg("w_bf16"), py::arg("lr"),
+          py::arg("momentum"), py::arg("max_grad_norm"), py::arg("g_sqnorm"), py::arg("d_sqnorm"), py::arg("n_pgd") = 0);
+    m.def("pgd_project", &pgd_project, py::arg("w"), py::arg("w0"), py::arg("w_bf16"), py::arg("clip"), py::arg("d_sqnorm"),
+          py::arg("n_pgd") = 0);
     m.def("softmax_xent", &softmax_xent);
     m.def("eval_metrics", &eval_metrics);
     m.def("ipc_alloc", &ipc_alloc);

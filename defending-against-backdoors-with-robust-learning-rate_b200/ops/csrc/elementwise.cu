@@ -62,9 +62,50 @@ cudaError_t launch_gather_normalize(const void* data, int in_is_float, const int
     return cudaGetLastError();
 }
 
-__global__ void advance_cursor_kernel(int* cursor, int delta) { *cursor += delta; }
-cudaError_t launch_advance_cursor(int* cursor, int delta, cudaStream_t st) {
-    advance_cursor_kernel<<<1, 1, 0, st>>>(cursor, delta);
+// end of a local step: the batch cursor moves on and (optionally) the Philox step counter of the dropout masks is bumped --
+// one single-thread node instead of a torch `+= 1` inside the captured step
+__global__ void advance_cursor_kernel(int* cursor, int delta, long long* step) {
+    *cursor += delta;
+    if (step) *step += 1;
+}
+cudaError_t launch_advance_cursor(int* cursor, int delta, long long* step, cudaStream_t st) {
+    advance_cursor_kernel<<<1, 1, 0, st>>>(cursor, delta, step);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// row padding for tiny-K operands: dst[r][0..Kp) = src[r][0..K) followed by zeros (bf16).  Used for the stem conv's channel-
+// padded input / filter and the im2col filter matrix ([Cout][k*k*Cin] -> [Cout][64]); the inverse adds the valid columns of an
+// fp32 [R][Kp] gradient into the [R][K] slice of the flat gradient.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pad_rows_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                         long long R, int K, int Kp) {
+    const long long n = R * Kp;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / Kp;
+        const int c = (int)(i - r * Kp);
+        dst[i] = c < K ? src[r * K + c] : __float2bfloat16(0.f);
+    }
+}
+cudaError_t launch_pad_rows(const __nv_bfloat16* src, __nv_bfloat16* dst, long long R, int K, int Kp, int num_sms, cudaStream_t st) {
+    if (K > Kp || R <= 0) return cudaErrorInvalidValue;
+    const long long want = (R * Kp + 255) / 256;
+    const int grid = (int)(want > (long long)num_sms * 8 ? (long long)num_sms * 8 : want);
+    pad_rows_kernel<<<grid, 256, 0, st>>>(src, dst, R, K, Kp);
+    return cudaGetLastError();
+}
+__global__ void __launch_bounds__(256) unpad_add_kernel(const float* __restrict__ src, float* __restrict__ dst, long long R, int K, int Kp) {
+    const long long n = R * K;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / K;
+        dst[i] += src[r * Kp + (i - r * K)];
+    }
+}
+cudaError_t launch_unpad_add(const float* src, float* dst, long long R, int K, int Kp, int num_sms, cudaStream_t st) {
+    if (K > Kp || R <= 0) return cudaErrorInvalidValue;
+    const long long want = (R * K + 255) / 256;
+    const int grid = (int)(want > (long long)num_sms * 8 ? (long long)num_sms * 8 : want);
+    unpad_add_kernel<<<grid, 256, 0, st>>>(src, dst, R, K, Kp);
     return cudaGetLastError();
 }
 
@@ -148,7 +189,7 @@ __global__ void __launch_bounds__(256) sgd_step_kernel(float* __restrict__ w, co
                                                          float* __restrict__ m, const float* __restrict__ w0,
                                                          __nv_bfloat16* __restrict__ wb, long long n4, float lr,
                                                          float momentum, float max_grad_norm,
-                                                         const double* __restrict__ g_sqnorm, double* d_sqnorm) {
+                                                         const double* __restrict__ g_sqnorm, double* d_sqnorm, long long n4_pgd) {
     __shared__ double scratch[32];
     float coef = 1.0f;
     if (max_grad_norm > 0.f && g_sqnorm) {
@@ -165,9 +206,13 @@ __global__ void __launch_bounds__(256) sgd_step_kernel(float* __restrict__ w, co
         st_f4(m + 4 * q, mn);
         st_f4(w + 4 * q, wn);
         if (d_sqnorm) {
-            const float4 o = ld_f4(w0 + 4 * q);
-            const float d0 = wn.x - o.x, d1 = wn.y - o.y, d2 = wn.z - o.z, d3 = wn.w - o.w;
-            dacc += (double)(d0 * d0 + d1 * d1) + (double)(d2 * d2 + d3 * d3);
+            // PGD radius is measured over the model parameters only ([0, n_pgd): the reference projects parameters_to_vector(),
+            // src/agent.py:54-60); BatchNorm running statistics stored behind them never count and are never rescaled
+            if (q < n4_pgd) {
+                const float4 o = ld_f4(w0 + 4 * q);
+                const float d0 = wn.x - o.x, d1 = wn.y - o.y, d2 = wn.z - o.z, d3 = wn.w - o.w;
+                dacc += (double)(d0 * d0 + d1 * d1) + (double)(d2 * d2 + d3 * d3);
+            }
         } else if (wb) {
             *reinterpret_cast<uint2*>(wb + 4 * q) = make_uint2(pack_bf16x2(wn.x, wn.y), pack_bf16x2(wn.z, wn.w));
         }
@@ -179,22 +224,23 @@ __global__ void __launch_bounds__(256) sgd_step_kernel(float* __restrict__ w, co
 }
 cudaError_t launch_sgd_step(float* w, const float* g, float* m, const float* w0, __nv_bfloat16* w_bf16, long long n,
                             float lr, float momentum, float max_grad_norm, const double* g_sqnorm, double* d_sqnorm,
-                            int num_sms, cudaStream_t st) {
-    if (n & 3) return cudaErrorInvalidValue;
+                            int num_sms, cudaStream_t st, long long n_pgd) {
+    if ((n & 3) || (n_pgd & 3)) return cudaErrorInvalidValue;
+    if (n_pgd <= 0 || n_pgd > n) n_pgd = n;
     sgd_step_kernel<<<grid_for(n / 4, 256, num_sms, 4), 256, 0, st>>>(w, g, m, w0, w_bf16, n / 4, lr, momentum,
-                                                                       max_grad_norm, g_sqnorm, d_sqnorm);
+                                                                       max_grad_norm, g_sqnorm, d_sqnorm, n_pgd / 4);
     return cudaGetLastError();
 }
 
 // PGD: w <- w0 + (w - w0) / max(1, ||w - w0|| / clip)   (src/agent.py:54-60), no host sync for the norm
 __global__ void __launch_bounds__(256) pgd_project_kernel(float* __restrict__ w, const float* __restrict__ w0,
                                                             __nv_bfloat16* __restrict__ wb, long long n4, float clip,
-                                                            const double* __restrict__ d_sqnorm) {
+                                                            const double* __restrict__ d_sqnorm, long long n4_pgd) {
     const float denom = fmaxf(1.0f, (float)sqrt(*d_sqnorm) / clip);
     const float inv = 1.0f / denom;
     for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (long long)gridDim.x * blockDim.x) {
         float4 wv = ld_f4(w + 4 * q);
-        if (denom > 1.0f) {
+        if (denom > 1.0f && q < n4_pgd) {
             const float4 o = ld_f4(w0 + 4 * q);
             wv.x = o.x + (wv.x - o.x) * inv; wv.y = o.y + (wv.y - o.y) * inv;
             wv.z = o.z + (wv.z - o.z) * inv; wv.w = o.w + (wv.w - o.w) * inv;
@@ -204,9 +250,10 @@ __global__ void __launch_bounds__(256) pgd_project_kernel(float* __restrict__ w,
     }
 }
 cudaError_t launch_pgd_project(float* w, const float* w0, __nv_bfloat16* w_bf16, long long n, float clip,
-                               const double* d_sqnorm, int num_sms, cudaStream_t st) {
-    if (n & 3) return cudaErrorInvalidValue;
-    pgd_project_kernel<<<grid_for(n / 4, 256, num_sms, 4), 256, 0, st>>>(w, w0, w_bf16, n / 4, clip, d_sqnorm);
+                               const double* d_sqnorm, int num_sms, cudaStream_t st, long long n_pgd) {
+    if ((n & 3) || (n_pgd & 3)) return cudaErrorInvalidValue;
+    if (n_pgd <= 0 || n_pgd > n) n_pgd = n;
+    pgd_project_kernel<<<grid_for(n / 4, 256, num_sms, 4), 256, 0, st>>>(w, w0, w_bf16, n / 4, clip, d_sqnorm, n_pgd / 4);
     return cudaGetLastError();
 }
 

@@ -70,7 +70,9 @@ cudaError_t launch_linear_wgrad_bf16(const void* dy, const void* x, float* dW, i
 
 // ---- norm.cu: NHWC bf16 layer kernels -----------------------------------------------------------------------------
 // per-channel sum / sum of squares of x[M][C]
-cudaError_t launch_channel_stats(const __nv_bfloat16* x, long long M, int C, float* stats /*[2][C], accumulates*/, int num_sms, cudaStream_t st);
+// only_sum: accumulate just sum x into stats[0..C) (bias gradients written straight into the flat gradient)
+cudaError_t launch_channel_stats(const __nv_bfloat16* x, long long M, int C, float* stats /*[2][C], accumulates*/, int num_sms, cudaStream_t st,
+                                 int only_sum = 0);
 // finalize statistics: mean/rstd (+ running stats update with momentum, unbiased variance)
 cudaError_t launch_bn_finalize(const float* stats, int slots, float* mean_rstd, float* running_mean, float* running_var, int C,
                                float count, float eps, float momentum, int train, cudaStream_t st);

@@ -156,6 +156,13 @@ void channel_stats(at::Tensor x, at::Tensor stats) {
     const int C = x.size(-1);
     check(rlr::launch_channel_stats(bf(x), x.numel() / C, C, f32(stats), num_sms(), cur_stream()), "channel_stats");
 }
+// bias gradient: db[C] += sum over rows of dy[M][C]  (db is a slice of the flat fp32 gradient, zero or partially accumulated on entry)
+void bias_grad(at::Tensor dy, at::Tensor db) {
+    c10::cuda::CUDAGuard g(dy.device());
+    const int C = dy.size(-1);
+    TORCH_CHECK(db.numel() == C && db.scalar_type() == at::kFloat && dy.is_contiguous(), "bias_grad: db must be fp32 [C]");
+    check(rlr::launch_channel_stats(bf(dy), dy.numel() / C, C, f32(db), num_sms(), cur_stream(), 1), "bias_grad");
+}
 void bn_finalize(at::Tensor stats, at::Tensor mean_rstd, at::Tensor rm, at::Tensor rv, double count, double eps, double momentum, bool train) {
     c10::cuda::CUDAGuard g(stats.device());
     const int C = mean_rstd.size(-1);
@@ -300,6 +307,7 @@ void register_gemm_bindings(py::module_& m) {
     m.def("linear_wgrad_bf16", &linear_wgrad_bf16);
     m.def("conv_wgrad_halo_bf16", &conv_wgrad_halo_bf16);
     m.def("channel_stats", &channel_stats);
+    m.def("bias_grad", &bias_grad);
     m.def("bn_finalize", &bn_finalize);
     m.def("bn_apply", &bn_apply);
     m.def("bn_bwd", &bn_bwd);

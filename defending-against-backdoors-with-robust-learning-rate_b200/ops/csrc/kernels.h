@@ -43,7 +43,10 @@ cudaError_t launch_gather_normalize(const void* data, int in_is_float, const int
                                     cudaStream_t st);
 cudaError_t launch_stamp_pixels(void* data, int is_float, const int64_t* sel, int S, const int* rows, const int* cols,
                                 const float* vals, int P, int H, int W, int C, int mode, cudaStream_t st);
-cudaError_t launch_advance_cursor(int* cursor, int delta, cudaStream_t st);
+cudaError_t launch_advance_cursor(int* cursor, int delta, long long* step /*optional: += 1*/, cudaStream_t st);
+// dst[R][Kp] (bf16) = src[R][K] zero-padded along the row | dst[R][K] (fp32) += src[R][Kp][:K]
+cudaError_t launch_pad_rows(const __nv_bfloat16* src, __nv_bfloat16* dst, long long R, int K, int Kp, int num_sms, cudaStream_t st);
+cudaError_t launch_unpad_add(const float* src, float* dst, long long R, int K, int Kp, int num_sms, cudaStream_t st);
 
 // ---- optimiser over flat buffers -------------------------------------------------------------------------
 cudaError_t launch_round_init(const float* w_global, float* w_local, __nv_bfloat16* w_bf16, float* mom, long long n,
@@ -51,9 +54,9 @@ cudaError_t launch_round_init(const float* w_global, float* w_local, __nv_bfloat
 cudaError_t launch_sqnorm(const float* x, long long n, double* out /*accumulates*/, int num_sms, cudaStream_t st);
 cudaError_t launch_sgd_step(float* w, const float* g, float* m, const float* w0, __nv_bfloat16* w_bf16, long long n,
                             float lr, float momentum, float max_grad_norm, const double* g_sqnorm, double* d_sqnorm,
-                            int num_sms, cudaStream_t st);
+                            int num_sms, cudaStream_t st, long long n_pgd = 0 /*PGD norm over [0, n_pgd); 0 = n*/);
 cudaError_t launch_pgd_project(float* w, const float* w0, __nv_bfloat16* w_bf16, long long n, float clip,
-                               const double* d_sqnorm, int num_sms, cudaStream_t st);
+                               const double* d_sqnorm, int num_sms, cudaStream_t st, long long n_pgd = 0);
 
 // ---- loss / evaluation -----------------------------------------------------------------------------------
 // logits [B,C] (kind 0 fp32 / 1 bf16); writes dlogits (same kind, scaled by 1/B) and accumulates loss_sum / correct.

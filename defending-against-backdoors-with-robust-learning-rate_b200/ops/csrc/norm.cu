@@ -38,7 +38,8 @@ template <int MODE, bool kRecompute = false>
 __global__ void __launch_bounds__(256, MODE == 0 ? 4 : 3) channel_reduce_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
                                                                const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean_rstd,
                                                                float* out, long long M, int C, int relu,
-                                                               const float* __restrict__ gamma = nullptr, const float* __restrict__ beta = nullptr) {
+                                                               const float* __restrict__ gamma = nullptr, const float* __restrict__ beta = nullptr,
+                                                               int out_cols = 0 /*0: both rows (2C values) | C: only the first row (bias gradients)*/) {
     // relu: 0 none | 1 mask = (y > 0) from the stored output | 2 mask recomputed as (x * scale + shift > 0) with exactly the
     // expression of bn_apply_kernel -- BatchNorm + ReLU without a residual: the output tensor is not read at all
     extern __shared__ float sh[];   // [rpi][2][C] per-row-slot partials (16 KB for every C)
@@ -105,18 +106,19 @@ __global__ void __launch_bounds__(256, MODE == 0 ? 4 : 3) channel_reduce_kernel(
 #pragma unroll
     for (int i = 0; i < 8; ++i) { mine[i] = a[i]; mine[C + i] = b[i]; }
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * C; i += 256) {
+    const int ncols = out_cols > 0 ? out_cols : 2 * C;
+    for (int i = threadIdx.x; i < ncols; i += 256) {
         float t = 0.f;
         for (int r = 0; r < rpi; ++r) t += sh[(size_t)r * 2 * C + i];
         atomicAdd(out + i, t);
     }
 }
 
-cudaError_t launch_channel_stats(const __nv_bfloat16* x, long long M, int C, float* stats, int num_sms, cudaStream_t st) {
+cudaError_t launch_channel_stats(const __nv_bfloat16* x, long long M, int C, float* stats, int num_sms, cudaStream_t st, int only_sum) {
     if (!chan_ok(C)) return cudaErrorInvalidValue;
     const int rpi = 256 / (C / 8);
     return launch_kernel(channel_reduce_kernel<0, false>, dim3(rows_grid(M, rpi * 8, num_sms, 2)), dim3(256), (size_t)rpi * 2 * C * sizeof(float), st,
-                         x, nullptr, nullptr, nullptr, stats, M, C, 0, nullptr, nullptr);
+                         x, nullptr, nullptr, nullptr, stats, M, C, 0, nullptr, nullptr, only_sum ? C : 0);
 }
 cudaError_t launch_bn_bwd_reduce(const __nv_bfloat16* dy, const __nv_bfloat16* y, const __nv_bfloat16* x, const float* mean_rstd,
                                  float* dsum, long long M, int C, int relu, int num_sms, cudaStream_t st, const float* gamma,
@@ -125,8 +127,8 @@ cudaError_t launch_bn_bwd_reduce(const __nv_bfloat16* dy, const __nv_bfloat16* y
     const int rpi = 256 / (C / 8);
     const int grid = rows_grid(M, rpi * 8, num_sms, 2);
     const size_t smem = (size_t)rpi * 2 * C * sizeof(float);
-    if (relu == 2) return launch_kernel(channel_reduce_kernel<1, true>, dim3(grid), dim3(256), smem, st, x, dy, y, mean_rstd, dsum, M, C, relu, gamma, beta);
-    return launch_kernel(channel_reduce_kernel<1, false>, dim3(grid), dim3(256), smem, st, x, dy, y, mean_rstd, dsum, M, C, relu, nullptr, nullptr);
+    if (relu == 2) return launch_kernel(channel_reduce_kernel<1, true>, dim3(grid), dim3(256), smem, st, x, dy, y, mean_rstd, dsum, M, C, relu, gamma, beta, 0);
+    return launch_kernel(channel_reduce_kernel<1, false>, dim3(grid), dim3(256), smem, st, x, dy, y, mean_rstd, dsum, M, C, relu, nullptr, nullptr, 0);
 }
 
 __global__ void bn_finalize_kernel(const float* __restrict__ stats, int slots, float* __restrict__ mean_rstd, float* running_mean,

@@ -47,6 +47,16 @@ def _ext():
     return ext()
 
 
+def _zero(t):
+    from . import zero_
+    return zero_(t)
+
+
+def _fallback(site, detail=""):
+    from . import note_fallback
+    note_fallback(site, detail)
+
+
 def scratch(tag, shape, dtype, device):
     """Persistent scratch tensor (stable address: safe to bake into CUDA graphs)."""
     key = (tag, tuple(shape), dtype, str(device))
@@ -101,18 +111,18 @@ def conv2d_fwd_sm100(x, w, bias, y, stride, pad, relu, stats, tag="fwd", zero_st
         Ho, Wo = y.shape[1], y.shape[2]
         A = scratch(("im2col", tag), (B * Ho * Wo, 64), x.dtype, x.device)
         e.im2col_small(x.contiguous(), A, k, pad)
-        wp = scratch(("wstem", tag, w.data_ptr()), (Cout, 64), w.dtype, w.device)       # columns >= k*k*Cin stay zero
-        wp[:, :k * k * Cin].copy_(w.reshape(Cout, k * k * Cin))
+        wp = scratch(("wstem", tag, w.data_ptr()), (Cout, 64), w.dtype, w.device)
+        e.pad_rows(w.reshape(Cout, k * k * Cin), wp)                                    # [Cout][k*k*Cin] -> [Cout][64], zero tail
         if stats is not None and zero_stats:
-            stats.zero_()
+            _zero(stats)
         e.gemm_bf16(A, wp, y.view(B * Ho * Wo, Cout), bias, bool(relu), False, stats)
         return y
     if Cin % 64:
         cp = (Cin + 63) // 64 * 64
         xp = scratch(("xpad", tag), (B, H, W, cp), x.dtype, x.device)
-        xp[..., :Cin].copy_(x)
+        e.pad_rows(x.reshape(B * H * W, Cin), xp.view(B * H * W, cp))                   # channel padding: rows = pixels
         wp = scratch(("wpad", tag, w.data_ptr()), (Cout, k, k, cp), w.dtype, w.device)
-        wp[..., :Cin].copy_(w)
+        e.pad_rows(w.reshape(Cout * k * k, Cin), wp.view(Cout * k * k, cp))
         x, w, Cin = xp, wp, cp
     if _halo_ok(k, stride, pad, Cin, H, W):
         # persistent halo-reuse kernel (conv_halo.cu): 36 KB of L2 traffic per 128-pixel tile instead of 216 KB
@@ -120,7 +130,7 @@ def conv2d_fwd_sm100(x, w, bias, y, stride, pad, relu, stats, tag="fwd", zero_st
             e.conv3x3_halo3_bf16(x, w.reshape(Cout, 9 * 64), y, bias, bool(relu), False)
             return y
         if stats is not None and zero_stats:
-            stats.zero_()
+            _zero(stats)
         e.conv3x3_halo_bf16(x, w.reshape(Cout, 9 * 64), y, bias, bool(relu), False, stats, 0, None)
         return y
     if stride == 2 and USE_STRIDED_TMA and stats is None:
@@ -139,7 +149,7 @@ def conv2d_fwd_sm100(x, w, bias, y, stride, pad, relu, stats, tag="fwd", zero_st
         x, planes = x4, 4
     dh, dw, pl = _taps(k, stride, pad)
     if stats is not None and zero_stats:
-        stats.zero_()
+        _zero(stats)
     e.conv_bf16(x, w.reshape(Cout, k * k * Cin), y, B, planes, dh, dw, pl, bias, bool(relu), False, stats, [], 0)
     return y
 
@@ -194,7 +204,7 @@ def _conv2d_dgrad_s2(e, dy, w, dx, pad, accumulate):
     if USE_STRIDED_TMA and Cin % 64 == 0 and dx.shape[1] == 2 * Ho and dx.shape[2] == 2 * Wo:
         # each parity plane is stored straight into dX by the conv epilogue (row index = strided pixel): no parity buffer, no merge
         if not accumulate and len(plan) < 4:
-            dx.zero_()                     # planes that receive no tap (1x1 shortcut: three of four)
+            _zero(dx)                      # planes that receive no tap (1x1 shortcut: three of four)
         for pi, pj, taps, dh, dw in plan:
             e.conv_bf16_strided(dy, w.reshape(Cout, k * k * Cin), dx, dh, dw, None, False, bool(accumulate), taps, k * k, 1, 2, pi, pj)
         return dx
@@ -225,16 +235,13 @@ def conv2d_wgrad_sm100(x, dy, gw, gb, stride, pad, tag="fwd", zero=True):
         Ho, Wo = dy.shape[1], dy.shape[2]
         A = scratch(("im2col", tag), (B * Ho * Wo, 64), x.dtype, x.device)               # filled by the forward pass
         dW = scratch(("dwstem", tag), (Cout, 64), torch.float32, x.device)
-        dW.zero_()
+        _zero(dW)
         e.linear_wgrad_bf16(dy.view(B * Ho * Wo, Cout), A, dW)
         if zero:
-            gw.zero_()
-        gw.view(Cout, k * k * Cin).add_(dW[:, :k * k * Cin])
+            _zero(gw)
+        e.unpad_add(dW, gw.view(Cout, k * k * Cin))                                      # valid K columns into the flat gradient
         if gb is not None:
-            st = scratch(("dbias", tag), (2, Cout), torch.float32, dy.device)
-            st.zero_()
-            e.channel_stats(dy, st)
-            gb.copy_(st[0])
+            _bias_grad(e, dy, gb, zero)
         return
     if Cin % 64:
         cp = (Cin + 63) // 64 * 64
@@ -247,7 +254,7 @@ def conv2d_wgrad_sm100(x, dy, gw, gb, stride, pad, tag="fwd", zero=True):
         planes = 4
     dh, dw, pl = _taps(k, stride, pad)
     if zero:
-        gw.zero_()
+        _zero(gw)
     if strided:
         e.conv_wgrad_bf16_strided(dy, x, gw, cin_valid, [dy_ - pad for dy_ in range(k) for _ in range(k)],
                                   [dx_ - pad for _ in range(k) for dx_ in range(k)], 2)
@@ -256,10 +263,23 @@ def conv2d_wgrad_sm100(x, dy, gw, gb, stride, pad, tag="fwd", zero=True):
     else:
         e.conv_wgrad_bf16(dy, x, gw, B, planes, cin_valid, dh, dw, pl)
     if gb is not None:
-        st = scratch(("dbias", tag), (2, Cout), torch.float32, dy.device)
-        st.zero_()
-        e.channel_stats(dy, st)
-        gb.copy_(st[0])
+        _bias_grad(e, dy, gb, zero)
+
+
+def _bias_ok(C):
+    return C >= 8 and C <= 2048 and C % 8 == 0 and 256 % (C // 8) == 0       # norm.cu chan_ok
+
+
+def _bias_grad(e, dy, gb, zero):
+    """gb[C] = column sums of dy[..., C], written straight into the flat gradient (one reduction kernel, no staging copy)."""
+    C = dy.shape[-1]
+    if zero:
+        _zero(gb)
+    if _bias_ok(C):
+        e.bias_grad(dy.contiguous(), gb)
+    else:
+        _fallback("bias_grad", f"C={C}")
+        gb.add_(dy.float().reshape(-1, C).sum(0))
 
 
 # =====================================================================================================================
@@ -276,7 +296,7 @@ def bn_fwd(x, y, res, gamma, beta, rm, rv, stats, mean_rstd, count, eps, momentu
                 stats = stats_buf
             else:
                 stats = scratch(("bnstats", mean_rstd.data_ptr()), (1, 2, C), torch.float32, x.device)
-                stats.zero_()
+                _zero(stats)
             e.channel_stats(x, stats)
         # mean / rstd are derived inside bn_apply from the raw sums (training) or the running statistics (evaluation): no
         # separate finalize launch; CTA 0 stores mean/rstd for the backward pass and updates the running statistics
@@ -331,6 +351,8 @@ def relu_bwd_(dy, y, impl):
     if impl == "sm100" and dy.numel() % 8 == 0:
         _ext().relu_bwd(dy, y)
     else:
+        if impl == "sm100":
+            _fallback("relu_bwd", f"numel={dy.numel()}")
         dy.mul_(y > 0)
 
 
@@ -341,6 +363,8 @@ def maxpool2_fwd(x, y, idx, impl):
     if impl == "sm100" and x.shape[-1] % 8 == 0:
         _ext().maxpool2_fwd(x, y, idx)
         return
+    if impl == "sm100":
+        _fallback("maxpool2_fwd", f"C={x.shape[-1]}")
     B, H, W, C = x.shape
     Ho, Wo = H // 2, W // 2
     win = x[:, :Ho * 2, :Wo * 2].reshape(B, Ho, 2, Wo, 2, C).permute(0, 1, 3, 5, 2, 4).reshape(B, Ho, Wo, C, 4)
@@ -352,6 +376,8 @@ def maxpool2_bwd(dy, idx, dx, impl):
     if impl == "sm100" and dx.shape[-1] % 8 == 0:
         _ext().maxpool2_bwd(dy, idx, dx)
         return
+    if impl == "sm100":
+        _fallback("maxpool2_bwd", f"C={dx.shape[-1]}")
     B, H, W, C = dx.shape
     Ho, Wo = H // 2, W // 2
     dx.zero_()
@@ -377,6 +403,8 @@ def dropout_fwd(x, y, mask, p, seed, step, stream, impl):
     if impl == "sm100" and x.numel() % 8 == 0:
         _ext().dropout_fwd(x, y, mask, float(p), int(seed), step, int(stream))
         return
+    if impl == "sm100":
+        _fallback("dropout_fwd", f"numel={x.numel()}")
     keep = torch.rand(x.shape, device=x.device) >= p
     mask.copy_(keep)
     y.copy_(x * keep / (1 - p))
@@ -386,6 +414,8 @@ def dropout_bwd(dy, mask, dx, p, impl):
     if impl == "sm100" and dx.numel() % 8 == 0:
         _ext().dropout_bwd(dy, mask, dx, float(p))
     else:
+        if impl == "sm100":
+            _fallback("dropout_bwd", f"numel={dx.numel()}")
         dx.copy_(dy * mask / (1 - p))
 
 
@@ -410,6 +440,7 @@ def linear_fwd(x, w, bias, y, relu, impl):
                 return
             _ext().gemm_bf16(x.contiguous(), w, y, bias, bool(relu), False, None)
             return
+        _fallback("linear_fwd", f"N={N} K={K}")
     out = F.linear(x, w.to(x.dtype), bias.to(x.dtype) if bias is not None else None)
     if relu:
         out = F.relu(out)
@@ -421,9 +452,9 @@ def linear_bwd(x, dy, w, dx, dw, db, acc_dx, impl, zero=True):
     if impl == "sm100" and N <= 32:
         if USE_HEAD_V2 and K % 2 == 0:
             if zero:                  # v2 accumulates with atomics (the native plan passes zero=False: the flat gradient is pre-zeroed)
-                dw.zero_()
+                _zero(dw)
                 if db is not None:
-                    db.zero_()
+                    _zero(db)
             _ext().linear_small_bwd2(x.contiguous(), dy.contiguous(), w, dx, dw, db, bool(acc_dx))
             return
         _ext().linear_small_bwd(x.contiguous(), dy.contiguous(), w, dx, dw, db, bool(acc_dx))
@@ -432,17 +463,18 @@ def linear_bwd(x, dy, w, dx, dw, db, acc_dx, impl, zero=True):
     sm = impl == "sm100" and K % 64 == 0 and N % 64 == 0
     if sm and (N <= 64 or N % 128 == 0):
         if zero:
-            dw.zero_()
+            _zero(dw)
         _ext().linear_wgrad_bf16(dy.contiguous(), x.contiguous(), dw)
     else:
+        if impl == "sm100":
+            _fallback("linear_wgrad", f"N={N} K={K}")
         dw.copy_(dyf.t() @ x)
     if db is not None:
-        if sm and N % 8 == 0 and 256 % (N // 8) == 0:
-            st = scratch(("dbias_lin", w.data_ptr()), (2, N), torch.float32, dy.device)
-            st.zero_()
-            _ext().channel_stats(dy.contiguous(), st)
-            db.copy_(st[0])
+        if sm and _bias_ok(N):
+            _bias_grad(_ext(), dy, db, zero)
         else:
+            if impl == "sm100":
+                _fallback("linear_bias_grad", f"N={N}")
             db.copy_(dyf.float().sum(0))
     if dx is not None:
         if sm:   # dx = dy @ W  ==  GEMM with the transposed weight as the K-major B operand
@@ -450,6 +482,8 @@ def linear_bwd(x, dy, w, dx, dw, db, acc_dx, impl, zero=True):
             _ext().filter_transpose(w, wt, N, 1, K)
             _ext().gemm_bf16(dy.contiguous(), wt, dx, None, False, bool(acc_dx), None)
             return
+        if impl == "sm100":
+            _fallback("linear_dgrad", f"N={N} K={K}")
         d = dyf @ w.to(x.dtype)
         if acc_dx:
             dx.add_(d)

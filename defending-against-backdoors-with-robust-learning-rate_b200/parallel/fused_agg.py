@@ -167,7 +167,7 @@ class FusedAggregator:
         mine = [j for j in range(n_part) if self.slot_owner(j)[0] == ctx.rank]
         local = torch.zeros(n_part, dtype=torch.float64, device=ctx.device)
         if mine:
-            norms = ops.update_norms(self.w_global, [self.slots[self.slot_owner(j)[1]] for j in mine])
+            norms = ops.update_norms(self.w_global, [self.slots[self.slot_owner(j)[1]] for j in mine], self.n_vote)
             local[torch.as_tensor(mine, device=ctx.device)] = norms ** 2
         ctx.all_reduce_sum(local)
         return local.sqrt()

@@ -35,7 +35,7 @@ class TorchTrainer:
         self.m = torch.zeros(n, dtype=torch.float32, device=device)
         self.compute_dtype = torch.bfloat16 if (cuda and args.dtype == "bf16") else torch.float32
         self.net = GraphNet(layout, self.w, self.g, self.compute_dtype)
-        self.opt = ops.FlatSGD(n, device, args.client_lr, args.client_moment, 10.0, args.clip)
+        self.opt = ops.FlatSGD(n, device, args.client_lr, args.client_moment, 10.0, args.clip, n_pgd=layout.n_vote)
         self.loss_sum = torch.zeros(1, dtype=torch.float32, device=device)
         self.bs = args.bs
         self.use_graphs = cuda and not args.no_graphs if use_graphs is None else use_graphs

@@ -187,6 +187,22 @@ class FakeExt:
         st[0] += xf.sum(0)
         st[1] += (xf * xf).sum(0)
 
+    def bias_grad(self, dy, db):
+        self.calls.append("bias_grad")
+        db += dy.reshape(-1, dy.shape[-1]).float().sum(0)
+
+    def pad_rows(self, src, dst):
+        self.calls.append("pad_rows")
+        dst.zero_()
+        dst[:, :src.shape[1]] = src
+
+    def unpad_add(self, src, dst):
+        self.calls.append("unpad_add")
+        dst += src[:, :dst.shape[1]]
+
+    def memset_zero(self, t):
+        t.zero_()
+
 
 @pytest.fixture
 def fake(monkeypatch):
