@@ -141,6 +141,47 @@ def run_reference(a):
     print(json.dumps(out))
 
 
+def ops_fallbacks():
+    """Library fall-throughs of the sm100 back-end recorded while the steps were built / captured ({} = none)."""
+    from rlr_b200 import ops
+    return ops.fallback_calls()
+
+
+def aggregation_check(eng, ctx, a):
+    """Correctness evidence for the multi-GPU fused path, OUTSIDE the timed region: one extra round in which every rank also
+    recomputes the server step from an all_gather of the participants' parameters with the fp64 oracle (ops.aggregate_oracle,
+    the re-statement of src/aggregation.py:19-45) and compares it with what the fused P2P/multicast kernel left in its
+    ``w_global``; plus a bit-wise comparison of ``w_global`` across ranks."""
+    import torch
+    from rlr_b200 import ops
+    try:
+        rnd = 20_000
+        chosen = eng.place_participants(eng.sample_agents(rnd))
+        prev = eng.w_global.clone()
+        # local training only (the engine's own code path), then gather BEFORE the fused kernel consumes the slots
+        eng.args.noise, noise_keep = 0.0, eng.args.noise                      # Philox noise has no oracle stream: check without it
+        eng.run_round(rnd)
+        eng.args.noise = noise_keep
+        ws = eng.fused.gather_participants(len(chosen))
+        weights = [float(eng.agent_data_sizes[i]) for i in chosen]
+        want, want_flipped = ops.aggregate_oracle(prev, ws, weights, eng.args.aggr, eng.args.robustLR_threshold, eng.args.server_lr,
+                                                  None, eng.layout.n_vote)
+        got = eng.global_params()
+        err = (got.double() - want.double()).abs().max()
+        scale = (want.double() - prev.double()).abs().max()
+        allw = ctx.all_gather(got)
+        same = bool((allw == allw[0:1]).all().item())
+        stats = torch.stack([err, scale])
+        ctx.all_reduce_max(stats)
+        _, flipped = eng.round_result()
+        pad = (eng.layout.n_vote - eng.layout.n_params) if eng.args.robustLR_threshold > 0 else 0
+        return {"agg_check_max_abs_err": float(stats[0]), "max_abs_update": float(stats[1]), "all_ranks_equal": same,
+                "flipped_kernel": flipped, "flipped_oracle": int(want_flipped) - pad, "participants": len(chosen),
+                "oracle": "fp64 ops.aggregate_oracle on an NCCL all_gather of the slots (src/aggregation.py:19-45 semantics)"}
+    except Exception as e:  # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+
+
 def run_ours(a):
     import torch
     from rlr_b200.engine import FLEngine
@@ -223,14 +264,17 @@ def run_ours(a):
       except Exception as e:  # noqa: BLE001  -- never lose the device-timed line because the end-to-end pass failed
         notes.append(f"e2e pass failed: {type(e).__name__}: {str(e)[:160]}")
     launches = eng.trainer.launches_per_step() * info["steps"] * a.steps + 2 * a.steps  # + round_init + fused aggregate
+    agg_check = aggregation_check(eng, ctx, a) if n > 1 else None
     if ctx.is_main:
         out = {"impl": "ours", "metric": "fl_rounds_per_sec", "value": a.steps * 1e3 / ms, "unit": "rounds/s", "n_gpus": n,
                "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
                "scaling": "strong", "vs_baseline": None, "dtype": a.dtype if cuda else "fp32", "data": "synthetic",
                "config": {**config_dict(a, n, "ours"), "trainer": eng.trainer.name, "agg_backend": eng.fused.backend,
                           "symm_provider": eng.fused.buf.provider, "multicast": bool(getattr(eng.fused, "use_multimem", False)),
-                          "local_steps_per_round_per_gpu": info["steps"], "n_params": eng.layout.n_params},
+                          "local_steps_per_round_per_gpu": info["steps"], "n_params": eng.layout.n_params,
+                          "fused_handoff": bool(eng.handoff)},
                "clocks": ck, "e2e": e2e, "gpu_launches": int(launches), "notes": notes,
+               "library_fallbacks": ops_fallbacks(), "agg_check": agg_check,
                "phase_ms_per_round_rank0": {k: v / a.steps for k, v in phases.items()}}
         print(json.dumps(out))
     eng.close()

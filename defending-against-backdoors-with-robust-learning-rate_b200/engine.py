@@ -101,6 +101,12 @@ class FLEngine:
         self.trainers = [self.trainer] + [make_trainer(args.trainer, self.layout, args, dev, max_shard) for _ in range(n_flight - 1)]
         # (on CPU the extra trainers are still used round-robin -- same bookkeeping, no overlap)
         self.streams = [torch.cuda.Stream(dev) for _ in range(n_flight)] if (n_flight > 1 and dev.type == "cuda") else None
+        # Round hand-off fused with the first local GEMM (native trainer only): no round_init pass, no barrier-out in the aggregation
+        # kernel -- the first step of every agent reads the broadcast buffer behind per-slice ready flags (parallel/fused_agg.py).
+        self.handoff = False
+        if not getattr(args, "no_fused_handoff", False) and all(hasattr(t, "attach_broadcast") for t in self.trainers):
+            if all([t.attach_broadcast(self.fused) for t in self.trainers]):
+                self.handoff = self.fused.enable_handoff()
         self._loss_parts = [torch.zeros(1, dtype=torch.float32, device=dev) for _ in range(n_flight)]
         self.logger = MetricLogger(args, enabled=ctx.is_main and bool(args.log_dir))
         self.aggregator = Aggregation(self.agent_data_sizes, self.layout.n_params, self.poisoned_val, args,
@@ -233,9 +239,14 @@ class FLEngine:
         return float(vals[0]), n_flip
 
     # ---- evaluation (src/federated.py:78-92) ---------------------------------------------------------------
+    def global_params(self):
+        """The current global parameter vector, complete on this rank (acquires the broadcast slices when the hand-off is fused)."""
+        self.fused.acquire()
+        return self.w_global
+
     def evaluate(self, rnd: int):
         args = self.args
-        fwd = self.trainer.eval_forward(self.w_global)
+        fwd = self.trainer.eval_forward(self.global_params())
         kw = dict(bs=args.bs, num_classes=self.n_classes, ctx=self.ctx)
         val_loss, (val_acc, per_class) = get_loss_n_accuracy(fwd, self.val_dataset, **kw)
         poison_loss, (poison_acc, _) = get_loss_n_accuracy(fwd, self.poisoned_val, **kw)
@@ -285,7 +296,7 @@ class FLEngine:
             self.logger.record(rnd, **rec)
             history.append({"round": rnd, **rec})
             if args.checkpoint and self.ctx.is_main and ((args.ckpt_every and rnd % args.ckpt_every == 0) or rnd == rounds):
-                save_checkpoint(args.checkpoint, self.w_global, rnd, args, self.layout,
+                save_checkpoint(args.checkpoint, self.global_params(), rnd, args, self.layout,
                                 {"cum_poison_acc_mean": self.cum_poison_acc_mean})
         if self.verbose:
             print("Training has finished!")

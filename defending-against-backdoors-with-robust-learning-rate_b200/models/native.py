@@ -66,6 +66,8 @@ class NativeNet:
                          linear=default, dropout=default) if not isinstance(impl, dict) else dict(impl)
         self.seed = seed
         self.fuse_bn_stats = False
+        self.first_wait = None        # (ready_ptr, lo, hi, epoch tensor): flag wait handed to the first layer's GEMM (round hand-off)
+        self.after_first_op = None    # callable run right after the first plan op of a forward pass
         self.step_counter = torch.zeros(1, dtype=torch.int64, device=device)  # Philox offset for dropout
         self._build_plan()
         self._alloc()
@@ -241,16 +243,27 @@ class NativeNet:
     # ------------------------------------------------------------------------------------------------------------
     # parameter views
     # ------------------------------------------------------------------------------------------------------------
-    def bind(self, w, wb, g):
-        """Point the net at flat fp32 params ``w``, their bf16 shadow ``wb`` and the flat fp32 gradient ``g``."""
+    def bind(self, w, wb, g, w_buffers=None):
+        """Point the net at flat fp32 params ``w``, their bf16 shadow ``wb`` and the flat fp32 gradient ``g``.  ``w_buffers``: flat
+        vector that holds the BatchNorm running statistics (default ``w``) -- the first step of a round reads its PARAMETERS from the
+        broadcast buffer but must update the running statistics in the trainer's own vector."""
         self.w, self.wb, self.g = w, wb, g
         lay = self.layout
-        self.pw = {p.name: lay.view(w, p) for p in lay.params + lay.buffers}
+        self.pw = {p.name: lay.view(w, p) for p in lay.params}
+        self.pw.update({b.name: lay.view(w if w_buffers is None else w_buffers, b) for b in lay.buffers})
         self.pwb = {p.name: lay.view(wb, p) for p in lay.params} if wb is not None else {}
         self.pg = {p.name: lay.view(g, p) for p in lay.params} if g is not None else {}
 
     def T(self, t, B):
-        return self.act[t][:B] if t != self.in_tid else self._x[:B]
+        return self.act[t][:B] if t != self.in_tid else self._x      # the input is handed in already sized for the batch
+
+    def stem_geometry(self):
+        """(k, pad, Ho, Wo) when the first layer takes the im2col stem path on this back-end (the trainer then lets the batch-assembly
+        kernel write the im2col matrix directly and passes it as the network input), else None."""
+        op = self.plan[0]
+        if op.kind != "conv" or op.x != self.in_tid or self.impl["conv_fwd"] != "sm100" or self.impl["conv_wgrad"] != "sm100":
+            return None
+        return ops.stem_geometry(op.in_shape, op.attrs)
 
     def G(self, t, B):
         return self.grad[t][:B]
@@ -260,21 +273,24 @@ class NativeNet:
     # ------------------------------------------------------------------------------------------------------------
     def forward(self, x_nhwc, train: bool):
         """``x_nhwc``: [B,H,W,C] bf16 (channels of the first conv, un-padded).  Returns fp32 logits [B,classes]."""
-        B = x_nhwc.shape[0]
         out = self.forward_raw(x_nhwc, train)
+        B = out.shape[0]
         self.logits[:B].copy_(out)
         return self.logits[:B]
 
     def forward_raw(self, x_nhwc, train: bool):
         """Forward pass; returns the head's output [B,classes] in the activation dtype, in place in its activation buffer (the
-        training step hands it straight to the loss kernel -- no fp32 staging copy)."""
-        B = x_nhwc.shape[0]
+        training step hands it straight to the loss kernel -- no fp32 staging copy).  ``x_nhwc``: [B,H,W,C], or the first layer's
+        im2col matrix [B*Ho*Wo, 64] when ``stem_geometry()`` is not None (batch = rows / (Ho*Wo))."""
+        B = x_nhwc.shape[0] if x_nhwc.dim() == 4 else x_nhwc.shape[0] // (self.plan[0].out_shape[0] * self.plan[0].out_shape[1])
         self._x, self._B, self._train = x_nhwc, B, train
         self._epoch = getattr(self, "_epoch", 0) + 1     # forward-pass id: lets stride-2 convs share their parity-split input copy
         if train:
             ops.zero_(self.stats_arena)
-        for op in self.plan:
+        for i, op in enumerate(self.plan):
             getattr(self, "_fwd_" + op.kind)(op, B, train)
+            if i == 0 and self.after_first_op is not None:
+                self.after_first_op()        # hand-off: acquire the rest of the broadcast once the first-layer GEMM is queued
         return self.T(self.out_tid, B).reshape(B, -1)
 
     def dlogits_buffer(self, B):
@@ -301,7 +317,8 @@ class NativeNet:
         # while it is still L2-resident (default: measured cheaper than the in-epilogue reduction, profiles/r1c notes)
         stats = op.saved.get("stats") if (train and op.saved.get("want_stats") and self.fuse_bn_stats) else None
         if self.impl["conv_fwd"] == "sm100" and ops.conv_supported(op.in_shape, a, "fwd"):
-            ops.conv2d_fwd_sm100(x, self.pwb[op.name + ".weight"], bias, y, a.get("stride", 1), a.get("pad", 0), op.relu, stats, tag=(id(self), op.name), zero_stats=False, s2d_epoch=self._epoch)
+            ops.conv2d_fwd_sm100(x, self.pwb[op.name + ".weight"], bias, y, a.get("stride", 1), a.get("pad", 0), op.relu, stats, tag=(id(self), op.name),
+                                 zero_stats=False, s2d_epoch=self._epoch, wait=self.first_wait if (op is self.plan[0] and x.dim() == 2) else None)
             return
         if self.impl["conv_fwd"] == "sm100":
             ops.note_fallback("conv_fwd", f"{op.name} in={op.in_shape} {a}")
@@ -438,21 +455,66 @@ class NativeTrainer:
         self.y = torch.zeros(self.bs, dtype=torch.int64, device=device)
         C, H, W = layout.in_shape
         self.x = torch.zeros(self.bs, H, W, C, dtype=ACT, device=device)
+        # tiny-K first layer: the batch-assembly kernel writes the stem convolution's im2col matrix directly (gather_im2col)
+        self.stem = self.net.stem_geometry()
+        self.xA = torch.zeros(self.bs * self.stem[2] * self.stem[3], 64, dtype=ACT, device=device) if self.stem else None
         self._graphs = {}
         self._eval_nets = {}
+        self.bcast = None             # round hand-off source (parallel.FusedAggregator) once attach_broadcast() was called
 
-    def _step(self, dataset, B, w0):
+    # ---- round hand-off fused with the first local step ---------------------------------------------------------------------
+    def attach_broadcast(self, fused):
+        """Fuse the parameter hand-off of a round with the first local step (SURVEY.md A9 / 5.8 "broadcast fused with the first GEMM").
+        Instead of a ``round_init`` pass (w <- w_global, bf16 shadow, m <- 0), the FIRST step of every agent reads its parameters
+        straight from the broadcast buffer of the aggregator -- fp32 ``w_global`` and the bf16 operand shadow that the aggregation
+        kernels of all GPUs multicast into every rank -- and its optimizer kernel starts from zero momentum.  The step's first kernel
+        that needs parameters is the stem convolution's GEMM: its producer warp acquires the ready word(s) of the slice(s) holding the
+        stem filter (in-kernel ``ld.acquire.sys`` spin) and starts while the remaining slices are still landing; a one-warp
+        ``acquire_slices`` kernel queued behind it waits for the rest and seeds the BatchNorm running statistics.  Needs the im2col
+        stem (every zoo model has one) and the bf16 shadow."""
+        if self.stem is None or fused.w_bf16 is None:
+            return False
+        self.bcast = fused
+        return True
+
+    def _bind_first(self, w0):
+        f = self.bcast
+        self.net.bind(f.w_global, f.w_bf16, self.g, w_buffers=self.w)
+        lay = self.layout
+        first_w = lay.by_name[self.net.plan[0].name + ".weight"]
+        lo, hi = f.slices_of(first_w.offset, first_w.offset + first_w.numel)
+        self.net.first_wait = (f.ready_ptr, lo, hi, f.epoch_dev) if f.ready_ptr else None
+        tail_src, tail_dst = f.w_global[lay.n_vote:], self.w[lay.n_vote:]
+        self.net.after_first_op = lambda: ops.ext().acquire_slices(f.ready_ptr, 0, max(0, f.n_slices - 1), f.epoch_dev, tail_src, tail_dst)
+
+    def _bind_normal(self):
+        self.net.bind(self.w, self.wb, self.g)
+        self.net.first_wait = None
+        self.net.after_first_op = None
+
+    def _step(self, dataset, B, w0, first=False):
+        if first:
+            self._bind_first(w0)
         meta = dataset.meta
-        ops.gather_normalize(dataset.data, self.perm, meta.mean, meta.std, out=self.x[:B], nhwc=True, cursor=self.cursor,
-                             targets=dataset.targets, out_labels=self.y, batch=B)
-        logits = self.net.forward_raw(self.x[:B], True)                       # bf16 [B,classes], in the head's activation buffer
+        if self.stem is not None:
+            k, pad, Ho, Wo = self.stem
+            xin = self.xA[:B * Ho * Wo]
+            ops.gather_im2col(dataset.data, self.perm, meta.mean, meta.std, k, pad, xin, cursor=self.cursor, targets=dataset.targets,
+                              out_labels=self.y, batch=B)
+        else:
+            xin = self.x[:B]
+            ops.gather_normalize(dataset.data, self.perm, meta.mean, meta.std, out=xin, nhwc=True, cursor=self.cursor,
+                                 targets=dataset.targets, out_labels=self.y, batch=B)
+        logits = self.net.forward_raw(xin, True)                              # bf16 [B,classes], in the head's activation buffer
         _, dl = ops.softmax_xent(logits, self.y[:B], True, self.loss_sum, dlogits=self.net.dlogits_buffer(B))
         self.net.backward(dl)
-        self.opt.step(self.w, self.g, self.m, w0=w0, w_bf16=self.wb)
+        self.opt.step(self.w, self.g, self.m, w0=w0, w_bf16=self.wb, w_in=self.bcast.w_global if first else None)
         ops.ext().advance_cursor(self.cursor, B, self.net.step_counter)       # next batch; next Philox step for the dropout masks
+        if first:
+            self._bind_normal()
 
-    def _get_graph(self, dataset, B, w0):
-        key = (B, dataset.data.data_ptr(), w0.data_ptr())
+    def _get_graph(self, dataset, B, w0, first=False):
+        key = (B, dataset.data.data_ptr(), w0.data_ptr(), bool(first))
         if key in self._graphs:
             return self._graphs[key]
         keep = (self.w.clone(), self.wb.clone(), self.m.clone(), self.cursor.clone(), self.loss_sum.clone(),
@@ -464,13 +526,13 @@ class NativeTrainer:
             for _ in range(3):
                 self.cursor.zero_()
                 c0 = ops.launch_calls()
-                self._step(dataset, B, w0)
+                self._step(dataset, B, w0, first)
                 self._launches = ops.launch_calls() - c0
         torch.cuda.current_stream(self.device).wait_stream(s)
         self.cursor.zero_()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph, capture_error_mode="thread_local"):
-            self._step(dataset, B, w0)
+            self._step(dataset, B, w0, first)
         self.w.copy_(keep[0]); self.wb.copy_(keep[1]); self.m.copy_(keep[2]); self.cursor.copy_(keep[3])
         self.loss_sum.copy_(keep[4]); self.net.step_counter.copy_(keep[5])
         self._graphs[key] = graph
@@ -481,10 +543,14 @@ class NativeTrainer:
         dataset, n = agent.dataset, agent.n_data
         self.loss_sum.zero_()
         graphs = self.use_graphs and n <= self.max_shard
+        fused = self.bcast is not None and w_global.data_ptr() == self.bcast.w_global.data_ptr()
         if graphs:
             full = self._get_graph(dataset, bs, w_global) if n >= bs else None
             tail = self._get_graph(dataset, n % bs, w_global) if n % bs else None
-        ops.round_init(w_global, self.w, self.wb, self.m)
+            if fused:     # first step of the round: parameters from the broadcast buffer, zero momentum (no round_init pass)
+                first_g = self._get_graph(dataset, bs if n >= bs else n % bs, w_global, first=True)
+        if not fused:
+            ops.round_init(w_global, self.w, self.wb, self.m)
         # dropout Philox stream = (seed, step counter, node): start every (agent, round) at its own counter so agents trained in
         # the same round -- on different GPUs or one after another -- draw independent masks, as the reference's agents do from
         # one sequential RNG (src/federated.py:68-72); the captured graphs increment the device counter once per step
@@ -494,10 +560,18 @@ class NativeTrainer:
             idx = agent.epoch_indices(args.seed, rnd, ep)
             self.perm[:n].copy_(idx)
             self.cursor.zero_()
-            for _ in range(n // bs):
-                full.replay() if graphs else self._step(dataset, bs, w_global)
+            for b in range(n // bs):
+                is_first = fused and ep == 0 and b == 0
+                if graphs:
+                    (first_g if is_first else full).replay()
+                else:
+                    self._step(dataset, bs, w_global, first=is_first)
             if n % bs:
-                tail.replay() if graphs else self._step(dataset, n % bs, w_global)
+                is_first = fused and ep == 0 and n < bs
+                if graphs:
+                    (first_g if is_first else tail).replay()
+                else:
+                    self._step(dataset, n % bs, w_global, first=is_first)
             steps += (n + bs - 1) // bs
         if out.data_ptr() != self.w.data_ptr():
             out.copy_(self.w)

@@ -24,7 +24,7 @@ _ext_err = None
 _lock = threading.Lock()
 
 MODE_IDS = {"avg": 0, "comed": 1, "sign": 2}
-MAX_FUSED_AGENTS = 128   # kMaxAgents of ops/csrc/aggregate.cu
+MAX_FUSED_AGENTS = 1024   # kMaxAgents of ops/csrc/aggregate.cu (participant tables of the fused kernel)
 
 
 class _Counter:
@@ -159,6 +159,33 @@ def gather_normalize(data, idxs, mean, std, dtype=torch.float32, nhwc=False, c_p
     return out
 
 
+def gather_im2col(data, idxs, mean, std, k, pad, out, cursor=None, targets=None, out_labels=None, batch=None):
+    """Batch assembly fused with the first layer's im2col (SURVEY.md K1+K2, tiny-K stems: C*k*k <= 64): row (b, ho, wo) of ``out``
+    [B*Ho*Wo, 64] (bf16) is the k x k x C patch of the normalised image around that output pixel in (tap, channel) order, zero
+    padded -- the A operand of the stem convolution as a single-k-block tcgen05 GEMM.  Same cursor / label contract as
+    ``gather_normalize``."""
+    N, H, W, C = data.shape
+    B = int(batch if batch is not None else idxs.shape[0])
+    Ho, Wo = H + 2 * pad - k + 1, W + 2 * pad - k + 1
+    if data.is_cuda:
+        ext().gather_im2col(data, idxs, cursor, targets, out, out_labels, B, int(k), int(pad), [float(m) for m in mean], [float(s) for s in std])
+        return out
+    off = int(cursor.item()) if cursor is not None else 0
+    sel = idxs[off:off + B]
+    x = data[sel].to(torch.float32)
+    if data.dtype == torch.uint8:
+        x = x / 255.0
+    x = (x - torch.tensor(mean, dtype=torch.float32)) / torch.tensor(std, dtype=torch.float32)          # [B,H,W,C]
+    xp = torch.nn.functional.pad(x, (0, 0, pad, pad, pad, pad))
+    cols = [xp[:, dy:dy + Ho, dx:dx + Wo, :] for dy in range(k) for dx in range(k)]                       # (tap, channel) order
+    A = torch.cat(cols, dim=-1).reshape(B * Ho * Wo, k * k * C)
+    out[:B * Ho * Wo].zero_()
+    out[:B * Ho * Wo, :k * k * C] = A.to(out.dtype)
+    if out_labels is not None and targets is not None:
+        out_labels[:B] = targets[sel]
+    return out
+
+
 def stamp_pixels(data, sel, rows, cols, vals, mode):
     """Apply a compiled trojan pixel program to images ``sel`` of ``data`` [N,H,W,C] in place."""
     if len(rows) == 0 or sel.numel() == 0:
@@ -198,9 +225,10 @@ def aggregate_oracle(w_global, w_agents, weights, mode="avg", theta=0, server_lr
     n = g.numel()
     n_vote = n if n_vote is None else int(n_vote)
     ups = [(w.double() - g) for w in w_agents]
+    wt = torch.as_tensor(weights, dtype=torch.float64, device=g.device)
+    mean_raw = sum(w_ * u for w_, u in zip(wt, ups)) / wt.sum()     # tail coordinates (BatchNorm statistics) are never clip-scaled
     if scales is not None:
         ups = [u * float(s) for u, s in zip(ups, scales)]
-    wt = torch.as_tensor(weights, dtype=torch.float64, device=g.device)
     mean = sum(w_ * u for w_, u in zip(wt, ups)) / wt.sum()
     signs = sum(torch.sign(u) for u in ups)
     if mode == "avg":
@@ -222,7 +250,7 @@ def aggregate_oracle(w_global, w_agents, weights, mode="avg", theta=0, server_lr
         flipped = int(neg.sum())
     new = g + lr * agg
     if n_vote < n:
-        new[n_vote:] = g[n_vote:] + mean[n_vote:]
+        new[n_vote:] = g[n_vote:] + mean_raw[n_vote:]
     return new.float(), flipped
 
 
@@ -233,10 +261,12 @@ def aggregate_partials(w_global, w_local_agents, local_weights, n_vote=None, sca
     g = w_global.double()
     vote = torch.zeros_like(w_global, dtype=torch.float32)
     wsum = torch.zeros_like(g)
+    nv = g.numel() if n_vote is None else int(n_vote)
     for i, (w, nk) in enumerate(zip(w_local_agents, local_weights)):
         u = w.double() - g
         if scales is not None:
-            u = u * float(scales[i])
+            u = u.clone()
+            u[:nv] *= float(scales[i])           # server clipping scales the voted coordinates only
         vote += torch.sign(u).float()
         wsum += float(nk) * u
     return vote, wsum
@@ -301,8 +331,9 @@ def fused_aggregate(w_global, w_agents, weights, mode="avg", theta=0, server_lr=
         return out
     dev = w_global.device
     if len(w_agents) > MAX_FUSED_AGENTS:
-        # more participants than the kernel's per-coordinate register/local-memory budget: exact torch evaluation on the device
-        # (fp64, same semantics; only reached by very large --num_agents * --agent_frac)
+        # more participants than the kernel's pointer / weight tables hold (1024): exact torch evaluation on the device (fp64, same
+        # semantics) -- recorded as a library fall-through
+        note_fallback("fused_aggregate", f"K={len(w_agents)} > {MAX_FUSED_AGENTS}")
         noise = None
         if noise_std > 0:
             gen = torch.Generator(device=dev).manual_seed(int(seed) * 1000003 + int(noise_stream))
@@ -374,21 +405,31 @@ class FlatSGD:
         self.n_pgd = int(n if n_pgd is None else n_pgd)
         self.norms = torch.zeros(2, dtype=torch.float64, device=device)  # [||g||^2, ||w-w0||^2]
 
-    def step(self, w, g, m, w0=None, w_bf16=None):
+    def step(self, w, g, m, w0=None, w_bf16=None, w_in=None):
+        """``w_in``: first local step of a round fused with the hand-off -- parameters are read from ``w_in`` (the round's global
+        parameters, i.e. the broadcast buffer) instead of ``w`` and the momentum counts as zero, so no separate
+        ``w <- w_global, m <- 0`` pass is needed; coordinates ``>= n_pgd`` (BatchNorm running statistics already updated in ``w``
+        by this step's forward pass) keep their value."""
         if w.is_cuda:
             e = ext()
             e.memset_zero(self.norms)
             e.sqnorm(g, self.norms[0:1])
             pgd = self.pgd_clip > 0
             e.sgd_step(w, g, m, w0 if pgd else None, w_bf16, self.lr, self.momentum, self.max_grad_norm,
-                       self.norms[0:1], self.norms[1:2] if pgd else None, self.n_pgd)
+                       self.norms[0:1], self.norms[1:2] if pgd else None, self.n_pgd, w_in)
             if pgd:
                 e.pgd_project(w, w0, w_bf16, self.pgd_clip, self.norms[1:2], self.n_pgd)
             return
         gn = g.double().norm()
         coef = min(1.0, self.max_grad_norm / (float(gn) + 1e-6)) if self.max_grad_norm > 0 else 1.0
-        m.mul_(self.momentum).add_(g, alpha=coef)
-        w.add_(m, alpha=-self.lr)
+        if w_in is not None:
+            k = self.n_pgd
+            m.zero_()
+            m[:k].add_(g[:k], alpha=coef)
+            w[:k].copy_(w_in[:k] - self.lr * m[:k])
+        else:
+            m.mul_(self.momentum).add_(g, alpha=coef)
+            w.add_(m, alpha=-self.lr)
         if self.pgd_clip > 0:
             k = self.n_pgd
             d = w[:k] - w0[:k]
@@ -445,4 +486,4 @@ def eval_metrics(logits, labels, loss_sum, confusion):
 
 
 from .nn import (avgpool_bwd, avgpool_fwd, bn_bwd, bn_fwd, conv2d_dgrad_sm100, conv2d_fwd_sm100, conv2d_wgrad_sm100, conv_supported,  # noqa: E402,F401
-                 dropout_bwd, dropout_fwd, linear_bwd, linear_fwd, maxpool2_bwd, maxpool2_fwd, relu_bwd_, scratch, STAT_SLOTS)
+                 dropout_bwd, dropout_fwd, linear_bwd, linear_fwd, maxpool2_bwd, maxpool2_fwd, relu_bwd_, scratch, stem_geometry, STAT_SLOTS)

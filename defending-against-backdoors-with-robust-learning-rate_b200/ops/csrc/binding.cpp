@@ -32,7 +32,7 @@ void fused_aggregate(at::Tensor w_agent_ptrs, at::Tensor weights, c10::optional<
                      bool use_multimem, int64_t begin, int64_t end, int64_t n_vote, int64_t mode, int64_t theta,
                      double server_lr, double noise_std, int64_t seed, int64_t noise_stream,
                      c10::optional<at::Tensor> flipped, c10::optional<at::Tensor> flag_ptrs,
-                     c10::optional<at::Tensor> local_sync, int64_t rank, int64_t world, int64_t epoch) {
+                     c10::optional<at::Tensor> local_sync, int64_t rank, int64_t world, int64_t epoch, bool handoff) {
     CHECK_CUDA(w_agent_ptrs); CHECK_CUDA(weights); CHECK_CUDA(out_ptrs);
     TORCH_CHECK(w_agent_ptrs.scalar_type() == at::kLong && out_ptrs.scalar_type() == at::kLong, "pointer tables must be int64");
     TORCH_CHECK(weights.scalar_type() == at::kDouble, "weights must be float64");
@@ -56,8 +56,23 @@ void fused_aggregate(at::Tensor w_agent_ptrs, at::Tensor weights, c10::optional<
     p.flag_ptrs = ptr_or_null<uint32_t* const>(flag_ptrs);
     p.local_sync = ptr_or_null<uint32_t>(local_sync);
     p.rank = (int)rank; p.world = (int)world; p.epoch = (uint32_t)epoch;
+    p.handoff = handoff ? 1 : 0;
     TORCH_CHECK(world <= 1 || (p.flag_ptrs && p.local_sync), "multi-GPU aggregation needs flag_ptrs and local_sync");
     check(rlr::launch_fused_aggregate(p, num_sms(), cur_stream()), "fused_aggregate");
+}
+
+// wait for broadcast slices [first, last] of round `epoch` (ready_ptr = address of this rank's ready words, 0 = nothing to wait for) and
+// copy the BatchNorm-statistics tail of the broadcast buffer into the trainer's parameters
+void acquire_slices(int64_t ready_ptr, int64_t first, int64_t last, c10::optional<at::Tensor> epoch, c10::optional<at::Tensor> tail_src,
+                    c10::optional<at::Tensor> tail_dst) {
+    TORCH_CHECK(ready_ptr == 0 || (epoch.has_value() && epoch->defined() && epoch->scalar_type() == at::kInt), "epoch must be an int32 device tensor");
+    const float* src = ptr_or_null<const float>(tail_src);
+    float* dst = ptr_or_null<float>(tail_dst);
+    const long long n = (src && dst) ? (long long)tail_dst->numel() : 0;
+    TORCH_CHECK(!(src && dst) || tail_src->numel() == tail_dst->numel(), "acquire_slices: tail size mismatch");
+    check(rlr::launch_acquire_slices(reinterpret_cast<const uint32_t*>(ready_ptr), (int)first, (int)last,
+                                     ready_ptr ? reinterpret_cast<const uint32_t*>(epoch->data_ptr()) : nullptr, src, dst, n, cur_stream()),
+          "acquire_slices");
 }
 
 void update_sqnorm(at::Tensor w_agent_ptrs, int64_t w_global_ptr, int64_t n, at::Tensor out) {
@@ -89,6 +104,25 @@ void gather_normalize(at::Tensor data, at::Tensor idx, c10::optional<at::Tensor>
                                        ptr_or_null<const int64_t>(targets), out.data_ptr(), out_kind,
                                        ptr_or_null<int64_t>(out_labels), (int)B, H, W, C, (int)c_pad, nchw ? 1 : 0, mu, sd,
                                        cur_stream()), "gather_normalize");
+}
+
+// gather + normalise + im2col: A[B*Ho*Wo][64] (bf16) for a k x k / pad stem convolution over data[N,H,W,C]  (C*k*k <= 64)
+void gather_im2col(at::Tensor data, at::Tensor idx, c10::optional<at::Tensor> cursor, c10::optional<at::Tensor> targets, at::Tensor A,
+                   c10::optional<at::Tensor> out_labels, int64_t B, int64_t k, int64_t pad, std::vector<double> mean, std::vector<double> stdv) {
+    CHECK_CUDA(data); CHECK_CUDA(idx); CHECK_CUDA(A);
+    TORCH_CHECK(data.dim() == 4 && idx.scalar_type() == at::kLong && A.scalar_type() == at::kBFloat16);
+    const int H = data.size(1), W = data.size(2), C = data.size(3);
+    TORCH_CHECK((int)mean.size() == C && (int)stdv.size() == C && C * k * k <= 64);
+    const int in_is_float = data.scalar_type() == at::kFloat;
+    TORCH_CHECK(in_is_float || data.scalar_type() == at::kByte, "dataset must be uint8 or float32");
+    const int64_t Ho = H + 2 * pad - k + 1, Wo = W + 2 * pad - k + 1;
+    TORCH_CHECK(A.numel() >= B * Ho * Wo * 64, "A too small");
+    float mu[4], sd[4];
+    for (int c = 0; c < C; ++c) { mu[c] = (float)mean[c]; sd[c] = (float)stdv[c]; }
+    c10::cuda::CUDAGuard guard(data.device());
+    check(rlr::launch_gather_im2col(data.data_ptr(), in_is_float, idx.data_ptr<int64_t>(), ptr_or_null<const int>(cursor),
+                                    ptr_or_null<const int64_t>(targets), reinterpret_cast<__nv_bfloat16*>(A.data_ptr()),
+                                    ptr_or_null<int64_t>(out_labels), (int)B, H, W, C, (int)k, (int)pad, mu, sd, cur_stream()), "gather_im2col");
 }
 
 void stamp_pixels(at::Tensor data, at::Tensor sel, at::Tensor rows, at::Tensor cols, at::Tensor vals, int64_t mode) {
@@ -155,7 +189,7 @@ void sqnorm(at::Tensor x, at::Tensor out) {
 
 void sgd_step(at::Tensor w, at::Tensor g, at::Tensor m, c10::optional<at::Tensor> w0, c10::optional<at::Tensor> w_bf16,
               double lr, double momentum, double max_grad_norm, c10::optional<at::Tensor> g_sqnorm,
-              c10::optional<at::Tensor> d_sqnorm, int64_t n_pgd) {
+              c10::optional<at::Tensor> d_sqnorm, int64_t n_pgd, c10::optional<at::Tensor> w_in) {
     CHECK_CUDA(w); CHECK_CUDA(g); CHECK_CUDA(m);
     TORCH_CHECK(w.numel() == g.numel() && w.numel() == m.numel());
     TORCH_CHECK(!(d_sqnorm.has_value() && d_sqnorm->defined()) || (w0.has_value() && w0->defined()), "PGD needs w0");
@@ -163,7 +197,7 @@ void sgd_step(at::Tensor w, at::Tensor g, at::Tensor m, c10::optional<at::Tensor
     check(rlr::launch_sgd_step(w.data_ptr<float>(), g.data_ptr<float>(), m.data_ptr<float>(), ptr_or_null<const float>(w0),
                                ptr_or_null<__nv_bfloat16>(w_bf16), w.numel(), (float)lr, (float)momentum,
                                (float)max_grad_norm, ptr_or_null<const double>(g_sqnorm), ptr_or_null<double>(d_sqnorm),
-                               num_sms(), cur_stream(), n_pgd), "sgd_step");
+                               num_sms(), cur_stream(), n_pgd, ptr_or_null<const float>(w_in)), "sgd_step");
 }
 
 void pgd_project(at::Tensor w, at::Tensor w0, c10::optional<at::Tensor> w_bf16, double clip, at::Tensor d_sqnorm, int64_t n_pgd) {
@@ -233,9 +267,16 @@ void register_gemm_bindings(py::module_& m);  // gemm_binding.cpp
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.doc() = "b200-robust-fl sm_100a kernels";
-    m.def("fused_aggregate", &fused_aggregate);
+    m.def("fused_aggregate", &fused_aggregate, py::arg("w_agent_ptrs"), py::arg("weights"), py::arg("scales"), py::arg("total_weight"),
+          py::arg("w_global_ptr"), py::arg("out_ptrs"), py::arg("out_bf16_ptrs"), py::arg("use_multimem"), py::arg("begin"), py::arg("end"),
+          py::arg("n_vote"), py::arg("mode"), py::arg("theta"), py::arg("server_lr"), py::arg("noise_std"), py::arg("seed"),
+          py::arg("noise_stream"), py::arg("flipped"), py::arg("flag_ptrs"), py::arg("local_sync"), py::arg("rank"), py::arg("world"),
+          py::arg("epoch"), py::arg("handoff") = false);
+    m.def("aggregate_max_agents", &rlr::aggregate_max_agents);
+    m.def("acquire_slices", &acquire_slices);
     m.def("update_sqnorm", &update_sqnorm);
     m.def("gather_normalize", &gather_normalize);
+    m.def("gather_im2col", &gather_im2col);
     m.def("stamp_pixels", &stamp_pixels);
     m.def("advance_cursor", &advance_cursor, py::arg("cursor"), py::arg("delta"), py::arg("step") = py::none());
     m.def("memset_zero", &memset_zero);
@@ -244,7 +285,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("round_init", &round_init);
     m.def("sqnorm", &sqnorm);
     m.def("sgd_step", &sgd_step, py::arg("w"), py::arg("g"), py::arg("m"), py::arg("w0"), py::arg("w_bf16"), py::arg("lr"),
-          py::arg("momentum"), py::arg("max_grad_norm"), py::arg("g_sqnorm"), py::arg("d_sqnorm"), py::arg("n_pgd") = 0);
+          py::arg("momentum"), py::arg("max_grad_norm"), py::arg("g_sqnorm"), py::arg("d_sqnorm"), py::arg("n_pgd") = 0, py::arg("w_in") = py::none());
     m.def("pgd_project", &pgd_project, py::arg("w"), py::arg("w0"), py::arg("w_bf16"), py::arg("clip"), py::arg("d_sqnorm"),
           py::arg("n_pgd") = 0);
     m.def("softmax_xent", &softmax_xent);

@@ -43,6 +43,110 @@ __global__ void gather_normalize_kernel(const TIn* __restrict__ data, const int6
     }
 }
 
+// Padded NHWC output (c_pad % 8 == 0, bf16): c_pad/8 threads per pixel, one 16-byte store each -> fully coalesced rows.
+template <typename TIn>
+__global__ void __launch_bounds__(256) gather_normalize_padded_kernel(const TIn* __restrict__ data, const int64_t* __restrict__ idx,
+                                                                        const int* __restrict__ cursor, const int64_t* __restrict__ targets,
+                                                                        __nv_bfloat16* __restrict__ out, int64_t* __restrict__ out_labels, int B,
+                                                                        int HW, int C, int c_pad, float4 mean, float4 inv_std, float in_scale) {
+    const int cpp = c_pad >> 3;                                  // chunks per pixel
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)B * HW * cpp) return;
+    const long long pix = t / cpp;
+    const int chunk = (int)(t - pix * cpp);
+    const int b = (int)(pix / HW), px = (int)(pix - (long long)b * HW);
+    const int64_t src = idx[(cursor ? *cursor : 0) + b];
+    if (px == 0 && chunk == 0 && out_labels) out_labels[b] = targets[src];
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (chunk == 0) {
+        const TIn* in = data + (src * HW + px) * C;
+        const float mu[4] = {mean.x, mean.y, mean.z, mean.w};
+        const float is[4] = {inv_std.x, inv_std.y, inv_std.z, inv_std.w};
+        float f[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int c = 0; c < C; ++c) f[c] = ((float)in[c] * in_scale - mu[c]) * is[c];
+        v.x = pack_bf16x2(f[0], f[1]); v.y = pack_bf16x2(f[2], f[3]);
+    }
+    *reinterpret_cast<uint4*>(out + pix * c_pad + chunk * 8) = v;
+}
+
+// Gather + normalise + im2col for tiny-K first layers (C*k*k <= 64): row m = (b, ho, wo) of A[B*Ho*Wo][64] holds the k x k x C patch
+// of the NORMALISED image around output pixel (ho, wo) in (tap, channel) order -- the K-major operand of the stem convolution as a
+// plain 64-deep GEMM -- with zeros for padding pixels and for columns >= k*k*C.  Eight threads per row, one 16-byte store each.
+// Replaces batch assembly (src/utils.py:52-54) + the first layer's implicit im2col (src/models.py:23,48) in one pass over the raw images.
+// One block per (image b, output row ho): the k input rows that output row needs are normalised ONCE into shared memory (zero
+// border included), then every thread assembles one 16-byte chunk of one im2col row from shared memory -- the global side is k
+// coalesced row reads per block and fully coalesced 128-byte row writes (a first version gathered bytes straight from global
+// memory: 67 us per 256-image batch, L1-wavefront bound; this one streams at the store rate).
+// CT / KT > 0: channel count / filter size known at compile time (index arithmetic becomes multiply-shift); 0 = run-time values.
+template <typename TIn, int CT, int KT>
+__global__ void __launch_bounds__(256) gather_im2col_kernel(const TIn* __restrict__ data, const int64_t* __restrict__ idx,
+                                                              const int* __restrict__ cursor, const int64_t* __restrict__ targets,
+                                                              __nv_bfloat16* __restrict__ A, int64_t* __restrict__ out_labels, int B, int H, int W,
+                                                              int C_rt, int k_rt, int pad, int Ho, int Wo, float4 mean, float4 inv_std, float in_scale) {
+    extern __shared__ float tile[];                               // [k][W + 2 pad][C] normalised input rows, zero outside the image
+    const int C = CT > 0 ? CT : C_rt, k = KT > 0 ? KT : k_rt;
+    const int ho = blockIdx.x, b = blockIdx.y;
+    const int Wp = W + 2 * pad;
+    const int64_t src = idx[(cursor ? *cursor : 0) + b];
+    if (ho == 0 && threadIdx.x == 0 && out_labels) out_labels[b] = targets[src];
+    const float mu[4] = {mean.x, mean.y, mean.z, mean.w};
+    const float is[4] = {inv_std.x, inv_std.y, inv_std.z, inv_std.w};
+    const TIn* img = data + src * (int64_t)H * W * C;
+    for (int i = threadIdx.x; i < k * Wp * C; i += blockDim.x) {
+        const int dy = i / (Wp * C), r = i - dy * (Wp * C);
+        const int wp = r / C, ch = r - wp * C;
+        const int hh = ho + dy - pad, ww = wp - pad;
+        float v = 0.f;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
+            const float m = ch == 0 ? mu[0] : ch == 1 ? mu[1] : ch == 2 ? mu[2] : mu[3];
+            const float s_ = ch == 0 ? is[0] : ch == 1 ? is[1] : ch == 2 ? is[2] : is[3];
+            v = ((float)img[(hh * W + ww) * C + ch] * in_scale - m) * s_;
+        }
+        tile[i] = v;
+    }
+    __syncthreads();
+    const int kvalid = k * k * C;
+    for (int t = threadIdx.x; t < Wo * 8; t += blockDim.x) {
+        const int wo = t >> 3, chunk = t & 7;
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int kk = chunk * 8 + j;
+            f[j] = 0.f;
+            if (kk < kvalid) {
+                const int tap = kk / C, ch = kk - tap * C;
+                const int dy = tap / k, dx = tap - dy * k;
+                f[j] = tile[(dy * Wp + wo + dx) * C + ch];
+            }
+        }
+        *reinterpret_cast<uint4*>(A + (((int64_t)b * Ho + ho) * Wo + wo) * 64 + chunk * 8) =
+            make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+    }
+}
+
+cudaError_t launch_gather_im2col(const void* data, int in_is_float, const int64_t* idx, const int* cursor, const int64_t* targets,
+                                 __nv_bfloat16* A, int64_t* out_labels, int B, int H, int W, int C, int k, int pad, const float* mean,
+                                 const float* stdv, cudaStream_t st) {
+    if (C > 4 || B <= 0 || k * k * C > 64) return cudaErrorInvalidValue;
+    float mu[4] = {0, 0, 0, 0}, is[4] = {1, 1, 1, 1};
+    for (int c = 0; c < C; ++c) { mu[c] = mean[c]; is[c] = 1.0f / stdv[c]; }
+    const float4 m4 = make_float4(mu[0], mu[1], mu[2], mu[3]), s4 = make_float4(is[0], is[1], is[2], is[3]);
+    const int Ho = H + 2 * pad - k + 1, Wo = W + 2 * pad - k + 1;
+    const dim3 grid(Ho, B);
+    const size_t smem = (size_t)k * (W + 2 * pad) * C * sizeof(float);
+    if (smem > 40 * 1024) return cudaErrorInvalidValue;
+    const int threads = Wo * 8 >= 256 ? 256 : ((Wo * 8 + 31) / 32) * 32;
+#define RLR_GI(TI, CT, KT, SC) gather_im2col_kernel<TI, CT, KT><<<grid, threads, smem, st>>>((const TI*)data, idx, cursor, targets, A, out_labels, B, H, W, C, k, pad, Ho, Wo, m4, s4, SC)
+    if (in_is_float) {
+        if (C == 1 && k == 3) RLR_GI(float, 1, 3, 1.0f); else if (C == 3 && k == 3) RLR_GI(float, 3, 3, 1.0f); else RLR_GI(float, 0, 0, 1.0f);
+    } else {
+        if (C == 1 && k == 3) RLR_GI(uint8_t, 1, 3, 1.0f / 255.0f); else if (C == 3 && k == 3) RLR_GI(uint8_t, 3, 3, 1.0f / 255.0f);
+        else RLR_GI(uint8_t, 0, 0, 1.0f / 255.0f);
+    }
+#undef RLR_GI
+    return cudaGetLastError();
+}
+
 cudaError_t launch_gather_normalize(const void* data, int in_is_float, const int64_t* idx, const int* cursor,
                                     const int64_t* targets, void* out, int out_kind, int64_t* out_labels, int B, int H,
                                     int W, int C, int c_pad, int nchw, const float* mean, const float* stdv,
@@ -53,6 +157,13 @@ cudaError_t launch_gather_normalize(const void* data, int in_is_float, const int
     const float4 m4 = make_float4(mu[0], mu[1], mu[2], mu[3]), s4 = make_float4(is[0], is[1], is[2], is[3]);
     const int HW = H * W, total = B * HW, threads = 256, blocks = (total + threads - 1) / threads;
     const float sc = in_is_float ? 1.0f : (1.0f / 255.0f);
+    if (!nchw && out_kind == 1 && c_pad > C && c_pad % 8 == 0) {      // channel-padded bf16 NHWC (stem input of the tcgen05 conv)
+        const long long tot = (long long)total * (c_pad / 8);
+        const int nb = (int)((tot + 255) / 256);
+        if (in_is_float) gather_normalize_padded_kernel<float><<<nb, 256, 0, st>>>((const float*)data, idx, cursor, targets, (__nv_bfloat16*)out, out_labels, B, HW, C, c_pad, m4, s4, sc);
+        else gather_normalize_padded_kernel<uint8_t><<<nb, 256, 0, st>>>((const uint8_t*)data, idx, cursor, targets, (__nv_bfloat16*)out, out_labels, B, HW, C, c_pad, m4, s4, sc);
+        return cudaGetLastError();
+    }
 #define RLR_GN(TI, TO)                                                                                          \
     gather_normalize_kernel<TI, TO><<<blocks, threads, 0, st>>>((const TI*)data, idx, cursor, targets, (TO*)out, \
                                                                  out_labels, B, HW, C, c_pad, nchw, m4, s4, sc)
@@ -80,16 +191,21 @@ cudaError_t launch_advance_cursor(int* cursor, int delta, long long* step, cudaS
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) pad_rows_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst,
                                                          long long R, int K, int Kp) {
-    const long long n = R * Kp;
+    // one thread per 8 output columns (Kp % 8 == 0): 16-byte stores; the <= K valid columns of a chunk are gathered one by one
+    const int cpr = Kp >> 3;
+    const long long n = R * cpr;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const long long r = i / Kp;
-        const int c = (int)(i - r * Kp);
-        dst[i] = c < K ? src[r * K + c] : __float2bfloat16(0.f);
+        const long long r = i / cpr;
+        const int c0 = (int)(i - r * cpr) * 8;
+        uint32_t h[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) h[j] = (c0 + j < K) ? (uint32_t)__bfloat16_as_ushort(src[r * K + c0 + j]) : 0u;
+        *reinterpret_cast<uint4*>(dst + r * Kp + c0) = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
     }
 }
 cudaError_t launch_pad_rows(const __nv_bfloat16* src, __nv_bfloat16* dst, long long R, int K, int Kp, int num_sms, cudaStream_t st) {
-    if (K > Kp || R <= 0) return cudaErrorInvalidValue;
-    const long long want = (R * Kp + 255) / 256;
+    if (K > Kp || R <= 0 || (Kp & 7)) return cudaErrorInvalidValue;
+    const long long want = (R * (Kp >> 3) + 255) / 256;
     const int grid = (int)(want > (long long)num_sms * 8 ? (long long)num_sms * 8 : want);
     pad_rows_kernel<<<grid, 256, 0, st>>>(src, dst, R, K, Kp);
     return cudaGetLastError();
@@ -189,7 +305,12 @@ __global__ void __launch_bounds__(256) sgd_step_kernel(float* __restrict__ w, co
                                                          float* __restrict__ m, const float* __restrict__ w0,
                                                          __nv_bfloat16* __restrict__ wb, long long n4, float lr,
                                                          float momentum, float max_grad_norm,
-                                                         const double* __restrict__ g_sqnorm, double* d_sqnorm, long long n4_pgd) {
+                                                         const double* __restrict__ g_sqnorm, double* d_sqnorm, long long n4_pgd,
+                                                         const float* __restrict__ w_in, int first) {
+    // first = 1: first local step of a round, fused with the round hand-off -- parameters are read from the broadcast buffer w_in
+    // (= the round's global parameters) and the momentum is taken as zero (fresh optimizer every round, src/agent.py:37-38), so no
+    // separate "w <- w_global, m <- 0" pass exists.  Coordinates >= n4_pgd (BatchNorm running statistics, already updated in w by
+    // this step's forward pass) keep their value.
     __shared__ double scratch[32];
     float coef = 1.0f;
     if (max_grad_norm > 0.f && g_sqnorm) {
@@ -198,7 +319,9 @@ __global__ void __launch_bounds__(256) sgd_step_kernel(float* __restrict__ w, co
     }
     double dacc = 0.0;
     for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (long long)gridDim.x * blockDim.x) {
-        const float4 gv = ld_f4(g + 4 * q), mv = ld_f4(m + 4 * q), wv = ld_f4(w + 4 * q);
+        if (first && q >= n4_pgd) { st_f4(m + 4 * q, make_float4(0.f, 0.f, 0.f, 0.f)); continue; }
+        const float4 gv = ld_f4(g + 4 * q), mv = first ? make_float4(0.f, 0.f, 0.f, 0.f) : ld_f4(m + 4 * q),
+                     wv = ld_f4((first ? w_in : w) + 4 * q);
         float4 mn, wn;
         mn.x = momentum * mv.x + coef * gv.x; mn.y = momentum * mv.y + coef * gv.y;
         mn.z = momentum * mv.z + coef * gv.z; mn.w = momentum * mv.w + coef * gv.w;
@@ -224,11 +347,11 @@ __global__ void __launch_bounds__(256) sgd_step_kernel(float* __restrict__ w, co
 }
 cudaError_t launch_sgd_step(float* w, const float* g, float* m, const float* w0, __nv_bfloat16* w_bf16, long long n,
                             float lr, float momentum, float max_grad_norm, const double* g_sqnorm, double* d_sqnorm,
-                            int num_sms, cudaStream_t st, long long n_pgd) {
+                            int num_sms, cudaStream_t st, long long n_pgd, const float* w_in) {
     if ((n & 3) || (n_pgd & 3)) return cudaErrorInvalidValue;
     if (n_pgd <= 0 || n_pgd > n) n_pgd = n;
     sgd_step_kernel<<<grid_for(n / 4, 256, num_sms, 4), 256, 0, st>>>(w, g, m, w0, w_bf16, n / 4, lr, momentum,
-                                                                       max_grad_norm, g_sqnorm, d_sqnorm, n_pgd / 4);
+                                                                       max_grad_norm, g_sqnorm, d_sqnorm, n_pgd / 4, w_in, w_in ? 1 : 0);
     return cudaGetLastError();
 }
 

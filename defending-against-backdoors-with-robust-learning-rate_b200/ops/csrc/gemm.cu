@@ -65,6 +65,8 @@ umma_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile_m = blockIdx.x, tile_n = blockIdx.y;
+    long long* dbg = p.dbg ? p.dbg + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
+    if (dbg && threadIdx.x == 0) { dbg[0] = (long long)gtimer(); uint32_t sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); dbg[7] = sm; }
 
     // ---- tile origin -------------------------------------------------------------------------------------------------
     int n0 = 0, h0 = 0, w0 = 0;
@@ -104,9 +106,35 @@ umma_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const uint32_t tmem_acc = tail->tmem_base;
     pdl_wait();        // everything above touched only parameters, shared memory and TMEM
     pdl_trigger();
+    if (dbg && threadIdx.x == 0) dbg[1] = (long long)gtimer();
 
     if (warp == 0) {
         // ================================ TMA producer =====================================================================
+        if (p.b_src) {
+            // stem GEMM (one k-block): the whole warp gathers the B tile from the un-padded filter.  First acquire the broadcast-ready
+            // words of the slices that hold it: the filter may still be in flight from the other GPUs' aggregation kernels.
+            if (p.wait_flags) {
+                const uint32_t epoch = *p.wait_epoch;
+                for (int r = p.wait_lo + lane; r <= p.wait_hi; r += 32)
+                    while ((int32_t)(ld_acquire_sys(p.wait_flags + r) - epoch) < 0) { __nanosleep(32); }
+                __syncwarp();
+            }
+            uint8_t* sb0 = smem + Cfg::kABytes;                      // stage 0
+            for (int idx = lane; idx < BN * 8; idx += 32) {
+                const int r = idx >> 3, c = idx & 7, n = tile_n * BN + r;
+                uint32_t h[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int col = c * 8 + j;
+                    h[j] = (n < p.N && col < p.b_kvalid) ? (uint32_t)__bfloat16_as_ushort(p.b_src[(size_t)n * p.b_ld + col]) : 0u;
+                }
+                // 128-byte swizzle of a K-major tile: 16-byte chunk c of row r lives at chunk (c ^ (r & 7)) of that row
+                *reinterpret_cast<uint4*>(sb0 + r * 128 + ((c ^ (r & 7)) << 4)) =
+                    make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes above -> tensor-core (async proxy) reads
+            __syncwarp();
+        }
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
@@ -114,7 +142,7 @@ umma_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 mbar_wait(&tail->empty[stage], phase ^ 1);
                 uint8_t* sa = smem + stage * Cfg::kStageBytes;
                 uint8_t* sb = sa + Cfg::kABytes;
-                mbar_expect_tx(&tail->full[stage], Cfg::kStageBytes);
+                mbar_expect_tx(&tail->full[stage], p.b_src ? Cfg::kABytes : Cfg::kStageBytes);
                 if (p.mode == 1) {
                     const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
                     tma_load_4d(&tmA, &tail->full[stage], sa, cb * BK, w0 * p.in_stride + p.dw[tap], h0 * p.in_stride + p.dh[tap],
@@ -122,7 +150,9 @@ umma_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 } else {
                     tma_load_2d(&tmA, &tail->full[stage], sa, kb * BK, tile_m * BM);
                 }
-                if (kBMN) {
+                if (p.b_src) {
+                    // B tile already written by the warp above
+                } else if (kBMN) {
                     // data gradient: B[k = co][n = ci] is a 64 x 64 box of the ORIGINAL filter W[co][tap][ci] (ci contiguous ->
                     // MN-major operand); one box per 64-wide ci group.  No transposed filter copy is ever materialised.
                     const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
@@ -131,6 +161,7 @@ umma_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 } else {
                     tma_load_2d(&tmB, &tail->full[stage], sb, kb * BK, tile_n * BN);
                 }
+                if (dbg && kb == 0) dbg[2] = (long long)gtimer();
                 if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
             }
         }
@@ -143,6 +174,7 @@ umma_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             for (int kb = 0; kb < p.num_kb; ++kb) {
                 mbar_wait(&tail->full[stage], phase);
                 tc_fence_after();
+                if (dbg && kb == 0) dbg[3] = (long long)gtimer();
                 const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
                 const uint32_t sb = sa + Cfg::kABytes;
 #pragma unroll
@@ -156,6 +188,7 @@ umma_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
             }
             umma_commit(&tail->tmem_full);          // accumulator complete
+            if (dbg) dbg[4] = (long long)gtimer();
         }
     } else {
         // ================================ epilogue (4 warps, 128 threads) =======================================================
@@ -164,6 +197,7 @@ umma_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         const int row = lane_base + lane;                // tile row held by this thread
         mbar_wait(&tail->tmem_full, 0);
         tc_fence_after();
+        if (dbg && et == 0) dbg[5] = (long long)gtimer();
         uint8_t* staging = smem;                         // operand ring is idle now: reuse it
         const int col0 = tile_n * BN;
         float* red = reinterpret_cast<float*>(staging + Cfg::kStagingBytes);   // [2][BN] per-tile column sums
@@ -246,6 +280,7 @@ umma_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     // ---- teardown ----------------------------------------------------------------------------------------------------------
     tc_fence_before();
     __syncthreads();
+    if (dbg && threadIdx.x == 0) dbg[6] = (long long)gtimer();
     if (warp == 2) tmem_dealloc(tmem_acc, BN);
 }
 
@@ -321,9 +356,11 @@ static cudaError_t launch_bn_occ3(const CUtensorMap& tmA, const CUtensorMap& tmB
 
 // gemm_2cta.cu (opt-in, RLR_CONV_2CTA=1): CTA pairs, tcgen05.mma.cta_group::2 with M = 256, half of the B tile per CTA
 template <int BN>
-cudaError_t launch_2cta_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, int m_tiles, cudaStream_t st);
+cudaError_t launch_2cta_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, int m_tiles, cudaStream_t st, int deep);
+// 0 off | 1 pairs with two CTAs per SM (96 KB rings) | 2 deep variant: one CTA per SM with a 192 KB ring whenever the grid fits in one wave
 static int g_2cta = -1;
-void set_conv_2cta(int on) { g_2cta = on ? 1 : 0; }
+static int g_pair_min_ctas = -1;
+void set_conv_2cta(int on) { g_2cta = on < 0 ? 0 : (on > 2 ? 2 : on); }
 static int sm_count() {
     static const int sms = [] {
         int dev = 0, n = 0;
@@ -335,13 +372,23 @@ static int sm_count() {
 // tile width of the CTA-pair kernel for an M-tiles x N problem, 0 = use the single-CTA kernels (flag off, shape not eligible, or
 // too few pairs to cover the SMs)
 static int pair_bn(int m_tiles, int N, bool eligible) {
-    if (g_2cta < 0) { const char* e = getenv("RLR_CONV_2CTA"); g_2cta = (e && atoi(e) > 0) ? 1 : 0; }
+    if (g_2cta < 0) { const char* e = getenv("RLR_CONV_2CTA"); set_conv_2cta(e ? atoi(e) : 0); }
+    if (g_pair_min_ctas < 0) { const char* e = getenv("RLR_PAIR_MIN_CTAS"); g_pair_min_ctas = e ? atoi(e) : 96; }
     if (!g_2cta || !eligible || N % 128) return 0;
     const int ctas_m = (m_tiles + 1) / 2 * 2;
+    // N = 256 tiles halve the bytes per FLOP again (A tile shared by 256 output channels): worth it even when the pairs leave some SMs idle
     int bn = (N % 256 == 0) ? 256 : 128;
-    if (bn == 256 && ctas_m * (N / 256) < sm_count()) bn = 128;
-    if (ctas_m * (N / bn) < sm_count()) return 0;
+    if (bn == 256 && ctas_m * (N / 256) < g_pair_min_ctas) bn = 128;
+    if (ctas_m * (N / bn) < g_pair_min_ctas) return 0;
     return bn;
+}
+static int pair_deep(int m_tiles, int N, int bn) {
+    const int ctas = (m_tiles + 1) / 2 * 2 * (N / bn);
+    return (g_2cta == 2 && ctas <= sm_count()) ? 1 : 0;
+}
+static cudaError_t launch_pair(int bn2, const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, int m_tiles, cudaStream_t st) {
+    const int deep = pair_deep(m_tiles, p.N, bn2);
+    return bn2 == 256 ? launch_2cta_bn<256>(tmA, tmB, p, m_tiles, st, deep) : launch_2cta_bn<128>(tmA, tmB, p, m_tiles, st, deep);
 }
 
 static int g_persistent = -1;   // -1: take RLR_PERSISTENT_CONV from the environment on first use
@@ -358,10 +405,16 @@ static int persistent_sms() {
     return sms;
 }
 
+static long long* g_trace = nullptr;
+void set_conv_trace(long long* buf) { g_trace = buf; }
+long long* conv_trace_buf() { return g_trace; }
+
 template <int BN>
-static cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, int m_tiles, cudaStream_t st) {
+static cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p_in, int m_tiles, cudaStream_t st) {
     using Cfg = TileCfg<BN>;
-    if (!p.stats && persistent_sms() > 0 && m_tiles * ((p.N + BN - 1) / BN) > persistent_sms())
+    ConvGemmParams p = p_in;
+    p.dbg = g_trace;
+    if (!p.stats && !p.b_src && persistent_sms() > 0 && m_tiles * ((p.N + BN - 1) / BN) > persistent_sms())
         return launch_persistent_bn<BN>(tmA, tmB, p, m_tiles, persistent_sms(), st);
     if (!p.stats && conv_occ3() >= (BN == 64 ? 1 : 2)) return launch_bn_occ3<BN>(tmA, tmB, p, m_tiles, st);
     static bool configured = false;
@@ -404,8 +457,32 @@ cudaError_t launch_gemm_bf16(const void* A, const void* B, void* out, int M, int
     ConvGemmParams p{};
     p.M = M; p.N = N; p.num_kb = K / BK; p.mode = 0; p.in_stride = 1; p.out_stride = 1;
     p.out = out; p.ldc = ldc; p.bias = bias; p.stats = stats; p.relu = relu; p.accumulate = accumulate;
-    if (bn2) return bn2 == 256 ? launch_2cta_bn<256>(tmA, tmB, p, m_tiles, st) : launch_2cta_bn<128>(tmA, tmB, p, m_tiles, st);
+    if (bn2) return launch_pair(bn2, tmA, tmB, p, m_tiles, st);
     return bn == 128 ? launch_bn<128>(tmA, tmB, p, m_tiles, st) : launch_bn<64>(tmA, tmB, p, m_tiles, st);
+}
+
+// Stem GEMM (tiny-K first layer): A is the im2col matrix [M][64] (gather_im2col), W the un-padded bf16 filter [N][ldw] with kvalid <= 64
+// valid columns, read by the producer warp (ConvGemmParams::b_src) -- from the trainer's own shadow, or straight from the multicast
+// broadcast buffer behind the ready flags.
+cudaError_t launch_stem_gemm_bf16(const void* A, const void* W, void* out, int M, int N, int kvalid, int ldw, const float* bias, int relu,
+                                  float* stats, const uint32_t* wait_flags, int wait_lo, int wait_hi, const uint32_t* wait_epoch,
+                                  cudaStream_t st) {
+    if (N % 8 || M <= 0 || kvalid < 1 || kvalid > BK || ldw < kvalid) return cudaErrorInvalidValue;
+    if (wait_flags && (!wait_epoch || wait_lo > wait_hi || wait_lo < 0)) return cudaErrorInvalidValue;
+    const int m_tiles = (M + BM - 1) / BM;
+    const int bn = pick_bn(N);
+    CUtensorMap tmA;
+    {
+        const uint64_t d[2] = {(uint64_t)BK, (uint64_t)M}, s[1] = {(uint64_t)BK * 2};
+        const uint32_t b[2] = {BK, BM};
+        RLR_CUDA_CHECK(make_tmap_bf16(&tmA, A, 2, d, s, b));
+    }
+    ConvGemmParams p{};
+    p.M = M; p.N = N; p.num_kb = 1; p.mode = 0; p.in_stride = 1; p.out_stride = 1;
+    p.out = out; p.ldc = N; p.bias = bias; p.stats = stats; p.relu = relu; p.accumulate = 0;
+    p.b_src = reinterpret_cast<const __nv_bfloat16*>(W); p.b_ld = ldw; p.b_kvalid = kvalid;
+    p.wait_flags = wait_flags; p.wait_lo = wait_lo; p.wait_hi = wait_hi; p.wait_epoch = wait_epoch;
+    return bn == 128 ? launch_bn<128>(tmA, tmA, p, m_tiles, st) : launch_bn<64>(tmA, tmA, p, m_tiles, st);   // tmB unused: B is gathered by the warp
 }
 
 static int pow2_ceil(int x) { int p = 1; while (p < x) p <<= 1; return p; }
@@ -458,14 +535,14 @@ cudaError_t launch_conv_bf16(const void* x, const void* w, void* out, int NB, in
         const uint32_t b[2] = {64, BK};
         RLR_CUDA_CHECK(make_tmap_bf16(&tmB, w, 2, d, s, b));
         const int bn2 = pair_bn(m_tiles, Cout, true);      // CTA pair: each CTA loads the 64-wide groups of its half of the tile
-        if (bn2) return bn2 == 256 ? launch_2cta_bn<256>(tmA, tmB, p, m_tiles, st) : launch_2cta_bn<128>(tmA, tmB, p, m_tiles, st);
+        if (bn2) return launch_pair(bn2, tmA, tmB, p, m_tiles, st);
     } else {
         const uint64_t K = (uint64_t)ntaps * Cin;
         const uint64_t d[2] = {K, (uint64_t)Cout}, s[1] = {K * 2};
         const int bn2 = pair_bn(m_tiles, Cout, stats == nullptr);
         const uint32_t b[2] = {BK, (uint32_t)(bn2 ? bn2 / 2 : bn)};       // CTA pair: each CTA stages half of the filter tile
         RLR_CUDA_CHECK(make_tmap_bf16(&tmB, w, 2, d, s, b));
-        if (bn2) return bn2 == 256 ? launch_2cta_bn<256>(tmA, tmB, p, m_tiles, st) : launch_2cta_bn<128>(tmA, tmB, p, m_tiles, st);
+        if (bn2) return launch_pair(bn2, tmA, tmB, p, m_tiles, st);
     }
     return bn == 128 ? launch_bn<128>(tmA, tmB, p, m_tiles, st) : launch_bn<64>(tmA, tmB, p, m_tiles, st);
 }

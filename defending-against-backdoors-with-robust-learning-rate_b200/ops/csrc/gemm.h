@@ -26,6 +26,18 @@ struct ConvGemmParams {
     int b_mn;                  // 1: B operand is read MN-major straight from the un-transposed filter (data gradients)
     int wtap[9];               // b_mn: filter tap that k-block tap t multiplies (flipped / parity-selected)
     int wcols;                 // b_mn: columns per filter tap in the 2-D filter view (= Cin of the forward conv)
+    // stem GEMM (tiny-K first layer, mode 0, one k-block): the B tile is NOT loaded by TMA but gathered by the producer warp from the
+    // un-padded bf16 filter b_src[N][b_ld] (b_kvalid <= 64 valid columns, zero beyond) and written in the 128-byte-swizzled operand layout.
+    // With wait_flags the producer first acquires the broadcast-ready words [wait_lo, wait_hi] (>= *wait_epoch): b_src then points into
+    // the NVLS-multicast parameter shadow that the aggregation kernels of ALL GPUs are still filling -- the first local-forward GEMM of
+    // a round starts as soon as the slice holding its filter has landed (broadcast (+) first-GEMM fusion, parallel/fused_agg.py).
+    long long* dbg;            // optional [CTAs][8] timeline (globaltimer ns): entry, setup done, first TMA issued, first data landed,
+                               // all MMAs issued, accumulator complete, epilogue done, SM id  (scripts/trace_conv.py)
+    const __nv_bfloat16* b_src;
+    int b_ld, b_kvalid;
+    const uint32_t* wait_flags;
+    int wait_lo, wait_hi;
+    const uint32_t* wait_epoch;
     void* out;                 // bf16 [M][ldc]
     int ldc;
     const float* bias;         // [N] or null
@@ -35,6 +47,11 @@ struct ConvGemmParams {
 
 cudaError_t launch_gemm_bf16(const void* A, const void* B, void* out, int M, int N, int K, int lda, int ldb, int ldc,
                              const float* bias, int relu, int accumulate, float* stats, cudaStream_t st);
+// stem GEMM: out[M][N] = A[M][64] * pad64(W[N][kvalid])^T (+bias)(relu); W is read un-padded by the producer warp (optionally after
+// acquiring broadcast-ready flags [wait_lo, wait_hi] >= *wait_epoch -- see ConvGemmParams::b_src)
+cudaError_t launch_stem_gemm_bf16(const void* A, const void* W, void* out, int M, int N, int kvalid, int ldw, const float* bias, int relu,
+                                  float* stats, const uint32_t* wait_flags, int wait_lo, int wait_hi, const uint32_t* wait_epoch,
+                                  cudaStream_t st);
 // programmatic dependent launch for the hot kernels (common.cuh: launch_kernel / pdl_wait); default: RLR_PDL env, off
 void set_pdl(int on);
 // gemm_splitk.cu (opt-in): small-M / deep-K GEMM, grid.z CTAs share a tile's k range and add fp32 partials into `ws` ([M][N], zero on
@@ -47,6 +64,9 @@ void set_conv_2cta(int on);
 void set_persistent_conv(int on);
 // three CTAs per SM: level 0 never, 1 (default) for the 64-wide tile, 2 also for the 128-wide tile (RLR_CONV_OCC3 env)
 void set_conv_occ3(int level);
+// per-CTA timeline buffer for the NEXT launches of the generic conv / GEMM kernel (nullptr = off); see ConvGemmParams::dbg
+void set_conv_trace(long long* buf);
+long long* conv_trace_buf();
 cudaError_t launch_conv_bf16(const void* x, const void* w, void* out, int NB, int planes, int Hin, int Win, int Cin, int Ho, int Wo,
                              int Cout, int ldc, int ntaps, const int* dh, const int* dw, const int* dplane, const float* bias,
                              int relu, int accumulate, float* stats, cudaStream_t st, const int* wtap = nullptr, int w_taps_total = 0,

@@ -28,15 +28,18 @@ using namespace umma;
 
 namespace {
 
-constexpr int CBM = 128, CBK = 64, CThreads = 192, CStages = 3;
+constexpr int CBM = 128, CBK = 64, CThreads = 192, CMaxStages = 8;
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;     // shared::cluster address of the same offset in the even (leader) CTA of the pair
 
-template <int BN>
+// kDeep = 0: ~96 KB of operand ring per CTA, two CTAs (of two different pairs) per SM so one's epilogue overlaps the other's main loop;
+// kDeep = 1: the whole shared memory as ONE deep ring (192 KB in flight per SM from a single CTA) -- for grids of at most one CTA per SM
+template <int BN, int kDeep>
 struct CCfg {
     static constexpr int kABytes = CBM * CBK * 2;               // 16 KB: this CTA's 128 rows
     static constexpr int kBBytes = (BN / 2) * CBK * 2;          // this CTA's half of the B tile
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kRingBytes = CStages * kStageBytes;
+    static constexpr int kStages = (kDeep ? 192 : 96) * 1024 / kStageBytes;      // 4 / 3 (BN = 128 / 256), deep: 8 / 6
+    static constexpr int kRingBytes = kStages * kStageBytes;
     static constexpr int kPitch = BN * 2 + 16;
     static constexpr int kStagingBytes = CBM * kPitch;          // aliases the ring once the accumulator is complete
     static_assert(kStagingBytes <= kRingBytes, "staging aliases the operand ring");
@@ -44,8 +47,8 @@ struct CCfg {
 };
 
 struct __align__(8) CShared {
-    uint64_t full[CStages];     // used in the leader CTA only (armed by the leader, completed by both CTAs' TMA loads)
-    uint64_t empty[CStages];    // in both CTAs: one multicast arrival per consumed stage
+    uint64_t full[CMaxStages];  // used in the leader CTA only (armed by the leader, completed by both CTAs' TMA loads)
+    uint64_t empty[CMaxStages]; // in both CTAs: one multicast arrival per consumed stage
     uint64_t tmem_full;         // in both CTAs: accumulator complete
     uint32_t tmem_base;
     uint32_t pad;
@@ -92,10 +95,11 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mas
                  ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
 }
 
-template <int BN, bool kBMN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CThreads, 2)
+template <int BN, bool kBMN, int kDeep>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CThreads, kDeep ? 1 : 2)
 umma_conv_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvGemmParams p) {
-    using Cfg = CCfg<BN>;
+    using Cfg = CCfg<BN, kDeep>;
+    constexpr int CStages = Cfg::kStages;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     CShared* sh = reinterpret_cast<CShared*>(smem + Cfg::kRingBytes);
@@ -103,6 +107,8 @@ umma_conv_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
     const uint32_t cta_rank = cluster_ctarank();        // 0 = leader (even M tile), 1 = peer
     const bool leader = cta_rank == 0;
     const int tile_m = blockIdx.x, tile_n = blockIdx.y; // cluster = M tiles (2i, 2i+1); an odd tail tile is fully masked
+    long long* dbg = p.dbg ? p.dbg + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;   // timeline, see ConvGemmParams::dbg
+    if (dbg && threadIdx.x == 0) { dbg[0] = (long long)gtimer(); uint32_t sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); dbg[7] = sm; }
 
     int n0 = 0, h0 = 0, w0 = 0;
     if (p.mode == 1) {
@@ -136,6 +142,7 @@ umma_conv_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
     const uint32_t tmem_acc = sh->tmem_base;
     pdl_wait();
     pdl_trigger();
+    if (dbg && threadIdx.x == 0) dbg[1] = (long long)gtimer();
 
     if (warp == 0) {
         // ================================ TMA producer (both CTAs) =============================================================
@@ -161,6 +168,7 @@ umma_conv_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
                 } else {
                     tma_load_2d_pair(&tmB, &sh->full[stage], sb, kb * CBK, n_half);
                 }
+                if (dbg && kb == 0) dbg[2] = (long long)gtimer();
                 if (++stage == CStages) { stage = 0; phase ^= 1; }
             }
         }
@@ -173,6 +181,7 @@ umma_conv_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
             for (int kb = 0; kb < p.num_kb; ++kb) {
                 mbar_wait(&sh->full[stage], phase);
                 tc_fence_after();
+                if (dbg && kb == 0) dbg[3] = (long long)gtimer();
                 const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
                 const uint32_t sb = sa + Cfg::kABytes;
 #pragma unroll
@@ -186,6 +195,7 @@ umma_conv_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
                 if (++stage == CStages) { stage = 0; phase ^= 1; }
             }
             umma_commit_pair(&sh->tmem_full, 0x3);             // accumulators complete in both CTAs
+            if (dbg) dbg[4] = (long long)gtimer();
         }
     } else {
         // ================================ epilogue (both CTAs; identical to gemm.cu without statistics) ========================
@@ -194,6 +204,7 @@ umma_conv_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
         const int row = lane_base + lane;
         mbar_wait(&sh->tmem_full, 0);
         tc_fence_after();
+        if (dbg && et == 0) dbg[5] = (long long)gtimer();
         uint8_t* staging = smem;                         // every MMA of the pair has completed: the operand ring is idle
         const int col0 = tile_n * BN;
 #pragma unroll
@@ -251,6 +262,7 @@ umma_conv_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
     // ---- teardown: neither CTA may free TMEM or exit while its partner can still touch it --------------------------------------
     tc_fence_before();
     __syncthreads();
+    if (dbg && threadIdx.x == 0) dbg[6] = (long long)gtimer();
     cluster_sync_all();
     if (warp == 2) tmem_dealloc_2cta(tmem_acc, BN);
 }
@@ -258,20 +270,29 @@ umma_conv_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
 }  // namespace
 
 // tmB must have been encoded with a {64, BN/2} box (K-major B) or the {64, 64} box of the forward filter view (b_mn).  Grid: M tiles rounded up to whole pairs x N tiles.
-template <int BN>
-cudaError_t launch_2cta_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, int m_tiles, cudaStream_t st) {
-    using Cfg = CCfg<BN>;
+template <int BN, int kDeep>
+static cudaError_t launch_2cta_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p_in, int m_tiles, cudaStream_t st) {
+    using Cfg = CCfg<BN, kDeep>;
+    ConvGemmParams p = p_in;
+    p.dbg = conv_trace_buf();
     static bool configured = false;
     if (!configured) {
-        RLR_CUDA_CHECK(cudaFuncSetAttribute(umma_conv_gemm_2cta_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-        RLR_CUDA_CHECK(cudaFuncSetAttribute(umma_conv_gemm_2cta_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        RLR_CUDA_CHECK(cudaFuncSetAttribute(umma_conv_gemm_2cta_kernel<BN, false, kDeep>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        RLR_CUDA_CHECK(cudaFuncSetAttribute(umma_conv_gemm_2cta_kernel<BN, true, kDeep>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         configured = true;
     }
     const dim3 grid((m_tiles + 1) / 2 * 2, (p.N + BN - 1) / BN);
-    if (p.b_mn) return launch_kernel(umma_conv_gemm_2cta_kernel<BN, true>, grid, dim3(CThreads), (size_t)Cfg::kSmemBytes, st, tmA, tmB, p);
-    return launch_kernel(umma_conv_gemm_2cta_kernel<BN, false>, grid, dim3(CThreads), (size_t)Cfg::kSmemBytes, st, tmA, tmB, p);
+    if (p.b_mn) return launch_kernel(umma_conv_gemm_2cta_kernel<BN, true, kDeep>, grid, dim3(CThreads), (size_t)Cfg::kSmemBytes, st, tmA, tmB, p);
+    return launch_kernel(umma_conv_gemm_2cta_kernel<BN, false, kDeep>, grid, dim3(CThreads), (size_t)Cfg::kSmemBytes, st, tmA, tmB, p);
 }
-template cudaError_t launch_2cta_bn<128>(const CUtensorMap&, const CUtensorMap&, const ConvGemmParams&, int, cudaStream_t);
-template cudaError_t launch_2cta_bn<256>(const CUtensorMap&, const CUtensorMap&, const ConvGemmParams&, int, cudaStream_t);
+
+// tmB must have been encoded with a {64, BN/2} box (K-major B) or the {64, 64} box of the forward filter view (b_mn).  Grid: M tiles rounded
+// up to whole pairs x N tiles.  deep = 1: one CTA per SM with the whole shared memory as operand ring (grids that do not exceed the SM count).
+template <int BN>
+cudaError_t launch_2cta_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, int m_tiles, cudaStream_t st, int deep) {
+    return deep ? launch_2cta_cfg<BN, 1>(tmA, tmB, p, m_tiles, st) : launch_2cta_cfg<BN, 0>(tmA, tmB, p, m_tiles, st);
+}
+template cudaError_t launch_2cta_bn<128>(const CUtensorMap&, const CUtensorMap&, const ConvGemmParams&, int, cudaStream_t, int);
+template cudaError_t launch_2cta_bn<256>(const CUtensorMap&, const CUtensorMap&, const ConvGemmParams&, int, cudaStream_t, int);
 
 }  // namespace rlr

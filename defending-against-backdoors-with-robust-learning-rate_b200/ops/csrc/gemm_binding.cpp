@@ -36,6 +36,19 @@ void gemm_bf16(at::Tensor A, at::Tensor B, at::Tensor out, c10::optional<at::Ten
                                 cur_stream()), "gemm_bf16");
 }
 
+// stem convolution as one 64-deep GEMM: out[M][N] = A[M][64] @ pad64(W[N][kvalid])^T; W is the UN-padded filter, gathered by the kernel's
+// producer warp.  ready_ptr != 0: device address of this rank's broadcast-ready words; the producer acquires words [lo, hi] >= *epoch first
+void stem_gemm_bf16(at::Tensor A, at::Tensor W, at::Tensor out, c10::optional<at::Tensor> bias, bool relu, c10::optional<at::Tensor> stats,
+                    int64_t ready_ptr, int64_t lo, int64_t hi, c10::optional<at::Tensor> epoch) {
+    c10::cuda::CUDAGuard g(A.device());
+    const int M = A.size(0), N = W.size(0), kvalid = W.size(1);
+    TORCH_CHECK(A.dim() == 2 && A.size(1) == 64 && W.dim() == 2 && W.is_contiguous() && out.size(0) == M && out.size(1) == N, "stem_gemm shapes");
+    TORCH_CHECK(ready_ptr == 0 || (epoch.has_value() && epoch->defined() && epoch->scalar_type() == at::kInt), "epoch must be an int32 device tensor");
+    check(rlr::launch_stem_gemm_bf16(bf(A), bf(W), bfm(out), M, N, kvalid, kvalid, opt<const float>(bias), relu, opt<float>(stats),
+                                     reinterpret_cast<const uint32_t*>(ready_ptr), (int)lo, (int)hi,
+                                     ready_ptr ? reinterpret_cast<const uint32_t*>(epoch->data_ptr()) : nullptr, cur_stream()), "stem_gemm_bf16");
+}
+
 // x: [planes*NB, Hin, Win, Cin]; w: [Cout, ntaps*Cin]; out: [NB, Ho, Wo, Cout]
 void conv_bf16(at::Tensor x, at::Tensor w, at::Tensor out, int64_t NB, int64_t planes, std::vector<int64_t> dh, std::vector<int64_t> dw,
                std::vector<int64_t> dplane, c10::optional<at::Tensor> bias, bool relu, bool accumulate, c10::optional<at::Tensor> stats,
@@ -293,10 +306,15 @@ void linear_small_bwd2(at::Tensor x, at::Tensor dy, at::Tensor w, c10::optional<
 void register_gemm_bindings(py::module_& m) {
     m.attr("STAT_SLOTS") = rlr::kStatSlots;
     m.def("set_persistent_conv", [](bool on) { rlr::set_persistent_conv(on ? 1 : 0); });
-    m.def("set_conv_2cta", [](bool on) { rlr::set_conv_2cta(on ? 1 : 0); });
+    m.def("set_conv_2cta", [](int64_t mode) { rlr::set_conv_2cta((int)mode); });   // 0 off | 1 CTA pairs | 2 + deep single-wave variant
     m.def("set_pdl", [](bool on) { rlr::set_pdl(on ? 1 : 0); });
     m.def("set_conv_occ3", [](int64_t level) { rlr::set_conv_occ3((int)level); });
+    m.def("set_conv_trace", [](c10::optional<at::Tensor> buf) {   // int64 [CTAs * 8] timeline buffer for the next generic conv / GEMM launches
+        rlr::set_conv_trace(buf.has_value() && buf->defined() ? reinterpret_cast<long long*>(buf->data_ptr<int64_t>()) : nullptr);
+    });
     m.def("gemm_bf16", &gemm_bf16);
+    m.def("stem_gemm_bf16", &stem_gemm_bf16, py::arg("A"), py::arg("W"), py::arg("out"), py::arg("bias"), py::arg("relu"), py::arg("stats"),
+          py::arg("ready_ptr") = 0, py::arg("lo") = 0, py::arg("hi") = 0, py::arg("epoch") = py::none());
     m.def("gemm_splitk_bf16", &gemm_splitk_bf16);
     m.def("conv_bf16", &conv_bf16);
     m.def("conv_bf16_strided", &conv_bf16_strided);

@@ -30,8 +30,13 @@ struct AggParams {
     uint32_t* local_sync;           // [2] intra-GPU: ready flag, finished-CTA counter
     int rank, world;
     uint32_t epoch;                 // monotonically increasing per call
+    int handoff;                    // 1: publish this rank's slice in the peers' ready words (flag slot 2*world + rank) instead of the barrier-out
 };
 cudaError_t launch_fused_aggregate(const AggParams& p, int num_sms, cudaStream_t st);
+int aggregate_max_agents();         // capacity of the kernel's participant tables
+// consumer side of the hand-off: wait for ready words [first, last] >= epoch (ready may be null), then copy the BatchNorm-statistics tail
+cudaError_t launch_acquire_slices(const uint32_t* ready, int first, int last, const uint32_t* epoch, const float* tail_src, float* tail_dst,
+                                  long long tail_n, cudaStream_t st);
 cudaError_t launch_update_sqnorm(const float* const* w_agents, const float* w_global, long long n, int K, double* out,
                                  int num_sms, cudaStream_t st);
 
@@ -41,6 +46,10 @@ cudaError_t launch_gather_normalize(const void* data, int in_is_float, const int
                                     const int64_t* targets, void* out, int out_kind, int64_t* out_labels, int B, int H,
                                     int W, int C, int c_pad, int nchw, const float* mean, const float* stdv,
                                     cudaStream_t st);
+// gather + normalise + im2col for the stem conv (C*k*k <= 64): A[B*Ho*Wo][64] bf16, (tap, channel) column order, zero padded
+cudaError_t launch_gather_im2col(const void* data, int in_is_float, const int64_t* idx, const int* cursor, const int64_t* targets,
+                                 __nv_bfloat16* A, int64_t* out_labels, int B, int H, int W, int C, int k, int pad, const float* mean,
+                                 const float* stdv, cudaStream_t st);
 cudaError_t launch_stamp_pixels(void* data, int is_float, const int64_t* sel, int S, const int* rows, const int* cols,
                                 const float* vals, int P, int H, int W, int C, int mode, cudaStream_t st);
 cudaError_t launch_advance_cursor(int* cursor, int delta, long long* step /*optional: += 1*/, cudaStream_t st);
@@ -54,7 +63,8 @@ cudaError_t launch_round_init(const float* w_global, float* w_local, __nv_bfloat
 cudaError_t launch_sqnorm(const float* x, long long n, double* out /*accumulates*/, int num_sms, cudaStream_t st);
 cudaError_t launch_sgd_step(float* w, const float* g, float* m, const float* w0, __nv_bfloat16* w_bf16, long long n,
                             float lr, float momentum, float max_grad_norm, const double* g_sqnorm, double* d_sqnorm,
-                            int num_sms, cudaStream_t st, long long n_pgd = 0 /*PGD norm over [0, n_pgd); 0 = n*/);
+                            int num_sms, cudaStream_t st, long long n_pgd = 0 /*PGD norm over [0, n_pgd); 0 = n*/,
+                            const float* w_in = nullptr /*first step of a round: read params from w_in, momentum = 0, keep w[n_pgd:]*/);
 cudaError_t launch_pgd_project(float* w, const float* w0, __nv_bfloat16* w_bf16, long long n, float clip,
                                const double* d_sqnorm, int num_sms, cudaStream_t st, long long n_pgd = 0);
 

@@ -21,25 +21,36 @@ USE_WGRAD_HALO = True   # 3x3/s1/p1, 64 input channels: halo-reuse weight-gradie
 # rows) -- no space_to_depth / depth_to_space passes.  Opt-in until measured on hardware (RLR_STRIDED_TMA=1).
 USE_STRIDED_TMA = bool(int(os.environ.get("RLR_STRIDED_TMA", "0")))
 # Stem convolutions (Cin * k * k <= 64, stride 1): gather the k x k x Cin patch of every output pixel into ONE 64-wide K block
-# (im2col_small) and run the plain tcgen05 GEMM on it, instead of k*k k-blocks of a 64-channel zero-padded input; the weight
-# gradient is a [Cout x 64] GEMM over the same matrix.  Opt-in until measured on hardware (RLR_IM2COL_STEM=1).
-USE_IM2COL_STEM = bool(int(os.environ.get("RLR_IM2COL_STEM", "0")))
+# (im2col_small, or -- in the training step -- directly by the batch-assembly kernel gather_im2col) and run the plain tcgen05 GEMM on
+# it, instead of k*k k-blocks of a 64-channel zero-padded input; the weight gradient is a [Cout x 64] GEMM over the same matrix.
+# Verified on B200 (tests/test_gpu_experimental.py::test_im2col_stem_conv_and_wgrad); RLR_IM2COL_STEM=0 restores the padded conv.
+USE_IM2COL_STEM = bool(int(os.environ.get("RLR_IM2COL_STEM", "1")))
 # BatchNorm(+ReLU, no residual) backward without reading the layer output: the mask is recomputed from x with the forward's own
 # scale/shift expression.  Opt-in until measured on hardware (RLR_BN_RECOMPUTE=1).
-USE_BN_RECOMPUTE = bool(int(os.environ.get("RLR_BN_RECOMPUTE", "0")))
+USE_BN_RECOMPUTE = bool(int(os.environ.get("RLR_BN_RECOMPUTE", "1")))
 # 3x3/s1/p1 convs with 64 input channels: three filter taps per N = 192 MMA with a lane shift-add epilogue (conv_halo3.cu) instead of
 # nine N = 64 MMAs per k-step.  Opt-in until measured on hardware (RLR_HALO3=1).
 USE_HALO3 = bool(int(os.environ.get("RLR_HALO3", "0")))
 # Dense layers with few output tiles and a deep reduction (FMNIST CNN fc1: 256 x 128 x 9216): split-K GEMM with an fp32 workspace
 # (gemm_splitk.cu).  Opt-in until measured on hardware (RLR_SPLITK=1).
-USE_SPLITK = bool(int(os.environ.get("RLR_SPLITK", "0")))
+USE_SPLITK = bool(int(os.environ.get("RLR_SPLITK", "1")))
 # Classifier-head kernels v2 (weights staged in shared memory, weight gradient spread over K/64 x B/16 blocks with float atomics).
 # Opt-in until measured on hardware (RLR_HEAD_V2=1).
-USE_HEAD_V2 = bool(int(os.environ.get("RLR_HEAD_V2", "0")))
+USE_HEAD_V2 = bool(int(os.environ.get("RLR_HEAD_V2", "1")))
 
 
 def _stem_ok(k, stride, cin, cout):
     return USE_IM2COL_STEM and stride == 1 and cin * k * k <= 64 and cout % 8 == 0 and (cout <= 64 or cout % 128 == 0)
+
+
+def stem_geometry(in_shape, a):
+    """(k, pad, Ho, Wo) if the conv with attributes ``a`` on an (H, W, C) input takes the im2col stem path, else None.  The native
+    trainer asks this for its first layer and, if so, lets the batch-assembly kernel write the im2col matrix directly."""
+    h, w, c = in_shape
+    k, s, p = a["k"], a.get("stride", 1), a.get("pad", 0)
+    if not _stem_ok(k, s, c, a["cout"]):
+        return None
+    return k, p, h + 2 * p - k + 1, w + 2 * p - k + 1
 
 
 def _ext():
@@ -101,21 +112,29 @@ def _taps(k, stride, pad):
     return dh, dw, pl
 
 
-def conv2d_fwd_sm100(x, w, bias, y, stride, pad, relu, stats, tag="fwd", zero_stats=True, s2d_epoch=None):
+def conv2d_fwd_sm100(x, w, bias, y, stride, pad, relu, stats, tag="fwd", zero_stats=True, s2d_epoch=None, wait=None):
     """y[B,Ho,Wo,Cout] = conv(x[B,H,W,Cin], w[Cout,k,k,Cin]) (+bias)(ReLU); ``stats`` [STAT_SLOTS,2,Cout] accumulates per-channel
-    sum / sum^2 partials (sum over dim 0 for the totals)."""
+    sum / sum^2 partials (sum over dim 0 for the totals).  ``wait`` = (ready_ptr, lo, hi, epoch_tensor): stem path only -- the GEMM's
+    producer warp acquires the broadcast-ready words [lo, hi] before it reads the filter (``w`` then lives in the multicast shadow)."""
     e = _ext()
-    B, H, W, Cin = x.shape
     Cout, k = w.shape[0], w.shape[1]
+    if x.dim() == 2:      # the batch-assembly kernel already produced the im2col matrix A[B*Ho*Wo][64] (gather_im2col)
+        B, Ho, Wo, Cin = y.shape[0], y.shape[1], y.shape[2], w.shape[3]
+        assert x.shape == (B * Ho * Wo, 64) and _stem_ok(k, stride, Cin, Cout)
+        if stats is not None and zero_stats:
+            _zero(stats)
+        rp, lo, hi, ep = wait if wait is not None else (0, 0, 0, None)
+        # the un-padded filter [Cout][k*k*Cin] is gathered (and zero-padded to K = 64) by the GEMM's producer warp: no padded copy
+        e.stem_gemm_bf16(x, w.reshape(Cout, k * k * Cin), y.view(B * Ho * Wo, Cout), bias, bool(relu), stats, int(rp), int(lo), int(hi), ep)
+        return y
+    B, H, W, Cin = x.shape
     if _stem_ok(k, stride, Cin, Cout):
         Ho, Wo = y.shape[1], y.shape[2]
         A = scratch(("im2col", tag), (B * Ho * Wo, 64), x.dtype, x.device)
         e.im2col_small(x.contiguous(), A, k, pad)
-        wp = scratch(("wstem", tag, w.data_ptr()), (Cout, 64), w.dtype, w.device)
-        e.pad_rows(w.reshape(Cout, k * k * Cin), wp)                                    # [Cout][k*k*Cin] -> [Cout][64], zero tail
         if stats is not None and zero_stats:
             _zero(stats)
-        e.gemm_bf16(A, wp, y.view(B * Ho * Wo, Cout), bias, bool(relu), False, stats)
+        e.stem_gemm_bf16(A, w.reshape(Cout, k * k * Cin), y.view(B * Ho * Wo, Cout), bias, bool(relu), stats, 0, 0, 0, None)
         return y
     if Cin % 64:
         cp = (Cin + 63) // 64 * 64
@@ -228,12 +247,13 @@ def conv2d_wgrad_sm100(x, dy, gw, gb, stride, pad, tag="fwd", zero=True):
     """gw[Cout,k,k,Cin] (fp32) = sum over pixels of dy (x) x  (+ gb = sum dy).  Reuses the channel-padded / parity-split
     copies of ``x`` that ``conv2d_fwd_sm100`` left in the scratch buffers of the same ``tag``."""
     e = _ext()
-    B, H, W, Cin = x.shape
     Cout, k = gw.shape[0], gw.shape[1]
+    pre = x.dim() == 2                                      # x is already the im2col matrix (gather_im2col)
+    B, H, W, Cin = (dy.shape[0], 0, 0, gw.shape[3]) if pre else x.shape
     cin_valid = Cin
-    if _stem_ok(k, stride, Cin, Cout):
+    if pre or _stem_ok(k, stride, Cin, Cout):
         Ho, Wo = dy.shape[1], dy.shape[2]
-        A = scratch(("im2col", tag), (B * Ho * Wo, 64), x.dtype, x.device)               # filled by the forward pass
+        A = x if pre else scratch(("im2col", tag), (B * Ho * Wo, 64), x.dtype, x.device)   # filled by the forward pass
         dW = scratch(("dwstem", tag), (Cout, 64), torch.float32, x.device)
         _zero(dW)
         e.linear_wgrad_bf16(dy.view(B * Ho * Wo, Cout), A, dW)

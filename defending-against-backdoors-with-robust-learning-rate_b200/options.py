@@ -57,6 +57,9 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--agents_in_flight", type=int, default=1,
                    help="agents a GPU trains CONCURRENTLY when it hosts several per round (one trainer + CUDA stream each); helps the "
                         "small launch-bound CNNs, costs one set of activation buffers per extra agent")
+    p.add_argument("--no_fused_handoff", action="store_true",
+                   help="keep the separate round_init pass and the aggregation kernel's barrier-out instead of fusing the parameter "
+                        "hand-off of a round with the first local GEMM (native trainer; on by default)")
     p.add_argument("--agg_transport", type=str, default="auto", choices=("auto", "gather", "reduce"),
                    help="nccl/gloo back-ends only: gather = all_gather every participant's parameters (needed for comed); reduce = "
                         "all_reduce per-coordinate vote / weighted-sum partials (avg, sign, RLR: O(N) traffic per rank); "

@@ -2,7 +2,10 @@
 
 Per-rank symmetric slab layout (byte offsets identical on every rank):
 
-    [ flags: uint32[2*world] (+pad to 4 KiB) | w_global fp32[n] | w_global bf16[n] | slot_0 fp32[n] | slot_1 ... ]
+    [ flags: uint32[3*world] (+pad to 4 KiB) | w_global fp32[n] | w_global bf16[n] | slot_0 fp32[n] | slot_1 ... ]
+
+Flag words of a rank: [0, world) barrier-in arrivals, [world, 2 world) barrier-out arrivals, [2 world, 3 world) broadcast-ready
+words ("slice r of the new global parameters has landed here", written by rank r).
 
 ``w_global`` is what every local trainer reads at the start of a round; ``slot_j`` receives the parameters of the
 j-th agent this rank trained.  One launch of ``fused_aggregate_kernel`` per rank then (i) waits until every rank has
@@ -14,6 +17,14 @@ signals/awaits "slice landed".  No NCCL call, no host synchronisation, no materi
 Reference counterpart: the Python dict ``agent_updates_dict[agent_id] = update`` (src/federated.py:67-70), the ~30 elementwise
 fp64 passes of ``Aggregation.aggregate_updates`` (src/aggregation.py:19-75) and the per-agent
 ``vector_to_parameters(copy.deepcopy(rnd_global_params), ...)`` "broadcast" (src/federated.py:72).
+
+Hand-off fused with the next round's first GEMM (``enable_handoff``): the kernel then has NO barrier-out.  Rank r
+publishes its slice in every peer's ready word and exits; the consumer of the broadcast is the first local step of the next round
+(``models.native.NativeTrainer``): the producer warp of the stem convolution's tcgen05 GEMM acquires the ready word(s) of the slice(s)
+that hold its filter -- it reads that filter straight out of the multicast bf16 shadow -- and a one-warp ``acquire_slices`` kernel
+queued right behind it waits for the remaining slices, so the first-layer GEMM overlaps the rest of the broadcast.  The separate
+``round_init`` pass (w <- w_global, bf16 shadow, momentum <- 0) does not exist on that path: the first optimizer step reads
+``w_global`` directly with zero momentum.  Host-side readers of ``w_global`` (evaluation, checkpoints, tests) call ``acquire()`` first.
 
 With ``backend in {nccl, gloo}`` (the baseline transport) the slots are all-gathered and the same kernel runs on the
 gathered copies locally; on CPU it runs the fp64 oracle.
@@ -65,6 +76,12 @@ class FusedAggregator:
         self.flipped_is_partial = False   # True after a launch in which every rank counted only its own coordinate slice
         self.epoch = 0
         self._tables = {}
+        # hand-off state: the epoch consumers of the broadcast wait for (device word read by captured kernels), ready-word address
+        self.handoff = False
+        self.epoch_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.ready_ptr = 0
+        self.n_slices = 0
+        self.per = n
         if use_symm:
             world = ctx.world
             self.local_sync = torch.zeros(2, dtype=torch.int32, device=dev)
@@ -80,8 +97,33 @@ class FusedAggregator:
                                       if self.with_bf16 else None)
             # coordinate slices: multiples of 4, cover [0, n)
             per = (n // 4 + world - 1) // world * 4
+            self.per = per
             self.begin = min(n, ctx.rank * per)
             self.end = min(n, self.begin + per)
+
+    # ---- hand-off fused with the next round's first GEMM -------------------------------------------------------------------
+    def enable_handoff(self):
+        """Replace the kernel's barrier-out by per-slice ready words that the consumers acquire (see the module docstring).  With
+        one process (no peers) there is nothing to wait for: consumers get ``ready_ptr = 0`` and only the round_init-free first step
+        remains.  Returns True."""
+        self.handoff = True
+        if self.backend == "fused" and self.ctx.is_dist:
+            world = self.ctx.world
+            self.ready_ptr = self.buf.peer_ptr(self.ctx.rank, self.off_flags) + 4 * 2 * world
+            self.n_slices = world
+        return True
+
+    def slices_of(self, lo: int, hi: int):
+        """Indices (first, last) of the broadcast slices that hold coordinates [lo, hi)."""
+        if not self.n_slices:
+            return 0, 0
+        return min(self.n_slices - 1, lo // self.per), min(self.n_slices - 1, max(lo, hi - 1) // self.per)
+
+    def acquire(self):
+        """Make every slice of the current global parameters visible to work queued afterwards on the current stream (needed
+        before reading ``w_global`` outside the trainers when the hand-off is fused; a no-op otherwise)."""
+        if self.handoff and self.ready_ptr:
+            ops.ext().acquire_slices(self.ready_ptr, 0, self.n_slices - 1, self.epoch_dev, None, None)
 
     # ---------------------------------------------------------------------------------------------------------
     def slot_owner(self, j: int):
@@ -113,7 +155,10 @@ class FusedAggregator:
                 self._agent_table(n_part).tensor, wt, sc, float(sum(float(x) for x in weights)), self.w_global.data_ptr(),
                 self.out_ptrs.tensor, self.out_bf16_ptrs.tensor if self.out_bf16_ptrs else None, self.use_multimem,
                 self.begin, self.end, self.n_vote, ops.MODE_IDS[mode], int(theta), float(server_lr), float(noise_std),
-                int(seed), int(rnd), self.flipped, self.flag_ptrs.tensor, self.local_sync, ctx.rank, ctx.world, self.epoch)
+                int(seed), int(rnd), self.flipped, self.flag_ptrs.tensor, self.local_sync, ctx.rank, ctx.world, self.epoch,
+                bool(self.handoff))
+            if self.handoff:
+                self.epoch_dev.fill_(self.epoch)      # what the next round's consumers wait for (stream-ordered before their graphs)
             return
         # ---- baseline transports / single process ------------------------------------------------------------------
         if ctx.is_dist and self.transport == "reduce" and mode in ("avg", "sign"):

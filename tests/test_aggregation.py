@@ -127,7 +127,7 @@ def test_property_oracle_invariants(K, theta, seed, aggr):
 
 
 def test_more_participants_than_the_kernel_limit_uses_exact_fallback():
-    K, n = ops.MAX_FUSED_AGENTS + 22, 512
+    K, n = ops.MAX_FUSED_AGENTS + 22, 64
     w0, ws = _mk(K, n, seed=9)
     wt = [1.0 + (i % 3) for i in range(K)]
     for mode in ("avg", "comed", "sign"):

@@ -198,3 +198,27 @@ def test_agents_in_flight_bookkeeping_matches_sequential():
     assert res[1][2] == res[3][2]
     torch.testing.assert_close(res[3][0], res[1][0], rtol=0, atol=0)
     assert abs(res[1][1] - res[3][1]) < 1e-4 * abs(res[1][1])          # per-trainer partial sums: float summation order only
+
+
+@pytest.mark.parametrize("pgd", [0.0, 0.05])
+def test_first_step_from_broadcast_buffer_equals_round_init_plus_step(pgd):
+    """The hand-off fused with the first local step (ops.FlatSGD.step(w_in=...)): reading the parameters from the broadcast buffer
+    with zero momentum must equal ``round_init`` (w <- w_global, m <- 0) followed by a normal step; coordinates behind ``n_pgd``
+    (BatchNorm running statistics, already updated in ``w`` by the step's forward pass) keep their value."""
+    from rlr_b200 import ops
+    torch.manual_seed(3)
+    n, n_vote = 4096, 3072
+    w_global, g = torch.randn(n), torch.randn(n) * 3
+    g[n_vote:] = 0                                              # buffers have no gradient
+    stats = torch.randn(n - n_vote)                             # what the step's forward left in the trainer's running statistics
+    # reference: separate round_init pass, then the step
+    w_a, m_a = torch.zeros(n), torch.randn(n)
+    ops.round_init(w_global, w_a, None, m_a)
+    w_a[n_vote:] = stats
+    ops.FlatSGD(n, "cpu", 0.1, 0.9, 10.0, pgd, n_pgd=n_vote).step(w_a, g, m_a, w0=w_global)
+    # fused: stale w / m, parameters come from w_in
+    w_b, m_b = torch.randn(n), torch.randn(n)
+    w_b[n_vote:] = stats
+    ops.FlatSGD(n, "cpu", 0.1, 0.9, 10.0, pgd, n_pgd=n_vote).step(w_b, g, m_b, w0=w_global, w_in=w_global)
+    torch.testing.assert_close(w_b, w_a, rtol=1e-6, atol=1e-6)      # (w - lr*m vs w.add_(m, alpha=-lr): last-bit rounding only)
+    torch.testing.assert_close(m_b, m_a, rtol=1e-6, atol=1e-6)

@@ -25,6 +25,26 @@ def test_gather_normalize(name, dtype, nhwc, cpad):
     torch.testing.assert_close(out.float().cpu(), ref, atol=tol, rtol=tol)
 
 
+@pytest.mark.parametrize("name,k,pad,B", [("cifar10", 3, 1, 37), ("fmnist", 3, 0, 64), ("cifar10", 3, 0, 5), ("fmnist", 5, 2, 19)])
+def test_gather_im2col_matches_oracle(name, k, pad, B):
+    """Batch assembly fused with the first layer's im2col (tiny-K stems) vs the CPU statement of the same op."""
+    tr, _ = make_synthetic(name, 200)
+    d = tr.clone().to(DEV)
+    perm = torch.randperm(200)
+    cur = torch.tensor([11], dtype=torch.int32)
+    H, W = tr.data.shape[1], tr.data.shape[2]
+    Ho, Wo = H + 2 * pad - k + 1, W + 2 * pad - k + 1
+    ref = torch.zeros(B * Ho * Wo, 64)
+    yref = torch.zeros(B, dtype=torch.int64)
+    ops.gather_im2col(tr.data, perm, tr.meta.mean, tr.meta.std, k, pad, ref, cursor=cur, targets=tr.targets, out_labels=yref, batch=B)
+    out = torch.full((B * Ho * Wo, 64), 7.0, dtype=torch.bfloat16, device=DEV)
+    y = torch.zeros(B, dtype=torch.int64, device=DEV)
+    ops.gather_im2col(d.data, perm.to(DEV), tr.meta.mean, tr.meta.std, k, pad, out, cursor=cur.to(DEV), targets=d.targets, out_labels=y, batch=B)
+    torch.testing.assert_close(out.float().cpu(), ref, atol=2e-2, rtol=2e-2)
+    assert torch.equal(y.cpu(), yref)
+    assert float(out[:, k * k * tr.data.shape[3]:].abs().max()) == 0.0          # padding columns are exact zeros
+
+
 def test_gather_cursor_and_labels():
     tr, _ = make_synthetic("cifar10", 256)
     d = tr.clone().to(DEV)
@@ -55,8 +75,12 @@ def test_stamp_pixels(ds, pat, agent):
 
 
 @pytest.mark.parametrize("mode", ["avg", "comed", "sign"])
-@pytest.mark.parametrize("K,theta", [(1, 0), (2, 2), (5, 3), (8, 4), (8, 0), (11, 4), (33, 8)])
+@pytest.mark.parametrize("K,theta", [(1, 0), (2, 2), (5, 3), (8, 4), (8, 0), (9, 3), (11, 4), (12, 5), (16, 0), (17, 6), (24, 9), (32, 8),
+                                     (33, 8), (40, 12), (41, 0), (48, 20), (64, 16), (65, 20), (100, 30), (128, 40), (200, 50), (321, 100),
+                                     (400, 0), (1024, 300)])
 def test_fused_aggregate_matches_oracle(mode, K, theta):
+    """Every path of the fused server-step kernel against the fp64 oracle: vector kernels (avg / sign / median K <= 8), register
+    sorting networks (median 8 < K <= 64), shared-memory staged bisection (64 < K <= 320) and global re-read bisection (K > 320)."""
     torch.manual_seed(K * 31 + theta)
     n, n_vote = 8192, 6144
     g = torch.randn(n)
@@ -154,8 +178,8 @@ def test_engine_round_gpu_torch_trainer_with_graphs():
                      poison_frac=0.5, robustLR_threshold=2, log_dir="", device=DEV, trainer="torch", dtype="fp32")
     eng = FLEngine(args, verbose=False)
     before = eng.w_global.clone()
-    for r in range(1, 4):
+    for r in range(1, 9):
         eng.run_round(r)
-    ev = eng.evaluate(3)
+    ev = eng.evaluate(8)
     assert not torch.equal(before, eng.w_global) and ev["val_acc"] > 0.3
     eng.close()

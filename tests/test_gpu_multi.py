@@ -107,3 +107,88 @@ def test_engine_fused_equals_nccl_baseline(tmp_path):
         assert torch.equal(f[r]["w"], f[0]["w"]), "all ranks hold the same global params after the fused broadcast"
     # fused vs NCCL transport: identical participants/shards/seeds => same training up to nondeterministic cuDNN/atomics
     assert abs(f[0]["acc"] - n[0]["acc"]) < 0.2 and f[0]["backend"] == "fused" and n[0]["backend"] == "nccl"
+
+
+def _handoff_worker(rank, world, port, outdir, fused):
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    from rlr_b200.engine import FLEngine
+    from rlr_b200.options import make_args
+    args = make_args(data="cifar10", model="cnn_cifar", synthetic=2048, synthetic_val=256, num_agents=2 * world, local_ep=1, bs=64, log_dir="",
+                     robustLR_threshold=2, num_corrupt=1, poison_frac=0.5, seed=7, no_fused_handoff=not fused)
+    for nd in []:
+        pass
+    eng = FLEngine(args, verbose=False)
+    assert eng.handoff == fused and eng.fused.backend == "fused"
+    for r in range(1, 5):
+        eng.run_round(r)
+    w = eng.global_params().clone()
+    torch.cuda.synchronize()
+    allw = eng.ctx.all_gather(w)
+    torch.save({"w": w.cpu(), "same": bool((allw == allw[0:1]).all().item()), "loss": eng.round_result()[0]},
+               os.path.join(outdir, f"handoff_{int(fused)}_{rank}.pt"))
+    eng.close()
+    dist.barrier(); dist.destroy_process_group()
+
+
+def test_fused_handoff_across_gpus_equals_barrier_path(tmp_path):
+    """Broadcast (+) first-GEMM fusion on >= 2 GPUs: the aggregation kernel publishes per-slice ready words instead of running its
+    barrier-out, the next round's stem GEMM reads the multicast shadow behind them.  Same global parameters as the barrier path on
+    every rank (up to the atomics order of the split-K weight gradients), identical across ranks bit for bit."""
+    world = min(torch.cuda.device_count(), 8)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    for fused in (False, True):
+        mp.spawn(_handoff_worker, args=(world, _free_port(), str(tmp_path), fused), nprocs=world, join=True)
+    a = [torch.load(tmp_path / f"handoff_1_{r}.pt") for r in range(world)]
+    b = [torch.load(tmp_path / f"handoff_0_{r}.pt") for r in range(world)]
+    for r in range(world):
+        assert a[r]["same"] and b[r]["same"], "all ranks hold identical global parameters"
+    torch.testing.assert_close(a[0]["w"], b[0]["w"], rtol=5e-3, atol=5e-4)
+
+
+def _stress_worker(rank, world, port, outdir, handoff, iters):
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    from rlr_b200 import ops
+    from rlr_b200.parallel import FusedAggregator, init_distributed
+    ctx = init_distributed()
+    n = 1 << 16
+    fa = FusedAggregator(ctx, n, n, 1, "fused")
+    if handoff:
+        fa.enable_handoff()
+    bad = 0
+    # every iteration: each rank's slot := its rank + iteration (a constant vector), FedAvg of K = world participants, so the new
+    # global parameters are known in closed form; any missed flag / stale read / torn broadcast shows up as a wrong value
+    expect = torch.zeros((), dtype=torch.float64)
+    fa.w_global.zero_()
+    torch.cuda.synchronize(); dist.barrier()
+    for it in range(iters):
+        fa.slots[0].copy_(fa.w_global + float(rank + 1))          # reads w_global: must see the complete broadcast of iteration it-1
+        if handoff:
+            pass                                                  # (the copy above is stream-ordered after acquire() below)
+        fa.aggregate([1.0] * world, "avg", 0, 1.0, 0.0, 0, it)
+        fa.acquire()
+        expect = expect + (world + 1) / 2.0
+        if it % 97 == 0 or it == iters - 1:
+            got = fa.w_global.double()
+            bad += int((got - expect).abs().max().item() > 1e-3 * max(1.0, float(expect)))
+    torch.cuda.synchronize()
+    torch.save({"bad": bad, "final": float(fa.w_global[0]), "expect": float(expect)}, os.path.join(outdir, f"stress_{int(handoff)}_{rank}.pt"))
+    fa.close()
+    dist.barrier(); dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("handoff", [False, True])
+def test_flag_protocol_stress_1000_epochs(tmp_path, handoff):
+    """1000 back-to-back aggregations without host synchronisation: epoch-counted release/acquire flags (barrier-in, barrier-out or
+    ready words) are reused every launch; a protocol error would corrupt the closed-form result."""
+    world = min(torch.cuda.device_count(), 8)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    mp.spawn(_stress_worker, args=(world, _free_port(), str(tmp_path), handoff, 1000), nprocs=world, join=True)
+    for r in range(world):
+        res = torch.load(tmp_path / f"stress_{int(handoff)}_{r}.pt")
+        assert res["bad"] == 0 and abs(res["final"] - res["expect"]) < 1e-3 * res["expect"], (r, res)

@@ -15,7 +15,14 @@ BF = torch.bfloat16
 
 
 def _rel(a, b):
+    """max-norm relative error (sensitive to the largest entries)."""
     return float((a.float() - b.float()).abs().max() / (b.float().abs().max() + 1e-6))
+
+
+def _rms_rel(a, b):
+    """RMS-relative error ||a - b||_2 / ||b||_2: unlike ``_rel`` it also sees errors spread over small-magnitude regions."""
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a - b).norm() / (b.norm() + 1e-12))
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 64, 64), (256, 128, 256), (300, 64, 128), (1000, 192, 576), (4096, 256, 1024), (77, 512, 4608)])
@@ -129,29 +136,50 @@ def test_linear_wgrad_and_gemm_linear():
 
 @pytest.mark.parametrize("C,M,relu,res", [(64, 5000, True, True), (128, 777, True, False), (512, 4096, False, False), (256, 100, True, True)])
 def test_bn_kernels(C, M, relu, res):
+    """BatchNorm(+residual)(+ReLU) forward / backward / evaluation kernels against an fp32 ``F.batch_norm`` AUTOGRAD reference fed
+    the same bf16-rounded inputs (not against the aten back-end of our own plan); the aten-bf16 back-end is run too and the
+    kernels must be at least as close to fp32 as it is (x1.5 + bf16 output rounding)."""
     torch.manual_seed(C + M)
-    x = (torch.randn(M, C, device=DEV) * 2 + 0.5).to(BF).view(M // 1 if False else M, 1, 1, C)
+    x = (torch.randn(M, C, device=DEV) * 2 + 0.5).to(BF).view(M, 1, 1, C)
     r = torch.randn_like(x) if res else None
     gamma, beta = torch.rand(C, device=DEV) + 0.5, torch.randn(C, device=DEV) * 0.1
+    dy = torch.randn(M, 1, 1, C, device=DEV, generator=torch.Generator(DEV).manual_seed(1)).to(BF)
+    # ---- fp32 autograd reference ----
+    xf = x.float().view(M, C).requires_grad_(True)
+    rf = r.float().view(M, C).requires_grad_(True) if res else None
+    gf, bf_ = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    rm0, rv0 = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+    z = F.batch_norm(xf, rm0, rv0, gf, bf_, True, 0.1, 1e-5)
+    if res:
+        z = z + rf
+    yf = F.relu(z) if relu else z
+    yf.backward(dy.float().view(M, C))
+    ye_ref = F.batch_norm(x.float().view(M, C), rm0, rv0, gamma, beta, False, 0.1, 1e-5)
+    if res:
+        ye_ref = ye_ref + r.float().view(M, C)
+    ye_ref = F.relu(ye_ref) if relu else ye_ref
+    ref = dict(y=yf.detach(), dx=xf.grad, dres=rf.grad if res else None, dg=gf.grad, db=bf_.grad, rm=rm0, rv=rv0, ye=ye_ref)
     out = {}
     for impl in ("aten", "sm100"):
         rm, rv = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
         y = torch.empty_like(x); mr = torch.zeros(2, C, device=DEV)
         ops.bn_fwd(x, y, r, gamma, beta, rm, rv, None, mr, M, 1e-5, 0.1, True, relu, impl)
-        dy = torch.randn(M, 1, 1, C, device=DEV, generator=torch.Generator(DEV).manual_seed(1)).to(BF)
         dx, dres = torch.empty_like(x), (torch.empty_like(x) if res else None)
         dg, db, ds = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV), torch.zeros(2, C, device=DEV)
         ops.bn_bwd(dy, y, x, gamma, mr, ds, dx, dres, dg, db, relu, impl)
         ye = torch.empty_like(x)
         ops.bn_fwd(x, ye, r, gamma, beta, rm, rv, None, torch.zeros(2, C, device=DEV), M, 1e-5, 0.1, False, relu, impl)
         out[impl] = dict(y=y, rm=rm, rv=rv, dx=dx, dres=dres, dg=dg, db=db, ye=ye)
-    a, b = out["aten"], out["sm100"]
-    for k in ("y", "dx", "ye"):
-        assert _rel(b[k], a[k]) < 2e-2, k
-    for k in ("rm", "rv", "dg", "db"):
-        torch.testing.assert_close(b[k], a[k], rtol=2e-2, atol=2e-2 * max(1.0, float(a[k].abs().max())))
-    if res:
-        assert _rel(b["dres"], a["dres"]) < 1e-2
+    b, a = out["sm100"], out["aten"]
+    for k in ("y", "dx", "ye", "dres", "dg", "db", "rm", "rv"):
+        if ref[k] is None:
+            continue
+        want = ref[k].reshape(b[k].shape)
+        e_sm, e_at = _rms_rel(b[k], want), _rms_rel(a[k], want)
+        print(f"bn C={C} M={M} {k}: rms-rel sm100 {e_sm:.2e} aten-bf16 {e_at:.2e}  max-rel sm100 {_rel(b[k], want):.2e}")
+        # bf16 outputs carry ~2^-9 relative rounding; statistics / parameter gradients are fp32 sums of bf16 products
+        assert e_sm < 1.5 * e_at + 4e-3, (k, e_sm, e_at)
+        assert _rel(b[k], want) < 2e-2, (k, _rel(b[k], want))
 
 
 def test_pool_dropout_s2d_transpose_linear_small():
@@ -205,20 +233,39 @@ def test_pool_dropout_s2d_transpose_linear_small():
     torch.testing.assert_close(dbb, dyy.float().sum(0), rtol=1e-3, atol=1e-3)
 
 
-@pytest.mark.parametrize("model,B", [("resnet18", 64), ("vgg11", 48), ("cnn_cifar", 32), ("cnn_mnist", 32)])
-def test_native_net_sm100_matches_aten_backend(model, B):
-    """Whole forward/backward: kernels (sm100) vs library calls (aten) through the same plan and buffers."""
+def _fp32_autograd_reference(lay, w, x_bf16, y):
+    """Logits and flat gradient of the IR through PyTorch autograd in fp32 (GraphNet over a flat fp32 buffer), fed the same
+    bf16-rounded input and the same (fp32 master) parameters."""
+    from rlr_b200.models.graph import GraphNet
+    wi, g = w.clone(), torch.zeros_like(w)
+    net = GraphNet(lay, wi, g, torch.float32)
+    net.train()
+    logits = net(x_bf16.float().permute(0, 3, 1, 2).contiguous())
+    F.cross_entropy(logits, y).backward()
+    return logits.detach(), g
+
+
+@pytest.mark.parametrize("model,B", [("resnet18", 64), ("vgg11", 48), ("cnn_cifar", 32), ("cnn_mnist", 32), ("resnet34", 32), ("vgg16", 32)])
+def test_native_net_sm100_vs_fp32_autograd(model, B):
+    """Whole forward/backward of every zoo model: our kernels (sm100 back-end, bf16 operands) against fp32 PyTorch AUTOGRAD, judged
+    per parameter tensor by the RMS-relative gradient error, with the library bf16 path (aten back-end: cuDNN / cuBLAS on the same
+    buffers) as the yardstick: sm100 may be at most 1.5x as far from fp32 as the library bf16 path is (+ 1 % slack for
+    the run-to-run order of the split-K atomics).  No library fall-through may occur in the sm100 run."""
     torch.manual_seed(0)
     lay = get_layout(model)
     for nd in lay.nodes:
         if nd.op == "dropout":
-            nd.attrs["p"] = 0.0   # masks come from different RNGs in the two back-ends
+            nd.attrs["p"] = 0.0   # masks come from different RNGs in the back-ends
     w = lay.init_(torch.zeros(lay.n_total, device=DEV), 1)
+    # the bf16 back-ends read the bf16 shadow of the parameters: give the fp32 reference the same (bf16-representable) values
+    w[: lay.n_vote] = w[: lay.n_vote].to(BF).float()
     C, H, W = lay.in_shape
     x = torch.randn(B, H, W, C, device=DEV).to(BF)
     y = torch.randint(0, 10, (B,), device=DEV)
+    l32, g32 = _fp32_autograd_reference(lay, w, x, y)
     res = {}
     for impl in ("aten", "sm100"):
+        ops.reset_fallbacks()
         net = NativeNet(lay, DEV, B, impl=impl)
         wi, g = w.clone(), torch.zeros_like(w)
         net.bind(wi, wi.to(BF), g)
@@ -226,14 +273,22 @@ def test_native_net_sm100_matches_aten_backend(model, B):
         _, dl = ops.softmax_xent(logits, y)
         net.backward(dl)
         res[impl] = (logits, g[: lay.n_vote].clone(), wi[lay.n_vote:].clone())
+        if impl == "sm100":
+            assert ops.fallback_calls() == {}, f"library fall-throughs in the sm100 plan of {model}: {ops.fallback_calls()}"
     (la, ga, sa), (ls, gs, ss) = res["aten"], res["sm100"]
-    print(model, "logit rel", _rel(ls, la), "grad cos", F.cosine_similarity(gs.double(), ga.double(), dim=0).item())
-    worst = sorted(((F.cosine_similarity(lay.view(gs, p).double().flatten(), lay.view(ga, p).double().flatten(), dim=0).item(), p.name)
-                    for p in lay.params))[:6]
-    print("   worst per-parameter gradient cosines:", worst)
-    assert _rel(ls, la) < 5e-2
-    cos = F.cosine_similarity(gs.double(), ga.double(), dim=0).item()
-    assert cos > (0.95 if sa.numel() else 0.99), cos   # BN backward at random init amplifies bf16 rounding
+    print(model, "logits rms-rel vs fp32: sm100", _rms_rel(ls, l32), "aten-bf16", _rms_rel(la, l32),
+          "| whole-gradient rms-rel: sm100", _rms_rel(gs, g32[: lay.n_vote]), "aten-bf16", _rms_rel(ga, g32[: lay.n_vote]))
+    assert _rms_rel(ls, l32) < 1.5 * _rms_rel(la, l32) + 1e-2
+    bad = []
+    for p in lay.params:
+        want = lay.view(g32, p).double().flatten()
+        e_sm, e_at = _rms_rel(lay.view(gs, p), want), _rms_rel(lay.view(ga, p), want)
+        if not e_sm <= 1.5 * e_at + 1e-2:
+            bad.append((p.name, round(e_sm, 4), round(e_at, 4)))
+    worst = sorted(((_rms_rel(lay.view(gs, p), lay.view(g32, p)), _rms_rel(lay.view(ga, p), lay.view(g32, p)), p.name) for p in lay.params),
+                   reverse=True)[:5]
+    print("   worst per-parameter gradient rms-rel (sm100, aten-bf16, name):", [(round(a_, 4), round(b_, 4), n_) for a_, b_, n_ in worst])
+    assert not bad, f"{model}: parameters whose sm100 gradient is > 1.5x further from fp32 than the library bf16 path: {bad[:8]}"
     if sa.numel():
         torch.testing.assert_close(ss, sa, rtol=5e-2, atol=5e-2)
 
@@ -249,16 +304,16 @@ def test_native_trainer_learns_like_torch_trainer(model):
         args = make_args(data="cifar10", model=model, num_agents=2, local_ep=2, bs=64, synthetic=1000, synthetic_val=200, log_dir="",
                          device=DEV, trainer=trainer, seed=2)
         eng = FLEngine(args, verbose=False)
-        for r in range(1, 7):
+        for r in range(1, 11):
             eng.run_round(r)
-        accs[trainer] = eng.evaluate(6)["val_acc"]
+        accs[trainer] = eng.evaluate(10)["val_acc"]
         assert eng.trainer.name == trainer
         eng.close()
     print(model, accs)
     # Accuracy after a handful of rounds on 1000 samples depends on the dropout-mask / atomics-order realisation (scripts/
     # debug_flaky.py: 0.73-1.0 after 3 rounds for EVERY back-end mix, incl. library kernels with a different mask stream), so
     # the bar is "clearly learned", not "matches the torch trainer's realisation".
-    assert accs["native"] > 0.7 and accs["torch"] > 0.7
+    assert accs["native"] > 0.85 and accs["torch"] > 0.85
 
 
 @pytest.mark.parametrize("B,H,W,Cout,acc", [(64, 32, 32, 64, False), (37, 16, 16, 64, True), (8, 32, 32, 128, False), (5, 16, 8, 32, False)])
@@ -298,11 +353,12 @@ def test_streaming_mode_after_resident_rounds_uses_valid_indices():
     eng = FLEngine(args, verbose=False)
     eng.run_round(1)
     eng.enable_input_streaming()
-    for r in (2, 3):
+    for r in range(2, 10):
         eng.run_round(r, stream_inputs=True)
     loss, _ = eng.round_result()
     torch.cuda.synchronize()
-    assert loss == loss and eng.evaluate(3)["val_acc"] > 0.2
+    # (after only 3 rounds this configuration is still at chance level for some dropout-mask realisations; 9 rounds learn it)
+    assert loss == loss and eng.evaluate(9)["val_acc"] > 0.3
     eng.close()
 
 
@@ -351,3 +407,51 @@ def test_persistent_conv_matches_default(B, H, W, Cin, Cout, k, s, p):
     for mode in (True, "occ3"):
         for a, b in zip(outs[False], outs[mode]):
             assert torch.equal(a, b), mode
+
+
+@pytest.mark.parametrize("N,kvalid,M,relu", [(64, 27, 1000, True), (32, 9, 300, False), (128, 27, 4096, True), (64, 64, 129, False)])
+def test_stem_gemm_gathers_unpadded_filter(N, kvalid, M, relu):
+    """Stem convolution as one 64-deep tcgen05 GEMM whose B tile is gathered + zero-padded + swizzled by the producer warp from the
+    UN-padded filter (gemm.cu b_src path; the same path reads the multicast broadcast buffer behind ready flags)."""
+    torch.manual_seed(N + kvalid + M)
+    A = torch.zeros(M, 64, device=DEV, dtype=BF)
+    A[:, :kvalid] = torch.randn(M, kvalid, device=DEV).to(BF)
+    A[:, kvalid:] = 7.0                      # junk in the padding columns of A must be cancelled by the zero padding of B
+    W = (torch.randn(N, kvalid, device=DEV) * 0.3).to(BF)
+    bias = torch.randn(N, device=DEV)
+    out = torch.empty(M, N, device=DEV, dtype=BF)
+    ops.ext().stem_gemm_bf16(A, W, out, bias, relu, None, 0, 0, 0, None)
+    ref = A[:, :kvalid].float() @ W.float().t() + bias
+    ref = F.relu(ref) if relu else ref
+    assert _rel(out, ref) < 1e-2 and _rms_rel(out, ref) < 5e-3
+    # with a (trivially satisfied) ready-flag wait: flags already carry the epoch
+    flags = torch.full((8,), 5, dtype=torch.int32, device=DEV)
+    epoch = torch.full((1,), 5, dtype=torch.int32, device=DEV)
+    out2 = torch.empty_like(out)
+    ops.ext().stem_gemm_bf16(A, W, out2, bias, relu, None, flags.data_ptr(), 2, 6, epoch)
+    assert torch.equal(out, out2)
+
+
+@pytest.mark.parametrize("model", ["resnet18", "cnn_mnist"])
+def test_fused_handoff_equals_round_init_path(model):
+    """Round hand-off fused with the first local GEMM (no round_init pass; first step reads the broadcast buffer, zero momentum) must
+    train exactly like the unfused path: same kernels in the same order on the same values -> bit-identical global parameters
+    (dropout off: masks are a pure function of (seed, agent, round, step) either way, but keep the check sharp)."""
+    from rlr_b200.engine import FLEngine
+    from rlr_b200.models import get_layout
+    from rlr_b200.options import make_args
+    res = {}
+    for fused in (False, True):
+        data = "cifar10" if model == "resnet18" else "fmnist"
+        args = make_args(data=data, model=model, num_agents=3, local_ep=2, bs=64, synthetic=640, synthetic_val=128, log_dir="", device=DEV,
+                         seed=4, no_fused_handoff=not fused, robustLR_threshold=2)
+        eng = FLEngine(args, verbose=False)
+        assert eng.handoff == fused and eng.trainer.name == "native"
+        for r in range(1, 4):
+            eng.run_round(r)
+        torch.cuda.synchronize()
+        res[fused] = (eng.global_params().clone(), eng.round_result())
+        eng.close()
+    # weight gradients are split-K reductions with fp32 atomics: summation order may differ run to run -> tight tolerance, not bitwise
+    torch.testing.assert_close(res[True][0], res[False][0], rtol=2e-3, atol=2e-4)
+    assert abs(res[True][1][0] - res[False][1][0]) < 0.02 * abs(res[False][1][0]) + 1e-3

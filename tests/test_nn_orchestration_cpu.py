@@ -150,6 +150,14 @@ class FakeExt:
         else:
             out.copy_(r)
 
+    def stem_gemm_bf16(self, A, W, out, bias, relu, stats, ready_ptr, lo, hi, epoch):
+        self.calls.append("stem_gemm_bf16")
+        assert A.shape[1] == 64 and W.shape[1] <= 64 and stats is None and ready_ptr == 0
+        r = A[:, :W.shape[1]] @ W.t()
+        if bias is not None:
+            r = r + bias
+        out.copy_(r.clamp_min(0) if relu else r)
+
     def linear_wgrad_bf16(self, dy, x, dW):
         self.calls.append("linear_wgrad_bf16")
         dW += dy.t() @ x
@@ -269,7 +277,7 @@ def test_conv_wrappers_hand_the_kernels_the_right_problem(fake, monkeypatch, mod
     if mode == "default" and s == 2:
         assert "space_to_depth" in fake.calls
     if mode == "stem" and Cin * k * k <= 64 and s == 1:
-        assert fake.calls.count("im2col_small") == 1 and "gemm_bf16" in fake.calls and "linear_wgrad_bf16" in fake.calls
+        assert fake.calls.count("im2col_small") == 1 and "stem_gemm_bf16" in fake.calls and "linear_wgrad_bf16" in fake.calls
     if mode == "halo3" and nn._halo_ok(k, s, p, Cin, H, W):
         assert "conv3x3_halo3_bf16" in fake.calls and "conv3x3_halo_bf16" not in fake.calls
 
