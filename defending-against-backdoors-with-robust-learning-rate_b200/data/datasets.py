@@ -216,17 +216,50 @@ def make_synthetic(name: str, n_train: int, n_val: int | None = None, seed: int 
     return draw(n_train), draw(n_val)
 
 
-def _load_torchvision(name: str, data_dir: str):
-    from torchvision import datasets  # local import: only needed for real data
+def _read_idx(path: str) -> torch.Tensor:
+    """IDX file (the FashionMNIST / MNIST raw format; ``.gz`` accepted): magic 0x0000 08 <ndim>, big-endian dims, uint8 payload."""
+    import gzip
+    import struct
+    opener = gzip.open if path.endswith(".gz") else open
+    with opener(path, "rb") as f:
+        raw = f.read()
+    zero, dtype, ndim = struct.unpack(">HBB", raw[:4])
+    if zero != 0 or dtype != 0x08:
+        raise ValueError(f"{path}: not a uint8 IDX file")
+    dims = struct.unpack(">" + "I" * ndim, raw[4:4 + 4 * ndim])
+    return torch.frombuffer(bytearray(raw[4 + 4 * ndim:]), dtype=torch.uint8).reshape(dims).clone()
 
+
+def _first_existing(*paths):
+    for p in paths:
+        if os.path.exists(p):
+            return p
+    raise FileNotFoundError(" | ".join(paths))
+
+
+def _load_torchvision(name: str, data_dir: str):
+    """Read FashionMNIST / CIFAR-10 from torchvision's ON-DISK layout (what ``download=True`` of the reference leaves under
+    ``../data``, src/utils.py:100-121) without torchvision's md5 checks or any download:
+    ``<dir>/FashionMNIST/raw/{train,t10k}-{images-idx3,labels-idx1}-ubyte[.gz]`` and ``<dir>/cifar-10-batches-py/{data_batch_1..5,test_batch}``.
+    Returns ((x_train uint8 NHWC / NHW, y_train int64), (x_val, y_val))."""
     if name == "fmnist":
-        tr = datasets.FashionMNIST(data_dir, train=True, download=False)
-        te = datasets.FashionMNIST(data_dir, train=False, download=False)
-        return (tr.data, tr.targets), (te.data, te.targets)
-    tr = datasets.CIFAR10(data_dir, train=True, download=False)
-    te = datasets.CIFAR10(data_dir, train=False, download=False)
-    return ((torch.from_numpy(tr.data), torch.as_tensor(tr.targets)),
-            (torch.from_numpy(te.data), torch.as_tensor(te.targets)))
+        raw = os.path.join(data_dir, "FashionMNIST", "raw")
+        out = []
+        for split in ("train", "t10k"):
+            x = _read_idx(_first_existing(os.path.join(raw, f"{split}-images-idx3-ubyte"), os.path.join(raw, f"{split}-images-idx3-ubyte.gz")))
+            y = _read_idx(_first_existing(os.path.join(raw, f"{split}-labels-idx1-ubyte"), os.path.join(raw, f"{split}-labels-idx1-ubyte.gz")))
+            out.append((x, y.long()))
+        return out[0], out[1]
+    import pickle
+    base = os.path.join(data_dir, "cifar-10-batches-py")
+
+    def batch(fn):
+        with open(_first_existing(os.path.join(base, fn)), "rb") as f:
+            d = pickle.load(f, encoding="latin1")
+        x = torch.as_tensor(d["data"], dtype=torch.uint8).reshape(-1, 3, 32, 32).permute(0, 2, 3, 1).contiguous()   # HWC like torchvision
+        return x, torch.as_tensor(d["labels"] if "labels" in d else d["fine_labels"], dtype=torch.int64)   # LongTensor (src/utils.py:122)
+    tr = [batch(f"data_batch_{i}") for i in range(1, 6)]
+    return (torch.cat([t[0] for t in tr]), torch.cat([t[1] for t in tr])), batch("test_batch")
 
 
 def get_datasets(data: str, data_dir: str = "../data", synthetic: int = 0, synthetic_val: int = 0,

@@ -20,6 +20,7 @@ Reference call sites replaced: src/models.py:22-31,47-58 (forward), src/agent.py
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 import torch.nn.functional as F
@@ -28,6 +29,10 @@ from .. import ops
 from .graph import FlatLayout
 
 ACT = torch.bfloat16   # default activation / GEMM-operand dtype on GPU (tests may run the plan in fp32 on CPU)
+# Weight gradients are off the critical path of the backward pass (nothing but the optimizer reads them): with RLR_WGRAD_OVERLAP=1 every
+# conv weight-gradient kernel is queued on a side stream (forked / joined with events, so it becomes a parallel branch of the captured
+# step graph) while the data-gradient / BatchNorm chain continues on the main stream.
+WGRAD_OVERLAP = bool(int(os.environ.get("RLR_WGRAD_OVERLAP", "0")))
 
 
 def dropout_stream_base(seed: int, agent_id: int, rnd: int) -> int:
@@ -305,8 +310,17 @@ class NativeNet:
             gout.copy_(dlogits.reshape(gout.shape))
         ops.zero_(self.g)        # tcgen05 weight gradients are split-K reductions (red.add) into the flat buffer
         ops.zero_(self.dsum_arena)
+        self._side = None
+        if WGRAD_OVERLAP and self.device.type == "cuda":
+            if getattr(self, "_side_stream", None) is None:
+                self._side_stream = torch.cuda.Stream(self.device)
+            self._side = self._side_stream
+            self._side.wait_stream(torch.cuda.current_stream(self.device))       # the flat gradient is zeroed
         for op in reversed(self.plan):
             getattr(self, "_bwd_" + op.kind)(op, B)
+        if self._side is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self._side)       # every weight gradient has landed before the optimizer
+            self._side = None
 
     # ---- conv ---------------------------------------------------------------------------------------------------
     def _fwd_conv(self, op, B, train):
@@ -340,7 +354,12 @@ class NativeNet:
         gw, gb = self.pg[name], self.pg.get(op.name + ".bias")
         s, p = a.get("stride", 1), a.get("pad", 0)
         if self.impl["conv_wgrad"] == "sm100" and ops.conv_supported(op.in_shape, a, "wgrad"):
-            ops.conv2d_wgrad_sm100(x, dy, gw, gb, s, p, tag=(id(self), op.name), zero=False)
+            if getattr(self, "_side", None) is not None:
+                self._side.wait_stream(torch.cuda.current_stream(self.device))   # dy (and its ReLU mask) is final
+                with torch.cuda.stream(self._side):
+                    ops.conv2d_wgrad_sm100(x, dy, gw, gb, s, p, tag=(id(self), op.name), zero=False)
+            else:
+                ops.conv2d_wgrad_sm100(x, dy, gw, gb, s, p, tag=(id(self), op.name), zero=False)
         else:
             if self.impl["conv_wgrad"] == "sm100":
                 ops.note_fallback("conv_wgrad", f"{op.name} in={op.in_shape} {a}")

@@ -269,6 +269,7 @@ umma_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 *reinterpret_cast<uint4*>(out + (size_t)gi * p.ldc + col0 + ch * 8) = val;
             }
         }
+        if (dbg && et == 0) dbg[6] = (long long)gtimer();      // end of this thread's share of the epilogue stores
         // ---- per-channel statistics: one global reduction per column and tile, spread over kStatSlots partial buffers ----
         if (kStats) {
             asm volatile("bar.sync 1, 128;" ::: "memory");   // (also orders the smem atomics above; the bar before the stores did too)
@@ -280,7 +281,6 @@ umma_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     // ---- teardown ----------------------------------------------------------------------------------------------------------
     tc_fence_before();
     __syncthreads();
-    if (dbg && threadIdx.x == 0) dbg[6] = (long long)gtimer();
     if (warp == 2) tmem_dealloc(tmem_acc, BN);
 }
 

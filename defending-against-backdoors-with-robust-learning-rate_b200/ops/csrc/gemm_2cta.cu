@@ -258,11 +258,11 @@ umma_conv_gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
                 *reinterpret_cast<uint4*>(out + (size_t)gi * p.ldc + col0 + ch * 8) = val;
             }
         }
+        if (dbg && et == 0) dbg[6] = (long long)gtimer();      // end of this thread's share of the epilogue stores
     }
     // ---- teardown: neither CTA may free TMEM or exit while its partner can still touch it --------------------------------------
     tc_fence_before();
     __syncthreads();
-    if (dbg && threadIdx.x == 0) dbg[6] = (long long)gtimer();
     cluster_sync_all();
     if (warp == 2) tmem_dealloc_2cta(tmem_acc, BN);
 }

@@ -18,8 +18,9 @@ STAT_SLOTS = 16         # conv epilogues spread their BatchNorm statistics over 
 USE_WGRAD_HALO = True   # 3x3/s1/p1, 64 input channels: halo-reuse weight-gradient kernel (wgrad.cu)
 # Stride-2 convolutions without parity-split copies: the forward conv and the weight gradient read the original input through a
 # TMA box with element strides 2, and the four parity planes of the data gradient are stored straight into dX (strided epilogue
-# rows) -- no space_to_depth / depth_to_space passes.  Opt-in until measured on hardware (RLR_STRIDED_TMA=1).
-USE_STRIDED_TMA = bool(int(os.environ.get("RLR_STRIDED_TMA", "0")))
+# rows) -- no space_to_depth / depth_to_space passes.  Measured on B200 (profiles/r2_conv_layers.md): stride-2 forward 37 -> 21 us
+# (layer2), data gradient 68 -> 49 us, 1x1 shortcut 30 -> 15 us; whole ResNet-18 round -4.6 %.  RLR_STRIDED_TMA=0 restores the copies.
+USE_STRIDED_TMA = bool(int(os.environ.get("RLR_STRIDED_TMA", "1")))
 # Stem convolutions (Cin * k * k <= 64, stride 1): gather the k x k x Cin patch of every output pixel into ONE 64-wide K block
 # (im2col_small, or -- in the training step -- directly by the batch-assembly kernel gather_im2col) and run the plain tcgen05 GEMM on
 # it, instead of k*k k-blocks of a 64-channel zero-padded input; the weight gradient is a [Cout x 64] GEMM over the same matrix.

@@ -39,10 +39,15 @@ for name in a.layers.split(","):
             fn()
         torch.cuda.synchronize()
         buf = torch.zeros(8192 * 8, dtype=torch.int64, device=DEV)
+        buf2 = torch.zeros(8192 * 8, dtype=torch.int64, device=DEV)
         e.set_conv_trace(buf)
+        fn()
+        e.set_conv_trace(buf2)        # a second, back-to-back launch: its first CTA start minus the first launch's last CTA end = launch gap
         fn()
         torch.cuda.synchronize()
         e.set_conv_trace(None)
+        t2 = buf2.view(-1, 8).cpu()
+        t2 = t2[t2[:, 0] > 0]
         t = buf.view(-1, 8).cpu()
         t = t[t[:, 0] > 0]
         n = t.shape[0]
@@ -50,7 +55,9 @@ for name in a.layers.split(","):
         rel = (t[:, :7] - t0).double() / 1e3          # us since the first CTA started
         span = float(rel[:, 6].max())
         q = lambda v: [round(float(x_), 2) for x_ in torch.quantile(v, torch.tensor([0.1, 0.5, 0.9], dtype=torch.float64))]
-        print(f"== {name} {d} pair={a.pair}: {n} CTAs, kernel span {span:.1f} us")
+        gap = (float(t2[:, 0].min()) - float(t[:, 6].max())) / 1e3
+        print(f"== {name} {d} pair={a.pair}: {n} CTAs, kernel span {span:.1f} us; gap to the next launch's first CTA {gap:.2f} us "
+              f"(next launch: first CTA -> last CTA start {(float(t2[:, 0].max()) - float(t2[:, 0].min())) / 1e3:.2f} us)")
         print("   CTA start (10/50/90 %)        :", q(rel[:, 0]))
         print("   set-up  (entry -> barriers)    :", q(rel[:, 1] - rel[:, 0]))
         ld = t[:, 3] > 0                              # CTAs that issue MMAs (all of them, or the pair leaders)
