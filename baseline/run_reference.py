@@ -62,7 +62,7 @@ def _synthetic_vision_dataset(name, n, seed, transform):
 
 
 def run(data="cifar10", model="resnet18", num_agents=1, local_ep=2, bs=256, aggr="avg", train_size=50000,
-        steps=3, warmup=3, theta=0, num_corrupt=0, poison_frac=0.0, device="cuda:0", seed=0):
+        steps=3, warmup=3, theta=0, num_corrupt=0, poison_frac=0.0, device="cuda:0", seed=0, agent_frac=1.0):
     """Returns dict(ms_per_round, rounds_per_s, h2d_bytes_per_round, wall_s)."""
     if not reference_available():
         raise FileNotFoundError("baseline/_ref/src missing; run baseline/install_reference.py")
@@ -73,7 +73,7 @@ def run(data="cifar10", model="resnet18", num_agents=1, local_ep=2, bs=256, aggr
     try:
         sys.argv = ["federated.py", f"--data={data}", f"--num_agents={num_agents}", f"--local_ep={local_ep}", f"--bs={bs}",
                     f"--aggr={aggr}", f"--robustLR_threshold={theta}", f"--num_corrupt={num_corrupt}",
-                    f"--poison_frac={poison_frac}", f"--device={device}", "--snap=1000000"]
+                    f"--poison_frac={poison_frac}", f"--device={device}", "--snap=1000000", f"--agent_frac={agent_frac}"]
         import utils as ref_utils  # noqa: E402  (reference module)
         import models as ref_models
         from agent import Agent

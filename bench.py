@@ -48,6 +48,8 @@ def parse():
                    help="number of FL agents (default 0 = one per GPU, the headline config); more agents than GPUs are time-multiplexed "
                         "-- e.g. --agents 10 --gpus 1 is the reference README's FMNIST setting")
     p.add_argument("--agents_in_flight", type=int, default=1, help="agents a GPU trains concurrently (ours only)")
+    p.add_argument("--agent_frac", type=float, default=1.0, help="fraction of the agents sampled per round (reference --agent_frac)")
+    p.add_argument("--pattern_type", type=str, default="plus")
     return p.parse_args()
 
 
@@ -100,7 +102,7 @@ def config_dict(a, n, impl):
             "agents_per_gpu": (k + n - 1) // n if impl == "ours" else k, "agents_in_flight": a.agents_in_flight if impl == "ours" else 1,
             "global_batch": a.bs * n if impl == "ours" else a.bs,
             "local_batch": a.bs, "local_ep": a.local_ep, "aggr": a.aggr, "robustLR_threshold": a.theta,
-            "num_corrupt": a.num_corrupt, "seq_len": None,
+            "num_corrupt": a.num_corrupt, "poison_frac": a.poison_frac, "agent_frac": a.agent_frac, "seq_len": None,
             "parallelism": f"agent-parallel: {k} agent(s) on {n} GPU(s)" if impl == "ours" else f"{k} agent(s) sequential on 1 GPU (reference design)",
             "l2_policy": "inputs larger than L2: each step streams a fresh batch from the 150 MB device-resident dataset plus "
                          "4x45 MB flat parameter/grad/momentum buffers and >100 MB of activations (L2 = 126 MB)",
@@ -122,11 +124,15 @@ def run_reference(a):
     if not torch.cuda.is_available():
         print(json.dumps({"impl": "reference", "unavailable": "no CUDA device visible"}))
         return
+    if a.data == "fedemnist":
+        print(json.dumps({"impl": "reference", "unavailable": "the reference reads Fed-EMNIST from one pickled file per client (src/agent.py:16-20); "
+                          "the dataset is not in this image and the synthetic shim only replaces utils.get_datasets"}))
+        return
     clocks = ClockSampler(0)
     t0 = time.time()
     res = rr.run(data=a.data, model=a.model, num_agents=a.agents or a.gpus, local_ep=a.local_ep, bs=a.bs, aggr=a.aggr,
                  train_size=a.train_size, steps=a.steps, warmup=a.warmup, theta=a.theta, num_corrupt=a.num_corrupt,
-                 poison_frac=a.poison_frac, device="cuda:0")
+                 poison_frac=a.poison_frac, device="cuda:0", agent_frac=a.agent_frac)
     ck = clocks.stop()
     out = {"impl": "reference", "metric": "fl_rounds_per_sec", "value": res["rounds_per_s"], "unit": "rounds/s",
            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": res["ms_per_round"],
@@ -195,7 +201,8 @@ def run_ours(a):
     def make_engine(trainer):
         args = make_args(data=a.data, model=a.model, num_agents=a.agents or n, agents_in_flight=a.agents_in_flight, local_ep=a.local_ep, bs=a.bs,
                          aggr=a.aggr,
-                         robustLR_threshold=a.theta, num_corrupt=a.num_corrupt, poison_frac=a.poison_frac,
+                         robustLR_threshold=a.theta, num_corrupt=a.num_corrupt, poison_frac=a.poison_frac, agent_frac=a.agent_frac,
+                         pattern_type=a.pattern_type,
                          synthetic=a.train_size, synthetic_val=1000, snap=10 ** 9, rounds=10 ** 9, log_dir="",
                          trainer=trainer, backend=a.backend, dtype=a.dtype, seed=0)
         return FLEngine(args, ctx=ctx, verbose=False)
