@@ -29,10 +29,11 @@ from .. import ops
 from .graph import FlatLayout
 
 ACT = torch.bfloat16   # default activation / GEMM-operand dtype on GPU (tests may run the plan in fp32 on CPU)
-# Weight gradients are off the critical path of the backward pass (nothing but the optimizer reads them): with RLR_WGRAD_OVERLAP=1 every
-# conv weight-gradient kernel is queued on a side stream (forked / joined with events, so it becomes a parallel branch of the captured
-# step graph) while the data-gradient / BatchNorm chain continues on the main stream.
-WGRAD_OVERLAP = bool(int(os.environ.get("RLR_WGRAD_OVERLAP", "0")))
+# Weight gradients are off the critical path of the backward pass (nothing but the optimizer reads them): every conv weight-gradient
+# kernel is queued on a side stream (forked / joined with events, so it becomes a parallel branch of the captured step graph) while the
+# data-gradient / BatchNorm chain continues on the main stream.  Measured on B200: ResNet-18 round 1065.7 -> 1030.0 ms (same box,
+# profiles/r2_step_ab.md).  RLR_WGRAD_OVERLAP=0 serialises them again.
+WGRAD_OVERLAP = bool(int(os.environ.get("RLR_WGRAD_OVERLAP", "1")))
 
 
 def dropout_stream_base(seed: int, agent_id: int, rnd: int) -> int:

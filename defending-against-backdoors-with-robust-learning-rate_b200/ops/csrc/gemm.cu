@@ -82,7 +82,7 @@ umma_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         prefetch_tmap(&tmB);
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&tail->full[s], 1); mbar_init(&tail->empty[s], 1); }
+        for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&tail->full[s], p.split_prod ? 2 : 1); mbar_init(&tail->empty[s], 1); }
         mbar_init(&tail->tmem_full, 1);
         fence_barrier_init();
     }
@@ -142,7 +142,7 @@ umma_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 mbar_wait(&tail->empty[stage], phase ^ 1);
                 uint8_t* sa = smem + stage * Cfg::kStageBytes;
                 uint8_t* sb = sa + Cfg::kABytes;
-                mbar_expect_tx(&tail->full[stage], p.b_src ? Cfg::kABytes : Cfg::kStageBytes);
+                mbar_expect_tx(&tail->full[stage], (p.b_src || p.split_prod) ? Cfg::kABytes : Cfg::kStageBytes);
                 if (p.mode == 1) {
                     const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
                     tma_load_4d(&tmA, &tail->full[stage], sa, cb * BK, w0 * p.in_stride + p.dw[tap], h0 * p.in_stride + p.dh[tap],
@@ -150,8 +150,8 @@ umma_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 } else {
                     tma_load_2d(&tmA, &tail->full[stage], sa, kb * BK, tile_m * BM);
                 }
-                if (p.b_src) {
-                    // B tile already written by the warp above
+                if (p.b_src || p.split_prod) {
+                    // B tile already written by the warp above / loaded by the second producer (warp 2)
                 } else if (kBMN) {
                     // data gradient: B[k = co][n = ci] is a 64 x 64 box of the ORIGINAL filter W[co][tap][ci] (ci contiguous ->
                     // MN-major operand); one box per 64-wide ci group.  No transposed filter copy is ever materialised.
@@ -161,7 +161,6 @@ umma_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 } else {
                     tma_load_2d(&tmB, &tail->full[stage], sb, kb * BK, tile_n * BN);
                 }
-                if (dbg && kb == 0) dbg[2] = (long long)gtimer();
                 if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
             }
         }
@@ -195,6 +194,25 @@ umma_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         const int et = threadIdx.x - 64;                 // 0..127
         const int lane_base = (warp & 3) * 32;           // TMEM lanes this warp may access
         const int row = lane_base + lane;                // tile row held by this thread
+        if (p.split_prod && warp == 2 && lane == 0) {
+            // second TMA producer: the B (filter) tiles of every k-block -- an independent request stream next to warp 0's A stream
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                mbar_wait(&tail->empty[stage], phase ^ 1);
+                uint8_t* sb = smem + stage * Cfg::kStageBytes + Cfg::kABytes;
+                mbar_expect_tx(&tail->full[stage], Cfg::kBBytes);
+                if (kBMN) {
+                    const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
+                    for (int g = 0; g < BN / 64; ++g)
+                        tma_load_2d(&tmB, &tail->full[stage], sb + g * 8192, p.wtap[tap] * p.wcols + tile_n * BN + g * 64, cb * BK);
+                } else {
+                    tma_load_2d(&tmB, &tail->full[stage], sb, kb * BK, tile_n * BN);
+                }
+                if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+            }
+        }
+        __syncwarp();
         mbar_wait(&tail->tmem_full, 0);
         tc_fence_after();
         if (dbg && et == 0) dbg[5] = (long long)gtimer();
@@ -235,6 +253,7 @@ umma_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         }
         tc_fence_before();
         asm volatile("bar.sync 1, 128;" ::: "memory");   // epilogue-only named barrier: staging tile complete
+        if (dbg && et == 0) dbg[2] = (long long)gtimer();   // TMEM -> registers -> shared staging done
         // ---- coalesced 16-byte stores (optionally accumulating into the existing output) ----
         constexpr int kChunks = BN * 2 / 16;             // 16 B chunks per row
         __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
@@ -405,6 +424,8 @@ static int persistent_sms() {
     return sms;
 }
 
+static int g_split_prod = -1;
+void set_conv_split_producer(int on) { g_split_prod = on ? 1 : 0; }
 static long long* g_trace = nullptr;
 void set_conv_trace(long long* buf) { g_trace = buf; }
 long long* conv_trace_buf() { return g_trace; }
@@ -414,6 +435,8 @@ static cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, con
     using Cfg = TileCfg<BN>;
     ConvGemmParams p = p_in;
     p.dbg = g_trace;
+    if (g_split_prod < 0) { const char* e = getenv("RLR_SPLIT_PRODUCER"); g_split_prod = (e && atoi(e) > 0) ? 1 : 0; }
+    p.split_prod = (g_split_prod && !p.b_src) ? 1 : 0;
     if (!p.stats && !p.b_src && persistent_sms() > 0 && m_tiles * ((p.N + BN - 1) / BN) > persistent_sms())
         return launch_persistent_bn<BN>(tmA, tmB, p, m_tiles, persistent_sms(), st);
     if (!p.stats && conv_occ3() >= (BN == 64 ? 1 : 2)) return launch_bn_occ3<BN>(tmA, tmB, p, m_tiles, st);

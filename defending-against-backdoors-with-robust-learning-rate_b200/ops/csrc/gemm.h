@@ -31,6 +31,7 @@ struct ConvGemmParams {
     // With wait_flags the producer first acquires the broadcast-ready words [wait_lo, wait_hi] (>= *wait_epoch): b_src then points into
     // the NVLS-multicast parameter shadow that the aggregation kernels of ALL GPUs are still filling -- the first local-forward GEMM of
     // a round starts as soon as the slice holding its filter has landed (broadcast (+) first-GEMM fusion, parallel/fused_agg.py).
+    int split_prod;            // 1: two TMA producer threads per CTA (warp 0 loads A, warp 2 loads B): two request streams into the TMA unit
     long long* dbg;            // optional [CTAs][8] timeline (globaltimer ns): entry, setup done, first TMA issued, first data landed,
                                // all MMAs issued, accumulator complete, epilogue done, SM id  (scripts/trace_conv.py)
     const __nv_bfloat16* b_src;
@@ -65,6 +66,7 @@ void set_persistent_conv(int on);
 // three CTAs per SM: level 0 never, 1 (default) for the 64-wide tile, 2 also for the 128-wide tile (RLR_CONV_OCC3 env)
 void set_conv_occ3(int level);
 // per-CTA timeline buffer for the NEXT launches of the generic conv / GEMM kernel (nullptr = off); see ConvGemmParams::dbg
+void set_conv_split_producer(int on);      // experiment: two TMA producer threads per CTA (RLR_SPLIT_PRODUCER env)
 void set_conv_trace(long long* buf);
 long long* conv_trace_buf();
 cudaError_t launch_conv_bf16(const void* x, const void* w, void* out, int NB, int planes, int Hin, int Win, int Cin, int Ho, int Wo,

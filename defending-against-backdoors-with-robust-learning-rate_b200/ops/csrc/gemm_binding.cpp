@@ -309,6 +309,7 @@ void register_gemm_bindings(py::module_& m) {
     m.def("set_conv_2cta", [](int64_t mode) { rlr::set_conv_2cta((int)mode); });   // 0 off | 1 CTA pairs | 2 + deep single-wave variant
     m.def("set_pdl", [](bool on) { rlr::set_pdl(on ? 1 : 0); });
     m.def("set_conv_occ3", [](int64_t level) { rlr::set_conv_occ3((int)level); });
+    m.def("set_conv_split_producer", [](bool on) { rlr::set_conv_split_producer(on ? 1 : 0); });
     m.def("set_conv_trace", [](c10::optional<at::Tensor> buf) {   // int64 [CTAs * 8] timeline buffer for the next generic conv / GEMM launches
         rlr::set_conv_trace(buf.has_value() && buf->defined() ? reinterpret_cast<long long*>(buf->data_ptr<int64_t>()) : nullptr);
     });

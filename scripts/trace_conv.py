@@ -19,11 +19,13 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--layers", default="l2,l3,l4")
 ap.add_argument("--dirs", default="fwd")
 ap.add_argument("--occ3", type=int, default=1)
+ap.add_argument("--split", type=int, default=0, help="1: two TMA producer threads per CTA")
 ap.add_argument("--pair", type=int, default=0, help="0 single-CTA kernel | 1 CTA pairs | 2 pairs with the deep ring")
 a = ap.parse_args()
 e = ops.ext()
 e.set_conv_occ3(a.occ3)
 e.set_conv_2cta(a.pair)
+e.set_conv_split_producer(bool(a.split))
 for name in a.layers.split(","):
     B, H, Cin, Cout, k, s, p = LAYERS[name]
     Ho = (H + 2 * p - k) // s + 1
@@ -61,10 +63,11 @@ for name in a.layers.split(","):
         print("   CTA start (10/50/90 %)        :", q(rel[:, 0]))
         print("   set-up  (entry -> barriers)    :", q(rel[:, 1] - rel[:, 0]))
         ld = t[:, 3] > 0                              # CTAs that issue MMAs (all of them, or the pair leaders)
-        print("   first TMA round trip           :", q((rel[:, 3] - rel[:, 2])[ld]))
+        print("   setup done -> first data landed:", q((rel[:, 3] - rel[:, 1])[ld]))
         print("   main loop (first data -> issued):", q((rel[:, 4] - rel[:, 3])[ld]))
         print("   drain (issued -> acc complete) :", q((rel[:, 5] - rel[:, 4])[ld]))
-        print("   epilogue                       :", q(rel[:, 6] - rel[:, 5]))
+        print("   epilogue: TMEM -> smem staging :", q(rel[:, 2] - rel[:, 5]))
+        print("   epilogue: smem -> global stores:", q(rel[:, 6] - rel[:, 2]))
         print("   CTA life                       :", q(rel[:, 6] - rel[:, 0]))
         sm = t[:, 7]
         per_sm = torch.bincount(sm)

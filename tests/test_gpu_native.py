@@ -435,13 +435,14 @@ def test_stem_gemm_gathers_unpadded_filter(N, kvalid, M, relu):
 @pytest.mark.parametrize("model", ["resnet18", "cnn_mnist"])
 def test_fused_handoff_equals_round_init_path(model):
     """Round hand-off fused with the first local GEMM (no round_init pass; first step reads the broadcast buffer, zero momentum) must
-    train exactly like the unfused path.  Checked where the comparison is sharp: FedAvg without the (discontinuous) sign vote, one
-    local step per agent and round -- every step is a FIRST step -- so the only difference left between the two runs is the
-    summation order of the split-K weight-gradient atomics; then two more rounds must stay close."""
+    train like the unfused path.  Checked where the comparison is sharp: FedAvg without the (discontinuous) sign vote, one local step
+    per agent and round -- every step is a FIRST step.  The only legitimate difference between two runs is the summation order of the
+    split-K weight-gradient atomics, so the yardstick is the run-to-run difference of the UNFUSED path with itself (BatchNorm at random
+    init amplifies that noise to ~1e-3): the fused run may differ from an unfused run by at most 3x that (+1e-5)."""
     from rlr_b200.engine import FLEngine
     from rlr_b200.options import make_args
-    res = {}
-    for fused in (False, True):
+
+    def run(fused):
         data = "cifar10" if model == "resnet18" else "fmnist"
         args = make_args(data=data, model=model, num_agents=3, local_ep=1, bs=64, synthetic=192, synthetic_val=64, log_dir="", device=DEV,
                          seed=4, no_fused_handoff=not fused)
@@ -452,10 +453,11 @@ def test_fused_handoff_equals_round_init_path(model):
             eng.run_round(r)
             snaps.append(eng.global_params().clone())
         torch.cuda.synchronize()
-        res[fused] = snaps
         eng.close()
-    d1 = _rms_rel(res[True][0] - res[False][0] + res[False][0], res[False][0])
-    upd = [(res[False][i] - (res[False][i - 1] if i else 0 * res[False][0])) for i in range(3)]
-    print(model, "round-1 rms-rel difference fused vs unfused:", d1, " after 3 rounds:", _rms_rel(res[True][2], res[False][2]))
-    assert d1 < 1e-4, d1
-    assert _rms_rel(res[True][2], res[False][2]) < 2e-2
+        return snaps
+    a, b, f = run(False), run(False), run(True)
+    noise1, diff1 = _rms_rel(b[0], a[0]), _rms_rel(f[0], a[0])
+    noise3, diff3 = _rms_rel(b[2], a[2]), _rms_rel(f[2], a[2])
+    print(model, f"round 1: unfused-vs-unfused {noise1:.2e}, fused-vs-unfused {diff1:.2e} | round 3: {noise3:.2e} vs {diff3:.2e}")
+    assert diff1 <= 3 * noise1 + 1e-5, (diff1, noise1)
+    assert diff3 <= 3 * noise3 + 1e-4, (diff3, noise3)
