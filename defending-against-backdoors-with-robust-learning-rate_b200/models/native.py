@@ -33,6 +33,10 @@ ACT = torch.bfloat16   # default activation / GEMM-operand dtype on GPU (tests m
 # kernel is queued on a side stream (forked / joined with events, so it becomes a parallel branch of the captured step graph) while the
 # data-gradient / BatchNorm chain continues on the main stream.  Measured on B200: ResNet-18 round 1065.7 -> 1030.0 ms (same box,
 # profiles/r2_step_ab.md).  RLR_WGRAD_OVERLAP=0 serialises them again.
+# partial-sum slots of the per-channel reductions: with N > 1 the CTAs of channel_reduce_kernel spread their atomics over N buffers
+# (consumers sum them) and the reductions run four / three CTAs per SM instead of two.  Measured on B200 (profiles/r2_step_ab.md):
+# 4 slots = +3.3 % round time, i.e. the two-CTA grid of round 1 stays the default; the knob is kept for re-measurement.
+FWD_SLOTS = BWD_SLOTS = max(1, int(os.environ.get("RLR_BN_SLOTS", "1")))
 WGRAD_OVERLAP = bool(int(os.environ.get("RLR_WGRAD_OVERLAP", "1")))
 
 
@@ -227,12 +231,13 @@ class NativeNet:
         S = ops.STAT_SLOTS
         tot = sum(2 * op.out_shape[-1] for op in need)
         self.stats_arena = torch.zeros(max(1, tot * S), dtype=torch.float32, device=dev)   # forward: [slots][sum, sum^2][C] per op
-        self.dsum_arena = torch.zeros(max(1, tot), dtype=torch.float32, device=dev)        # backward: sum dy, sum dy*xhat
+        D = BWD_SLOTS
+        self.dsum_arena = torch.zeros(max(1, tot * D), dtype=torch.float32, device=dev)    # backward: [slots][sum dy, sum dy*xhat][C] per op
         off = 0
         for op in need:
             c = op.out_shape[-1]
             op.saved["stats"] = self.stats_arena[off * S:(off + 2 * c) * S].view(S, 2, c)
-            op.saved["dsum"] = self.dsum_arena[off:off + 2 * c].view(2, c)
+            op.saved["dsum"] = self.dsum_arena[off * D:(off + 2 * c) * D].view(D, 2, c)
             op.saved["mean_rstd"] = torch.zeros(2, c, dtype=torch.float32, device=dev)
             off += 2 * c
         for op in self.plan:
@@ -399,7 +404,7 @@ class NativeNet:
         count = x.numel() // x.shape[-1]
         ops.bn_fwd(x, y, res, gamma, beta, rm, rv, stats, op.saved["mean_rstd"], count, a.get("eps", 1e-5),
                    a.get("momentum", 0.1), train, op.relu, self.impl["bn"],
-                   stats_buf=op.saved["stats"][0:1] if train else None)   # slot 0 of the (pre-zeroed) statistics arena
+                   stats_buf=op.saved["stats"][0:FWD_SLOTS] if train else None)   # first slots of the (pre-zeroed) statistics arena
 
     def _bwd_bn(self, op, B):
         x, y, dy = self.T(op.x, B), self.T(op.y, B), self.G(op.y, B)

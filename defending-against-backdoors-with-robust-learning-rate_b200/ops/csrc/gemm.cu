@@ -57,7 +57,8 @@ struct __align__(8) SharedTail {
 
 template <int BN, bool kStats, bool kBMN, int kOcc = 2>
 __global__ void __launch_bounds__(kThreads, kOcc)
-umma_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvGemmParams p) {
+umma_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+                      const ConvGemmParams p) {
     using Cfg = TileCfg<BN, kOcc>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -80,6 +81,7 @@ umma_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA);
         prefetch_tmap(&tmB);
+        if (p.tma_store) prefetch_tmap(&tmC);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&tail->full[s], p.split_prod ? 2 : 1); mbar_init(&tail->empty[s], 1); }
@@ -224,33 +226,71 @@ umma_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             for (int i = et; i < 2 * BN; i += kEpiThreads) red[i] = 0.f;
             asm volatile("bar.sync 1, 128;" ::: "memory");
         }
+        const bool tma_out = !kStats && p.tma_store;
+        // TMEM -> registers two 32-column loads at a time (one wait for both), bias / ReLU / bf16 pack, -> staging tile.
+        // Staging layout: TMA-store path = 128-byte-swizzled [64-channel group][128 rows][128 B] tiles (what cp.async.bulk.tensor reads);
+        //                 accumulate / statistics path = padded row pitch for the coalesced read-modify-write stores below.
 #pragma unroll
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld_32x32(tmem_acc + ((uint32_t)lane_base << 16) + c0, v);
-            uint32_t packed[16];
-            float f1[32], f2[32];
+        for (int c0 = 0; c0 < BN; c0 += 64) {
+            uint32_t vv[2][32];
+            tmem_ld_32x32_nowait(tmem_acc + ((uint32_t)lane_base << 16) + c0, vv[0]);
+            tmem_ld_32x32_nowait(tmem_acc + ((uint32_t)lane_base << 16) + c0 + 32, vv[1]);
+            tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-                float a = __uint_as_float(v[j]), b = __uint_as_float(v[j + 1]);
-                if (p.bias && col0 + c0 + j < p.N) { a += p.bias[col0 + c0 + j]; b += p.bias[col0 + c0 + j + 1]; }
-                if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-                packed[j >> 1] = pack_bf16x2(a, b);
-                if (kStats) {   // statistics of the bf16-rounded values BatchNorm will read back; masked rows count as zero
-                    const float2 rq = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&packed[j >> 1]));
-                    f1[j] = row_ok ? rq.x : 0.f; f1[j + 1] = row_ok ? rq.y : 0.f;
-                    f2[j] = f1[j] * f1[j]; f2[j + 1] = f1[j + 1] * f1[j + 1];
+            for (int h = 0; h < 2; ++h) {
+                const int cc = c0 + h * 32;
+                uint32_t (&v)[32] = vv[h];
+                uint32_t packed[16];
+                float f1[32], f2[32];
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    float a = __uint_as_float(v[j]), b = __uint_as_float(v[j + 1]);
+                    if (p.bias && col0 + cc + j < p.N) { a += p.bias[col0 + cc + j]; b += p.bias[col0 + cc + j + 1]; }
+                    if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+                    packed[j >> 1] = pack_bf16x2(a, b);
+                    if (kStats) {   // statistics of the bf16-rounded values BatchNorm will read back; masked rows count as zero
+                        const float2 rq = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&packed[j >> 1]));
+                        f1[j] = row_ok ? rq.x : 0.f; f1[j + 1] = row_ok ? rq.y : 0.f;
+                        f2[j] = f1[j] * f1[j]; f2[j + 1] = f1[j + 1] * f1[j + 1];
+                    }
+                }
+                if (tma_out) {
+                    uint8_t* gbase = staging + (cc >> 6) * (BM * 128) + row * 128;     // 64-channel group tile, this thread's 128-byte row
+                    const int ch0 = (cc & 63) >> 3;                                    // first 16-byte chunk of this 32-column piece
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        *reinterpret_cast<uint4*>(gbase + (((ch0 + q) ^ (row & 7)) << 4)) =
+                            make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+                } else {
+                    uint4* dst = reinterpret_cast<uint4*>(staging + row * Cfg::kPitch + cc * 2);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) dst[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+                }
+                if (kStats) {   // warp-level column sums (31 shuffles each), 4 warps meet in shared memory
+                    const float c1 = warp_transpose_sum32(f1, lane), c2 = warp_transpose_sum32(f2, lane);
+                    atomicAdd(&red[cc + lane], c1);
+                    atomicAdd(&red[BN + cc + lane], c2);
                 }
             }
-            uint4* dst = reinterpret_cast<uint4*>(staging + row * Cfg::kPitch + c0 * 2);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) dst[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
-            if (kStats) {   // warp-level column sums (31 shuffles each), 4 warps meet in shared memory
-                const float c1 = warp_transpose_sum32(f1, lane), c2 = warp_transpose_sum32(f2, lane);
-                atomicAdd(&red[c0 + lane], c1);
-                atomicAdd(&red[BN + c0 + lane], c2);
-            }
         }
+        if (tma_out) {
+            fence_proxy_async_smem();                        // generic-proxy staging writes -> TMA (async proxy) reads
+            tc_fence_before();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (dbg && et == 0) dbg[2] = (long long)gtimer();
+            if (et == 0) {
+                // one TMA tensor store per 64-channel group: the box is the tile's pixel box of the NHWC output (rows / columns outside
+                // the tensor are clipped by the TMA unit) -- no per-thread address arithmetic, fully coalesced, asynchronous
+#pragma unroll
+                for (int g = 0; g < BN / 64; ++g) {
+                    if (col0 + g * 64 >= p.N) break;
+                    if (p.mode == 1) tma_store_4d(&tmC, staging + g * (BM * 128), col0 + g * 64, w0, h0, n0);
+                    else tma_store_2d(&tmC, staging + g * (BM * 128), col0 + g * 64, tile_m * BM);
+                }
+                tma_store_commit_and_wait_read();
+                if (dbg) dbg[6] = (long long)gtimer();
+            }
+        } else {
         tc_fence_before();
         asm volatile("bar.sync 1, 128;" ::: "memory");   // epilogue-only named barrier: staging tile complete
         if (dbg && et == 0) dbg[2] = (long long)gtimer();   // TMEM -> registers -> shared staging done
@@ -296,6 +336,7 @@ umma_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 if (col0 + (i % BN) < p.N)
                     atomicAdd(p.stats + (size_t)(blockIdx.x % kStatSlots) * 2 * p.N + (i < BN ? 0 : p.N) + col0 + (i % BN), red[i]);
         }
+        }   // !tma_out
     }
     // ---- teardown ----------------------------------------------------------------------------------------------------------
     tc_fence_before();
@@ -360,7 +401,8 @@ static int conv_occ3() {
 
 // default (RLR_CONV_OCC3=0 disables): 64-wide tiles with a 3-stage ring at three CTAs per SM (three TMA producers / MMA issue threads per SM)
 template <int BN>
-static cudaError_t launch_bn_occ3(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, int m_tiles, cudaStream_t st) {
+static cudaError_t launch_bn_occ3(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const ConvGemmParams& p, int m_tiles,
+                                  cudaStream_t st) {
     using Cfg = TileCfg<BN, 3>;
     static bool configured = false;
     if (!configured) {
@@ -369,8 +411,8 @@ static cudaError_t launch_bn_occ3(const CUtensorMap& tmA, const CUtensorMap& tmB
         configured = true;
     }
     dim3 grid(m_tiles, (p.N + BN - 1) / BN);
-    if (p.b_mn) return launch_kernel(umma_conv_gemm_kernel<BN, false, true, 3>, grid, dim3(kThreads), Cfg::kSmemBytes, st, tmA, tmB, p);
-    return launch_kernel(umma_conv_gemm_kernel<BN, false, false, 3>, grid, dim3(kThreads), Cfg::kSmemBytes, st, tmA, tmB, p);
+    if (p.b_mn) return launch_kernel(umma_conv_gemm_kernel<BN, false, true, 3>, grid, dim3(kThreads), Cfg::kSmemBytes, st, tmA, tmB, tmC, p);
+    return launch_kernel(umma_conv_gemm_kernel<BN, false, false, 3>, grid, dim3(kThreads), Cfg::kSmemBytes, st, tmA, tmB, tmC, p);
 }
 
 // gemm_2cta.cu (opt-in, RLR_CONV_2CTA=1): CTA pairs, tcgen05.mma.cta_group::2 with M = 256, half of the B tile per CTA
@@ -430,16 +472,42 @@ static long long* g_trace = nullptr;
 void set_conv_trace(long long* buf) { g_trace = buf; }
 long long* conv_trace_buf() { return g_trace; }
 
+static int g_tma_store = -1;    // epilogue through TMA tensor stores (default on; RLR_TMA_STORE=0 restores the per-thread coalesced stores)
+void set_conv_tma_store(int on) { g_tma_store = on ? 1 : 0; }
+static bool tma_store_enabled() {
+    if (g_tma_store < 0) { const char* e = getenv("RLR_TMA_STORE"); g_tma_store = (e && atoi(e) == 0) ? 0 : 1; }
+    return g_tma_store != 0;
+}
+// Output tensor map for the TMA-store epilogue: the [M][N] matrix (plain) or the NHWC image grid the tile's pixel box addresses
+// (conv; a strided data-gradient plane is expressed through doubled global strides and an offset base).  64-channel (128-byte) boxes.
+static cudaError_t make_out_tmap(CUtensorMap* tmC, const ConvGemmParams& p) {
+    if (p.ldc % 8) return cudaErrorInvalidValue;
+    if (p.mode == 1) {
+        const uint64_t d[4] = {(uint64_t)p.N, (uint64_t)p.Wo, (uint64_t)p.Ho, (uint64_t)p.NB};
+        const uint64_t s[3] = {(uint64_t)p.out_stride * p.ldc * 2, (uint64_t)p.out_stride * p.OutW * p.ldc * 2, (uint64_t)p.OutH * p.OutW * p.ldc * 2};
+        const uint32_t b[4] = {64, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN};
+        const char* base = reinterpret_cast<const char*>(p.out) + ((size_t)p.out_ph * p.OutW + p.out_pw) * p.ldc * 2;
+        return make_tmap_bf16(tmC, base, 4, d, s, b);
+    }
+    const uint64_t d[2] = {(uint64_t)p.N, (uint64_t)p.M}, s[1] = {(uint64_t)p.ldc * 2};
+    const uint32_t b[2] = {64, BM};
+    return make_tmap_bf16(tmC, p.out, 2, d, s, b);
+}
+
 template <int BN>
 static cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p_in, int m_tiles, cudaStream_t st) {
     using Cfg = TileCfg<BN>;
     ConvGemmParams p = p_in;
     p.dbg = g_trace;
-    if (g_split_prod < 0) { const char* e = getenv("RLR_SPLIT_PRODUCER"); g_split_prod = (e && atoi(e) > 0) ? 1 : 0; }
+    CUtensorMap tmC = tmA;                                       // dummy unless the TMA-store epilogue applies
+    p.tma_store = 0;
+    if (tma_store_enabled() && !p.accumulate && !p.stats && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) && make_out_tmap(&tmC, p) == cudaSuccess)
+        p.tma_store = 1;
+    if (g_split_prod < 0) { const char* e = getenv("RLR_SPLIT_PRODUCER"); g_split_prod = (e && atoi(e) == 0) ? 0 : 1; }   // default on: -2.2 % per round (profiles/r2_step_ab.md)
     p.split_prod = (g_split_prod && !p.b_src) ? 1 : 0;
     if (!p.stats && !p.b_src && persistent_sms() > 0 && m_tiles * ((p.N + BN - 1) / BN) > persistent_sms())
         return launch_persistent_bn<BN>(tmA, tmB, p, m_tiles, persistent_sms(), st);
-    if (!p.stats && conv_occ3() >= (BN == 64 ? 1 : 2)) return launch_bn_occ3<BN>(tmA, tmB, p, m_tiles, st);
+    if (!p.stats && conv_occ3() >= (BN == 64 ? 1 : 2)) return launch_bn_occ3<BN>(tmA, tmB, tmC, p, m_tiles, st);
     static bool configured = false;
     if (!configured) {
         RLR_CUDA_CHECK(cudaFuncSetAttribute(umma_conv_gemm_kernel<BN, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -448,9 +516,9 @@ static cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, con
         configured = true;
     }
     dim3 grid(m_tiles, (p.N + BN - 1) / BN);
-    if (p.b_mn) return launch_kernel(umma_conv_gemm_kernel<BN, false, true>, grid, dim3(kThreads), Cfg::kSmemBytes, st, tmA, tmB, p);
-    if (p.stats) return launch_kernel(umma_conv_gemm_kernel<BN, true, false>, grid, dim3(kThreads), Cfg::kSmemBytes, st, tmA, tmB, p);
-    return launch_kernel(umma_conv_gemm_kernel<BN, false, false>, grid, dim3(kThreads), Cfg::kSmemBytes, st, tmA, tmB, p);
+    if (p.b_mn) return launch_kernel(umma_conv_gemm_kernel<BN, false, true>, grid, dim3(kThreads), Cfg::kSmemBytes, st, tmA, tmB, tmC, p);
+    if (p.stats) return launch_kernel(umma_conv_gemm_kernel<BN, true, false>, grid, dim3(kThreads), Cfg::kSmemBytes, st, tmA, tmB, tmC, p);
+    return launch_kernel(umma_conv_gemm_kernel<BN, false, false>, grid, dim3(kThreads), Cfg::kSmemBytes, st, tmA, tmB, tmC, p);
 }
 
 static int pick_bn(int N) { return (N % 128 == 0) ? 128 : 64; }

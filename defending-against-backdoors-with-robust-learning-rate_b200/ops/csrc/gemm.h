@@ -31,6 +31,7 @@ struct ConvGemmParams {
     // With wait_flags the producer first acquires the broadcast-ready words [wait_lo, wait_hi] (>= *wait_epoch): b_src then points into
     // the NVLS-multicast parameter shadow that the aggregation kernels of ALL GPUs are still filling -- the first local-forward GEMM of
     // a round starts as soon as the slice holding its filter has landed (broadcast (+) first-GEMM fusion, parallel/fused_agg.py).
+    int tma_store;             // 1: epilogue writes the tile with TMA tensor stores from a swizzled staging tile (tmC valid; no accumulate / stats)
     int split_prod;            // 1: two TMA producer threads per CTA (warp 0 loads A, warp 2 loads B): two request streams into the TMA unit
     long long* dbg;            // optional [CTAs][8] timeline (globaltimer ns): entry, setup done, first TMA issued, first data landed,
                                // all MMAs issued, accumulator complete, epilogue done, SM id  (scripts/trace_conv.py)
@@ -66,6 +67,7 @@ void set_persistent_conv(int on);
 // three CTAs per SM: level 0 never, 1 (default) for the 64-wide tile, 2 also for the 128-wide tile (RLR_CONV_OCC3 env)
 void set_conv_occ3(int level);
 // per-CTA timeline buffer for the NEXT launches of the generic conv / GEMM kernel (nullptr = off); see ConvGemmParams::dbg
+void set_conv_tma_store(int on);           // epilogue via TMA tensor stores (default on; RLR_TMA_STORE=0)
 void set_conv_split_producer(int on);      // experiment: two TMA producer threads per CTA (RLR_SPLIT_PRODUCER env)
 void set_conv_trace(long long* buf);
 long long* conv_trace_buf();
@@ -93,8 +95,8 @@ cudaError_t launch_linear_wgrad_bf16(const void* dy, const void* x, float* dW, i
 // ---- norm.cu: NHWC bf16 layer kernels -----------------------------------------------------------------------------
 // per-channel sum / sum of squares of x[M][C]
 // only_sum: accumulate just sum x into stats[0..C) (bias gradients written straight into the flat gradient)
-cudaError_t launch_channel_stats(const __nv_bfloat16* x, long long M, int C, float* stats /*[2][C], accumulates*/, int num_sms, cudaStream_t st,
-                                 int only_sum = 0);
+cudaError_t launch_channel_stats(const __nv_bfloat16* x, long long M, int C, float* stats /*[nslots][2][C], accumulates*/, int num_sms, cudaStream_t st,
+                                 int only_sum = 0, int nslots = 1);
 // finalize statistics: mean/rstd (+ running stats update with momentum, unbiased variance)
 cudaError_t launch_bn_finalize(const float* stats, int slots, float* mean_rstd, float* running_mean, float* running_var, int C,
                                float count, float eps, float momentum, int train, cudaStream_t st);
@@ -106,12 +108,12 @@ cudaError_t launch_bn_apply(const __nv_bfloat16* x, const __nv_bfloat16* res, __
                             float eps, float momentum, float* running_mean, float* running_var, int num_sms, cudaStream_t st);
 // dsum[0][c] = sum dz, dsum[1][c] = sum dz * xhat   (dz = dy * mask; relu 1: mask = (y > 0), relu 2: mask recomputed from x, gamma, beta)
 cudaError_t launch_bn_bwd_reduce(const __nv_bfloat16* dy, const __nv_bfloat16* y, const __nv_bfloat16* x, const float* mean_rstd,
-                                 float* dsum /*accumulates*/, long long M, int C, int relu, int num_sms, cudaStream_t st,
-                                 const float* gamma = nullptr, const float* beta = nullptr);
+                                 float* dsum /*[nslots][2][C], accumulates*/, long long M, int C, int relu, int num_sms, cudaStream_t st,
+                                 const float* gamma = nullptr, const float* beta = nullptr, int nslots = 1);
 // dx = gamma * rstd * (dz - dsum0/M - xhat * dsum1/M); dres = dz; dgamma = dsum1, dbeta = dsum0
 cudaError_t launch_bn_bwd_apply(const __nv_bfloat16* dy, const __nv_bfloat16* y, const __nv_bfloat16* x, const float* gamma,
                                 const float* mean_rstd, const float* dsum, __nv_bfloat16* dx, __nv_bfloat16* dres, float* dgamma,
-                                float* dbeta, long long M, int C, int relu, int num_sms, cudaStream_t st, const float* beta = nullptr);
+                                float* dbeta, long long M, int C, int relu, int num_sms, cudaStream_t st, const float* beta = nullptr, int nslots = 1);
 cudaError_t launch_relu_bwd(__nv_bfloat16* dy, const __nv_bfloat16* y, long long n, int num_sms, cudaStream_t st);
 cudaError_t launch_maxpool2_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, uint8_t* idx, int B, int H, int W, int C, cudaStream_t st);
 cudaError_t launch_maxpool2_bwd(const __nv_bfloat16* dy, const uint8_t* idx, __nv_bfloat16* dx, int B, int H, int W, int C, cudaStream_t st);

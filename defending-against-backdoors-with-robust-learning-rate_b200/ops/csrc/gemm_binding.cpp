@@ -167,7 +167,9 @@ void linear_wgrad_bf16(at::Tensor dy, at::Tensor x, at::Tensor dW) {
 void channel_stats(at::Tensor x, at::Tensor stats) {
     c10::cuda::CUDAGuard g(x.device());
     const int C = x.size(-1);
-    check(rlr::launch_channel_stats(bf(x), x.numel() / C, C, f32(stats), num_sms(), cur_stream()), "channel_stats");
+    const int nslots = (int)(stats.numel() / (2 * C));       // stats is [nslots][2][C]: CTAs spread their atomics over the slots
+    TORCH_CHECK(nslots >= 1 && stats.numel() == (int64_t)nslots * 2 * C, "stats must be [slots, 2, C]");
+    check(rlr::launch_channel_stats(bf(x), x.numel() / C, C, f32(stats), num_sms(), cur_stream(), 0, nslots), "channel_stats");
 }
 // bias gradient: db[C] += sum over rows of dy[M][C]  (db is a slice of the flat fp32 gradient, zero or partially accumulated on entry)
 void bias_grad(at::Tensor dy, at::Tensor db) {
@@ -205,11 +207,14 @@ void bn_bwd(at::Tensor dy, at::Tensor y, at::Tensor x, at::Tensor gamma, at::Ten
     c10::cuda::CUDAGuard g(x.device());
     const int C = x.size(-1);
     const long long M = x.numel() / C;
-    if (zero_dsum) check(cudaMemsetAsync(dsum.data_ptr(), 0, sizeof(float) * 2 * C, cur_stream()), "bn_bwd/memset");
-    check(rlr::launch_bn_bwd_reduce(bf(dy), bf(y), bf(x), f32(mean_rstd), f32(dsum), M, C, relu, num_sms(), cur_stream()), "bn_bwd_reduce");
+    const int nslots = (int)(dsum.numel() / (2 * C));         // dsum is [nslots][2][C]
+    TORCH_CHECK(nslots >= 1 && dsum.numel() == (int64_t)nslots * 2 * C, "dsum must be [slots, 2, C]");
+    if (zero_dsum) check(cudaMemsetAsync(dsum.data_ptr(), 0, sizeof(float) * dsum.numel(), cur_stream()), "bn_bwd/memset");
+    check(rlr::launch_bn_bwd_reduce(bf(dy), bf(y), bf(x), f32(mean_rstd), f32(dsum), M, C, relu, num_sms(), cur_stream(), nullptr, nullptr, nslots),
+          "bn_bwd_reduce");
     check(rlr::launch_bn_bwd_apply(bf(dy), bf(y), bf(x), (const float*)gamma.data_ptr(), f32(mean_rstd), f32(dsum), bfm(dx),
                                    const_cast<__nv_bfloat16*>(bfo(dres)), (float*)dgamma.data_ptr(), (float*)dbeta.data_ptr(), M, C, relu,
-                                   num_sms(), cur_stream()), "bn_bwd_apply");
+                                   num_sms(), cur_stream(), nullptr, nslots), "bn_bwd_apply");
 }
 // BatchNorm + ReLU without a residual: the ReLU mask is recomputed from x (same expression as the forward), y is never read
 void bn_bwd_recompute(at::Tensor dy, at::Tensor x, at::Tensor gamma, at::Tensor beta, at::Tensor mean_rstd, at::Tensor dsum, at::Tensor dx,
@@ -217,12 +222,14 @@ void bn_bwd_recompute(at::Tensor dy, at::Tensor x, at::Tensor gamma, at::Tensor 
     c10::cuda::CUDAGuard g(x.device());
     const int C = x.size(-1);
     const long long M = x.numel() / C;
-    if (zero_dsum) check(cudaMemsetAsync(dsum.data_ptr(), 0, sizeof(float) * 2 * C, cur_stream()), "bn_bwd/memset");
+    const int nslots = (int)(dsum.numel() / (2 * C));
+    TORCH_CHECK(nslots >= 1 && dsum.numel() == (int64_t)nslots * 2 * C, "dsum must be [slots, 2, C]");
+    if (zero_dsum) check(cudaMemsetAsync(dsum.data_ptr(), 0, sizeof(float) * dsum.numel(), cur_stream()), "bn_bwd/memset");
     check(rlr::launch_bn_bwd_reduce(bf(dy), nullptr, bf(x), f32(mean_rstd), f32(dsum), M, C, 2, num_sms(), cur_stream(),
-                                    (const float*)gamma.data_ptr(), (const float*)beta.data_ptr()), "bn_bwd_reduce(recompute)");
+                                    (const float*)gamma.data_ptr(), (const float*)beta.data_ptr(), nslots), "bn_bwd_reduce(recompute)");
     check(rlr::launch_bn_bwd_apply(bf(dy), nullptr, bf(x), (const float*)gamma.data_ptr(), f32(mean_rstd), f32(dsum), bfm(dx), nullptr,
                                    (float*)dgamma.data_ptr(), (float*)dbeta.data_ptr(), M, C, 2, num_sms(), cur_stream(),
-                                   (const float*)beta.data_ptr()), "bn_bwd_apply(recompute)");
+                                   (const float*)beta.data_ptr(), nslots), "bn_bwd_apply(recompute)");
 }
 void relu_bwd(at::Tensor dy, at::Tensor y) {
     c10::cuda::CUDAGuard g(dy.device());
@@ -309,6 +316,7 @@ void register_gemm_bindings(py::module_& m) {
     m.def("set_conv_2cta", [](int64_t mode) { rlr::set_conv_2cta((int)mode); });   // 0 off | 1 CTA pairs | 2 + deep single-wave variant
     m.def("set_pdl", [](bool on) { rlr::set_pdl(on ? 1 : 0); });
     m.def("set_conv_occ3", [](int64_t level) { rlr::set_conv_occ3((int)level); });
+    m.def("set_conv_tma_store", [](bool on) { rlr::set_conv_tma_store(on ? 1 : 0); });
     m.def("set_conv_split_producer", [](bool on) { rlr::set_conv_split_producer(on ? 1 : 0); });
     m.def("set_conv_trace", [](c10::optional<at::Tensor> buf) {   // int64 [CTAs * 8] timeline buffer for the next generic conv / GEMM launches
         rlr::set_conv_trace(buf.has_value() && buf->defined() ? reinterpret_cast<long long*>(buf->data_ptr<int64_t>()) : nullptr);

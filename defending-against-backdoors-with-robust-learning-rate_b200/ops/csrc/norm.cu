@@ -3,6 +3,8 @@
 // max-pool, global average pool, dropout (Philox), space-to-depth for strided convs, filter transpose for dgrad, and
 // the tiny classifier heads.  They replace the ATen elementwise / cuDNN-BN calls behind autograd in the reference's
 // local step (src/agent.py:46-48) and are what the tcgen05 conv kernels hand their outputs to.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "gemm.h"
 
@@ -39,7 +41,8 @@ __global__ void __launch_bounds__(256, MODE == 0 ? 4 : 3) channel_reduce_kernel(
                                                                const __nv_bfloat16* __restrict__ y, const float* __restrict__ mean_rstd,
                                                                float* out, long long M, int C, int relu,
                                                                const float* __restrict__ gamma = nullptr, const float* __restrict__ beta = nullptr,
-                                                               int out_cols = 0 /*0: both rows (2C values) | C: only the first row (bias gradients)*/) {
+                                                               int out_cols = 0 /*0: both rows (2C values) | C: only the first row (bias gradients)*/,
+                                                               int nslots = 1 /*partial buffers out[nslots][2][C]: CTA b adds into slot b % nslots*/) {
     // relu: 0 none | 1 mask = (y > 0) from the stored output | 2 mask recomputed as (x * scale + shift > 0) with exactly the
     // expression of bn_apply_kernel -- BatchNorm + ReLU without a residual: the output tensor is not read at all
     extern __shared__ float sh[];   // [rpi][2][C] per-row-slot partials (16 KB for every C)
@@ -107,28 +110,30 @@ __global__ void __launch_bounds__(256, MODE == 0 ? 4 : 3) channel_reduce_kernel(
     for (int i = 0; i < 8; ++i) { mine[i] = a[i]; mine[C + i] = b[i]; }
     __syncthreads();
     const int ncols = out_cols > 0 ? out_cols : 2 * C;
+    float* dst = out + (size_t)(blockIdx.x % nslots) * 2 * C;       // same-address atomics spread over the slots
     for (int i = threadIdx.x; i < ncols; i += 256) {
         float t = 0.f;
         for (int r = 0; r < rpi; ++r) t += sh[(size_t)r * 2 * C + i];
-        atomicAdd(out + i, t);
+        atomicAdd(dst + i, t);
     }
 }
 
-cudaError_t launch_channel_stats(const __nv_bfloat16* x, long long M, int C, float* stats, int num_sms, cudaStream_t st, int only_sum) {
-    if (!chan_ok(C)) return cudaErrorInvalidValue;
+cudaError_t launch_channel_stats(const __nv_bfloat16* x, long long M, int C, float* stats, int num_sms, cudaStream_t st, int only_sum, int nslots) {
+    if (!chan_ok(C) || nslots < 1) return cudaErrorInvalidValue;
     const int rpi = 256 / (C / 8);
-    return launch_kernel(channel_reduce_kernel<0, false>, dim3(rows_grid(M, rpi * 8, num_sms, 2)), dim3(256), (size_t)rpi * 2 * C * sizeof(float), st,
-                         x, nullptr, nullptr, nullptr, stats, M, C, 0, nullptr, nullptr, only_sum ? C : 0);
+    // four CTAs per SM (twice the bytes in flight of the two-CTA grid) once the atomics have slots to spread over
+    return launch_kernel(channel_reduce_kernel<0, false>, dim3(rows_grid(M, rpi * 8, num_sms, nslots >= 4 ? 4 : 2)), dim3(256),
+                         (size_t)rpi * 2 * C * sizeof(float), st, x, nullptr, nullptr, nullptr, stats, M, C, 0, nullptr, nullptr, only_sum ? C : 0, nslots);
 }
 cudaError_t launch_bn_bwd_reduce(const __nv_bfloat16* dy, const __nv_bfloat16* y, const __nv_bfloat16* x, const float* mean_rstd,
                                  float* dsum, long long M, int C, int relu, int num_sms, cudaStream_t st, const float* gamma,
-                                 const float* beta) {
-    if (!chan_ok(C) || (relu == 2 && (!gamma || !beta)) || (relu == 1 && !y)) return cudaErrorInvalidValue;
+                                 const float* beta, int nslots) {
+    if (!chan_ok(C) || (relu == 2 && (!gamma || !beta)) || (relu == 1 && !y) || nslots < 1) return cudaErrorInvalidValue;
     const int rpi = 256 / (C / 8);
-    const int grid = rows_grid(M, rpi * 8, num_sms, 2);
+    const int grid = rows_grid(M, rpi * 8, num_sms, nslots >= 3 ? 3 : 2);
     const size_t smem = (size_t)rpi * 2 * C * sizeof(float);
-    if (relu == 2) return launch_kernel(channel_reduce_kernel<1, true>, dim3(grid), dim3(256), smem, st, x, dy, y, mean_rstd, dsum, M, C, relu, gamma, beta, 0);
-    return launch_kernel(channel_reduce_kernel<1, false>, dim3(grid), dim3(256), smem, st, x, dy, y, mean_rstd, dsum, M, C, relu, nullptr, nullptr, 0);
+    if (relu == 2) return launch_kernel(channel_reduce_kernel<1, true>, dim3(grid), dim3(256), smem, st, x, dy, y, mean_rstd, dsum, M, C, relu, gamma, beta, 0, nslots);
+    return launch_kernel(channel_reduce_kernel<1, false>, dim3(grid), dim3(256), smem, st, x, dy, y, mean_rstd, dsum, M, C, relu, nullptr, nullptr, 0, nslots);
 }
 
 __global__ void bn_finalize_kernel(const float* __restrict__ stats, int slots, float* __restrict__ mean_rstd, float* running_mean,
@@ -165,7 +170,8 @@ struct BnFinalize {
     float count, eps, momentum;
     float* running_mean; float* running_var;
 };
-__global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
+template <int U, int kMinBlocks>
+__global__ void __launch_bounds__(256, kMinBlocks) bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
                                                          __nv_bfloat16* __restrict__ y, const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, float* __restrict__ mean_rstd,
                                                          long long M, int C, int relu, BnFinalize fin) {
@@ -198,21 +204,34 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __re
         sc[i] = gamma[c] * rstd;
         sh[i] = beta[c] - mean * sc[i];
     }
-    for (long long r = (long long)blockIdx.x * rpi + ry; r < M; r += (long long)gridDim.x * rpi) {
-        const size_t off = (size_t)r * C + cg * 8;
-        bf8 v = load8(x + off);
+    // U rows per thread in flight (all loads issued before the first use): one 16-byte load per thread and iteration leaves the kernel
+    // latency-bound at ~3.9 TB/s (32 KB in flight per SM); measured same-box A/B in profiles/r2_step_ab.md
+    const long long stride = (long long)gridDim.x * rpi;
+    for (long long r0 = (long long)blockIdx.x * rpi + ry; r0 < M; r0 += stride * U) {
+        uint4 xr[U], rr[U];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v.v[i] = v.v[i] * sc[i] + sh[i];
-        if (res) {
-            const bf8 rv = load8(res + off);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v.v[i] += rv.v[i];
+        for (int u = 0; u < U; ++u) {
+            const long long r = r0 + u * stride;
+            const size_t off = (size_t)(r < M ? r : r0) * C + cg * 8;
+            xr[u] = *reinterpret_cast<const uint4*>(x + off);
+            if (res) rr[u] = *reinterpret_cast<const uint4*>(res + off);
         }
-        if (relu) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v.v[i] = fmaxf(v.v[i], 0.f);
+        for (int u = 0; u < U; ++u) {
+            const long long r = r0 + u * stride;
+            if (r >= M) continue;
+            const __nv_bfloat162* xh = reinterpret_cast<const __nv_bfloat162*>(&xr[u]);
+            const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&rr[u]);
+            bf8 v;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 xv = __bfloat1622float2(xh[i]);
+                v.v[2 * i] = xv.x * sc[2 * i] + sh[2 * i]; v.v[2 * i + 1] = xv.y * sc[2 * i + 1] + sh[2 * i + 1];
+                if (res) { const float2 q = __bfloat1622float2(rh[i]); v.v[2 * i] += q.x; v.v[2 * i + 1] += q.y; }
+                if (relu) { v.v[2 * i] = fmaxf(v.v[2 * i], 0.f); v.v[2 * i + 1] = fmaxf(v.v[2 * i + 1], 0.f); }
+            }
+            store8(y + (size_t)r * C + cg * 8, v);
         }
-        store8(y + off, v);
     }
 }
 cudaError_t launch_bn_apply(const __nv_bfloat16* x, const __nv_bfloat16* res, __nv_bfloat16* y, const float* gamma, const float* beta,
@@ -221,17 +240,28 @@ cudaError_t launch_bn_apply(const __nv_bfloat16* x, const __nv_bfloat16* res, __
     if (!chan_ok(C)) return cudaErrorInvalidValue;
     const int rpi = 256 / (C / 8);
     BnFinalize fin{fin_mode, stats, slots, count, eps, momentum, running_mean, running_var};
-    return launch_kernel(bn_apply_kernel, dim3(rows_grid(M, rpi * 4, num_sms, 8)), dim3(256), (size_t)0, st, x, res, y, gamma, beta, mean_rstd, M, C,
+    // rows per thread in flight: 1 (default) | 4 (RLR_BN_UNROLL=4).  Four rows look better in isolation but cost +0.7 % per round on
+    // B200 inside the step (profiles/r2_step_ab.md) -- the same verdict as in round 1, now from a same-box A/B
+    static const int unroll = [] { const char* e = getenv("RLR_BN_UNROLL"); return e ? atoi(e) : 1; }();
+    // RLR_BN_OCC=1: register caps that let one more CTA per SM be resident (more loads in flight through occupancy instead of unrolling)
+    static const int occ = [] { const char* e = getenv("RLR_BN_OCC"); return e ? atoi(e) : 0; }();
+    if (unroll <= 1 && occ)
+        return launch_kernel(bn_apply_kernel<1, 6>, dim3(rows_grid(M, rpi * 4, num_sms, 12)), dim3(256), (size_t)0, st, x, res, y, gamma, beta, mean_rstd,
+                             M, C, relu, fin);
+    if (unroll <= 1)
+        return launch_kernel(bn_apply_kernel<1, 1>, dim3(rows_grid(M, rpi * 4, num_sms, 8)), dim3(256), (size_t)0, st, x, res, y, gamma, beta, mean_rstd, M,
+                             C, relu, fin);
+    return launch_kernel(bn_apply_kernel<4, 1>, dim3(rows_grid(M, rpi * 4, num_sms, 6)), dim3(256), (size_t)0, st, x, res, y, gamma, beta, mean_rstd, M, C,
                          relu, fin);
 }
 
-template <bool kRecompute>
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
+template <bool kRecompute, int U, int kMinBlocks = 1>
+__global__ void __launch_bounds__(256, kMinBlocks) bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
                                                              const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
                                                              const float* __restrict__ mean_rstd, const float* __restrict__ dsum,
                                                              __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dres,
                                                              float* dgamma, float* dbeta, long long M, int C, int relu,
-                                                             const float* __restrict__ beta = nullptr) {
+                                                             const float* __restrict__ beta = nullptr, int nslots = 1) {
     pdl_wait();
     pdl_trigger();
     const int tpr = C / 8, rpi = 256 / tpr;
@@ -242,43 +272,77 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* 
     for (int i = 0; i < 8; ++i) {
         const int c = cg * 8 + i;
         mu[i] = mean_rstd[c]; rs[i] = mean_rstd[C + c]; g[i] = gamma[c] * rs[i];
-        k1[i] = dsum[c] * invM; k2[i] = dsum[C + c] * invM;
+        float s0 = 0.f, s1 = 0.f;
+        for (int k = 0; k < nslots; ++k) { s0 += dsum[(size_t)k * 2 * C + c]; s1 += dsum[(size_t)k * 2 * C + C + c]; }
+        k1[i] = s0 * invM; k2[i] = s1 * invM;
         msh[i] = kRecompute ? beta[c] - mu[i] * g[i] : 0.f;     // g = gamma * rstd is bn_apply's scale, msh its shift
     }
     if (blockIdx.x == 0 && ry == 0) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { dbeta[cg * 8 + i] = dsum[cg * 8 + i]; dgamma[cg * 8 + i] = dsum[C + cg * 8 + i]; }
+        for (int i = 0; i < 8; ++i) { dbeta[cg * 8 + i] = k1[i] * (float)M; dgamma[cg * 8 + i] = k2[i] * (float)M; }
     }
-    for (long long r = (long long)blockIdx.x * rpi + ry; r < M; r += (long long)gridDim.x * rpi) {
-        const size_t off = (size_t)r * C + cg * 8;
-        bf8 dz = load8(dy + off);
-        const bf8 xv = load8(x + off);
-        if (!kRecompute && relu) {
-            const bf8 yv = load8(y + off);
+    // U rows per thread in flight (see bn_apply_kernel)
+    const long long stride = (long long)gridDim.x * rpi;
+    for (long long r0 = (long long)blockIdx.x * rpi + ry; r0 < M; r0 += stride * U) {
+        bf8 dzv[U], xvv[U], yvv[U];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) dz.v[i] = yv.v[i] > 0.f ? dz.v[i] : 0.f;
-        } else if (kRecompute) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) dz.v[i] = (xv.v[i] * g[i] + msh[i]) > 0.f ? dz.v[i] : 0.f;
+        for (int u = 0; u < U; ++u) {
+            const long long r = r0 + u * stride;
+            const size_t off = (size_t)(r < M ? r : r0) * C + cg * 8;
+            dzv[u] = load8(dy + off);
+            xvv[u] = load8(x + off);
+            if (!kRecompute && relu) yvv[u] = load8(y + off);
         }
-        if (dres) store8(dres + off, dz);
-        bf8 o;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o.v[i] = g[i] * (dz.v[i] - k1[i] - (xv.v[i] - mu[i]) * rs[i] * k2[i]);
-        store8(dx + off, o);
+        for (int u = 0; u < U; ++u) {
+            const long long r = r0 + u * stride;
+            if (r >= M) continue;
+            const size_t off = (size_t)r * C + cg * 8;
+            bf8 dz = dzv[u];
+            const bf8 xv = xvv[u];
+            if (!kRecompute && relu) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) dz.v[i] = yvv[u].v[i] > 0.f ? dz.v[i] : 0.f;
+            } else if (kRecompute) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) dz.v[i] = (xv.v[i] * g[i] + msh[i]) > 0.f ? dz.v[i] : 0.f;
+            }
+            if (dres) store8(dres + off, dz);
+            bf8 o;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o.v[i] = g[i] * (dz.v[i] - k1[i] - (xv.v[i] - mu[i]) * rs[i] * k2[i]);
+            store8(dx + off, o);
+        }
     }
 }
 cudaError_t launch_bn_bwd_apply(const __nv_bfloat16* dy, const __nv_bfloat16* y, const __nv_bfloat16* x, const float* gamma,
                                 const float* mean_rstd, const float* dsum, __nv_bfloat16* dx, __nv_bfloat16* dres, float* dgamma,
-                                float* dbeta, long long M, int C, int relu, int num_sms, cudaStream_t st, const float* beta) {
-    if (!chan_ok(C) || (relu == 2 && !beta) || (relu == 1 && !y)) return cudaErrorInvalidValue;
+                                float* dbeta, long long M, int C, int relu, int num_sms, cudaStream_t st, const float* beta, int nslots) {
+    if (!chan_ok(C) || (relu == 2 && !beta) || (relu == 1 && !y) || nslots < 1) return cudaErrorInvalidValue;
     const int rpi = 256 / (C / 8);
     const int grid = rows_grid(M, rpi * 4, num_sms, 8);
+    static const int unroll = [] { const char* e = getenv("RLR_BN_UNROLL"); return e ? atoi(e) : 1; }();     // see launch_bn_apply
+    if (unroll > 1) {
+        if (relu == 2)
+            return launch_kernel(bn_bwd_apply_kernel<true, 2>, dim3(grid), dim3(256), (size_t)0, st, dy, y, x, gamma, mean_rstd, dsum, dx, dres, dgamma,
+                                 dbeta, M, C, relu, beta, nslots);
+        return launch_kernel(bn_bwd_apply_kernel<false, 2>, dim3(grid), dim3(256), (size_t)0, st, dy, y, x, gamma, mean_rstd, dsum, dx, dres, dgamma, dbeta,
+                             M, C, relu, nullptr, nslots);
+    }
+    static const int occ = [] { const char* e = getenv("RLR_BN_OCC"); return e ? atoi(e) : 0; }();       // see launch_bn_apply
+    if (occ) {
+        const int grid2 = rows_grid(M, rpi * 4, num_sms, 12);
+        if (relu == 2)
+            return launch_kernel(bn_bwd_apply_kernel<true, 1, 4>, dim3(grid2), dim3(256), (size_t)0, st, dy, y, x, gamma, mean_rstd, dsum, dx, dres, dgamma,
+                                 dbeta, M, C, relu, beta, nslots);
+        return launch_kernel(bn_bwd_apply_kernel<false, 1, 4>, dim3(grid2), dim3(256), (size_t)0, st, dy, y, x, gamma, mean_rstd, dsum, dx, dres, dgamma,
+                             dbeta, M, C, relu, nullptr, nslots);
+    }
     if (relu == 2)
-        return launch_kernel(bn_bwd_apply_kernel<true>, dim3(grid), dim3(256), (size_t)0, st, dy, y, x, gamma, mean_rstd, dsum, dx, dres, dgamma, dbeta, M,
-                             C, relu, beta);
-    return launch_kernel(bn_bwd_apply_kernel<false>, dim3(grid), dim3(256), (size_t)0, st, dy, y, x, gamma, mean_rstd, dsum, dx, dres, dgamma, dbeta, M, C,
-                         relu, nullptr);
+        return launch_kernel(bn_bwd_apply_kernel<true, 1>, dim3(grid), dim3(256), (size_t)0, st, dy, y, x, gamma, mean_rstd, dsum, dx, dres, dgamma, dbeta, M,
+                             C, relu, beta, nslots);
+    return launch_kernel(bn_bwd_apply_kernel<false, 1>, dim3(grid), dim3(256), (size_t)0, st, dy, y, x, gamma, mean_rstd, dsum, dx, dres, dgamma, dbeta, M, C,
+                         relu, nullptr, nslots);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

@@ -56,13 +56,15 @@ def timed(fn, reps):
 
 def set_variant(v):
     e = ops.ext()
-    e.set_conv_2cta(0); e.set_conv_occ3(1); e.set_persistent_conv(0); e.set_conv_split_producer(False)
+    e.set_conv_2cta(0); e.set_conv_occ3(1); e.set_persistent_conv(0); e.set_conv_split_producer(False); e.set_conv_tma_store(True)
     nn.USE_HALO3 = False; nn.USE_STRIDED_TMA = False; nn.USE_WGRAD_HALO = True; nn.USE_BN_RECOMPUTE = False
     for tok in v.split("+"):
         if tok == "default":
             pass
         elif tok == "pair":
             e.set_conv_2cta(1)
+        elif tok == "notmastore":
+            e.set_conv_tma_store(False)
         elif tok == "split":
             e.set_conv_split_producer(True)
         elif tok == "pairdeep":

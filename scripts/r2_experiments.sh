@@ -25,7 +25,7 @@ good=""
 #   name          pytest -k expression          flag
 while read -r name expr flag; do
     [ -z "$name" ] && continue
-    RLR_EXPERIMENTAL=1 timeout 150 python -m pytest tests/test_gpu_experimental.py -m gpu -q -s -k "$expr" > gpurun_out/r2_exp_$name.txt 2>&1
+    timeout 150 python -m pytest tests/test_gpu_variants.py -m gpu -q -s -k "$expr" > gpurun_out/r2_exp_$name.txt 2>&1
     rc=$?
     echo "test $name: exit $rc ($(tail -1 gpurun_out/r2_exp_$name.txt))" | tee -a gpurun_out/r2_summary.txt
     if [ $rc -eq 0 ]; then
@@ -45,12 +45,12 @@ pair         cta_pair                     RLR_CONV_2CTA=1
 LIST
 [ -n "$good" ] && bench combined $good      # every experiment whose test passed, together
 # concurrency of several agents per GPU (the reference's README workload: FMNIST CNN, 10 agents on one GPU)
-RLR_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_gpu_experimental.py -m gpu -q -s -k agents_in_flight > gpurun_out/r2_exp_inflight.txt 2>&1
+timeout 200 python -m pytest tests/test_gpu_variants.py -m gpu -q -s -k agents_in_flight > gpurun_out/r2_exp_inflight.txt 2>&1
 echo "test inflight: exit $? ($(tail -1 gpurun_out/r2_exp_inflight.txt))" | tee -a gpurun_out/r2_summary.txt
-RLR_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_gpu_experimental.py -m gpu -q -s -k deeper_family > gpurun_out/r2_exp_family.txt 2>&1
+timeout 200 python -m pytest tests/test_gpu_variants.py -m gpu -q -s -k deeper_family > gpurun_out/r2_exp_family.txt 2>&1
 echo "test resnet34/vgg16 on native kernels: exit $? ($(grep "logit rel" gpurun_out/r2_exp_family.txt | tr '\n' ';') $(tail -1 gpurun_out/r2_exp_family.txt))" | tee -a gpurun_out/r2_summary.txt
 for v in 0 1; do
-    RLR_GEMM_SMALL_BN64=$v RLR_EXPERIMENTAL=1 timeout 120 python -m pytest tests/test_gpu_experimental.py -m gpu -q -s -k small_batch_gemm 2>&1 \
+    RLR_GEMM_SMALL_BN64=$v timeout 120 python -m pytest tests/test_gpu_variants.py -m gpu -q -s -k small_batch_gemm 2>&1 \
         | grep "gemm \|passed\|failed" | sed "s/^/RLR_GEMM_SMALL_BN64=$v  /" | tee -a gpurun_out/r2_summary.txt
 done
 readme="--model cnn_mnist --data fmnist --train_size 60000 --agents 10 --steps 3 --warmup 3 --no_e2e"

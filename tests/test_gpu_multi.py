@@ -109,43 +109,47 @@ def test_engine_fused_equals_nccl_baseline(tmp_path):
     assert abs(f[0]["acc"] - n[0]["acc"]) < 0.2 and f[0]["backend"] == "fused" and n[0]["backend"] == "nccl"
 
 
-def _handoff_worker(rank, world, port, outdir, fused):
+def _handoff_worker(rank, world, port, outdir, fused, tag):
     sys.path.insert(0, ROOT)
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     import torch.distributed as dist
     from rlr_b200.engine import FLEngine
     from rlr_b200.options import make_args
-    args = make_args(data="cifar10", model="cnn_cifar", synthetic=2048, synthetic_val=256, num_agents=2 * world, local_ep=1, bs=64, log_dir="",
-                     robustLR_threshold=2, num_corrupt=1, poison_frac=0.5, seed=7, no_fused_handoff=not fused)
-    for nd in []:
-        pass
+    # FedAvg without the (discontinuous) sign vote, ONE local step per agent and round: every step is a first step of the hand-off path
+    args = make_args(data="cifar10", model="cnn_cifar", synthetic=64 * 2 * world, synthetic_val=128, num_agents=2 * world, local_ep=1, bs=64,
+                     log_dir="", seed=7, no_fused_handoff=not fused)
     eng = FLEngine(args, verbose=False)
     assert eng.handoff == fused and eng.fused.backend == "fused"
-    for r in range(1, 5):
+    snaps = []
+    for r in range(1, 4):
         eng.run_round(r)
-    w = eng.global_params().clone()
+        snaps.append(eng.global_params().clone())
     torch.cuda.synchronize()
-    allw = eng.ctx.all_gather(w)
-    torch.save({"w": w.cpu(), "same": bool((allw == allw[0:1]).all().item()), "loss": eng.round_result()[0]},
-               os.path.join(outdir, f"handoff_{int(fused)}_{rank}.pt"))
+    allw = eng.ctx.all_gather(snaps[-1])
+    torch.save({"w": [s_.cpu() for s_ in snaps], "same": bool((allw == allw[0:1]).all().item())}, os.path.join(outdir, f"handoff_{tag}_{rank}.pt"))
     eng.close()
     dist.barrier(); dist.destroy_process_group()
 
 
 def test_fused_handoff_across_gpus_equals_barrier_path(tmp_path):
     """Broadcast (+) first-GEMM fusion on >= 2 GPUs: the aggregation kernel publishes per-slice ready words instead of running its
-    barrier-out, the next round's stem GEMM reads the multicast shadow behind them.  Same global parameters as the barrier path on
-    every rank (up to the atomics order of the split-K weight gradients), identical across ranks bit for bit."""
+    barrier-out, and the next round's stem GEMM reads the multicast bf16 shadow behind them.  Global parameters must be bit-identical
+    across ranks, and equal to the barrier path up to the run-to-run noise of that path itself (split-K atomics order; dropout masks
+    are a pure function of (seed, agent, round, step) in both)."""
     world = min(torch.cuda.device_count(), 8)
     if world < 2:
         pytest.skip("needs >= 2 GPUs")
-    for fused in (False, True):
-        mp.spawn(_handoff_worker, args=(world, _free_port(), str(tmp_path), fused), nprocs=world, join=True)
-    a = [torch.load(tmp_path / f"handoff_1_{r}.pt") for r in range(world)]
-    b = [torch.load(tmp_path / f"handoff_0_{r}.pt") for r in range(world)]
-    for r in range(world):
-        assert a[r]["same"] and b[r]["same"], "all ranks hold identical global parameters"
-    torch.testing.assert_close(a[0]["w"], b[0]["w"], rtol=5e-3, atol=5e-4)
+    for fused, tag in ((False, "a"), (False, "b"), (True, "f")):
+        mp.spawn(_handoff_worker, args=(world, _free_port(), str(tmp_path), fused, tag), nprocs=world, join=True)
+    res = {t: [torch.load(tmp_path / f"handoff_{t}_{r}.pt") for r in range(world)] for t in "abf"}
+    for t in "abf":
+        for r in range(world):
+            assert res[t][r]["same"], "all ranks hold identical global parameters"
+    rel = lambda x, y: float((x.double() - y.double()).norm() / (y.double().norm() + 1e-12))
+    for i in (0, 2):
+        noise, diff = rel(res["b"][0]["w"][i], res["a"][0]["w"][i]), rel(res["f"][0]["w"][i], res["a"][0]["w"][i])
+        print(f"round {i + 1}: barrier-vs-barrier {noise:.2e}  fused-vs-barrier {diff:.2e}")
+        assert diff <= 3 * noise + (1e-5 if i == 0 else 1e-4), (i, diff, noise)
 
 
 def _stress_worker(rank, world, port, outdir, handoff, iters):

@@ -1,6 +1,6 @@
 """CPU check of the HOST-SIDE orchestration in ops/nn.py (tap tables, parity planes, padding, scratch reuse, opt-in code paths)
 against PyTorch convolutions, with the CUDA extension replaced by a small fp32 emulator of each kernel's documented contract
-(ops/csrc/gemm_binding.cpp).  The kernels themselves are tested on the GPU (tests/test_gpu_native.py, test_gpu_experimental.py);
+(ops/csrc/gemm_binding.cpp).  The kernels themselves are tested on the GPU (tests/test_gpu_native.py, test_gpu_variants.py);
 this suite makes sure that what Python hands them is right -- in particular for paths that could not be run on hardware yet."""
 import pytest
 import torch
@@ -170,9 +170,10 @@ class FakeExt:
         xhat = (xf - mean_rstd[0]) * mean_rstd[1]
         if zero_dsum:
             dsum.zero_()
-        d2 = dsum.view(2, C)
-        d2[0] += dzf.sum(0)
-        d2[1] += (dzf * xhat).sum(0)
+        d3 = dsum.view(-1, 2, C)                      # [slots][2][C]: the kernels spread their atomics over the slots, consumers sum them
+        d3[0, 0] += dzf.sum(0)
+        d3[0, 1] += (dzf * xhat).sum(0)
+        d2 = d3.sum(0)
         if dres is not None:
             dres.copy_(dzf.reshape(dres.shape))
         dx.copy_((gamma * mean_rstd[1] * (dzf - d2[0] / M - xhat * d2[1] / M)).reshape(dx.shape))
@@ -192,8 +193,9 @@ class FakeExt:
     def channel_stats(self, x, st):
         self.calls.append("channel_stats")
         xf = x.reshape(-1, x.shape[-1])
-        st[0] += xf.sum(0)
-        st[1] += (xf * xf).sum(0)
+        s3 = st.view(-1, 2, x.shape[-1])              # [slots][2][C]
+        s3[0, 0] += xf.sum(0)
+        s3[0, 1] += (xf * xf).sum(0)
 
     def bias_grad(self, dy, db):
         self.calls.append("bias_grad")
