@@ -36,6 +36,10 @@ ACT = torch.bfloat16   # default activation / GEMM-operand dtype on GPU (tests m
 # partial-sum slots of the per-channel reductions: with N > 1 the CTAs of channel_reduce_kernel spread their atomics over N buffers
 # (consumers sum them) and the reductions run four / three CTAs per SM instead of two.  Measured on B200 (profiles/r2_step_ab.md):
 # 4 slots = +3.3 % round time, i.e. the two-CTA grid of round 1 stays the default; the knob is kept for re-measurement.
+# Dropout after a max-pool or a Linear+ReLU is fused into that producer: the pooling kernel / the GEMM epilogue applies the
+# Philox keep-mask, the backward recomputes it (pool) or reads it off the output together with the ReLU mask (linear).  RLR_FUSE_DROPOUT=0
+# restores the stand-alone dropout kernels.
+FUSE_DROPOUT = bool(int(os.environ.get("RLR_FUSE_DROPOUT", "1")))
 FWD_SLOTS = BWD_SLOTS = max(1, int(os.environ.get("RLR_BN_SLOTS", "1")))
 WGRAD_OVERLAP = bool(int(os.environ.get("RLR_WGRAD_OVERLAP", "1")))
 
@@ -185,9 +189,21 @@ class NativeNet:
                 self.tshape[tid(nd.out)] = shape[nd.out]
             elif nd.op == "dropout":
                 shp = shape[nd.inp]
-                op = _Op("dropout", node=i, attrs=a, x=src, in_shape=shp, out_shape=shp)
-                op.y = new_out(nd.out, shp)
-                plan.append(op)
+                prod = next((q for q in reversed(plan) if q.y == src), None)
+                fusable = (prod is not None and a.get("p", 0.0) > 0 and "drop" not in prod.saved and
+                           (prod.kind == "maxpool" or
+                            (prod.kind == "linear" and prod.relu and ops.linear_fused_dropout_ok(prod.attrs["cout"], prod.attrs["cin"]))))
+                if fusable and FUSE_DROPOUT:
+                    # dropout fused into the producer (pooling kernel / GEMM epilogue): no op, no mask tensor, the output IS the dropped tensor
+                    prod.saved["drop"] = (float(a["p"]), i)
+                    ver[nd.out] += 1
+                    alias[tid(nd.out)] = src
+                    shape[nd.out] = shp
+                    self.tshape[tid(nd.out)] = shp
+                else:
+                    op = _Op("dropout", node=i, attrs=a, x=src, in_shape=shp, out_shape=shp)
+                    op.y = new_out(nd.out, shp)
+                    plan.append(op)
             elif nd.op == "linear":
                 op = _Op("linear", node=i, name=nd.name, attrs=a, x=src, in_shape=shape[nd.inp], out_shape=(a["cout"],))
                 j, nx = next_same_slot(i, nd.out)
@@ -243,6 +259,8 @@ class NativeNet:
         for op in self.plan:
             if op.kind == "maxpool":
                 op.saved["idx"] = torch.empty((B, *op.out_shape), dtype=torch.uint8, device=dev)
+                if "drop" in op.saved and self.impl["pool"] != "sm100":
+                    op.saved["dmask"] = torch.ones((B, *op.out_shape), dtype=torch.uint8, device=dev)   # aten back-end only
             if op.kind == "dropout":
                 op.saved["mask"] = torch.empty((B, *op.out_shape), dtype=torch.uint8, device=dev)
         self._bn_src = {}
@@ -416,11 +434,21 @@ class NativeNet:
                    beta=self.pw[op.name + ".bias"])
 
     # ---- pooling ---------------------------------------------------------------------------------------------------
+    def _drop(self, op, train=True):
+        """(p, seed, step counter, node id) of the dropout fused into ``op`` (None in evaluation mode / when nothing is fused)."""
+        d = op.saved.get("drop")
+        return (d[0], self.seed, self.step_counter, d[1]) if (d is not None and train) else None
+
     def _fwd_maxpool(self, op, B, train):
-        ops.maxpool2_fwd(self.T(op.x, B), self.T(op.y, B), op.saved["idx"][:B], self.impl["pool"])
+        drop = self._drop(op, train)
+        op.saved["drop_on"] = drop is not None
+        mask = op.saved["dmask"][:B] if (drop is not None and "dmask" in op.saved) else None
+        ops.maxpool2_fwd(self.T(op.x, B), self.T(op.y, B), op.saved["idx"][:B], self.impl["pool"], drop, mask)
 
     def _bwd_maxpool(self, op, B):
-        ops.maxpool2_bwd(self.G(op.y, B), op.saved["idx"][:B], self.G(op.x, B), self.impl["pool"])
+        drop = self._drop(op, op.saved.get("drop_on", False))
+        mask = op.saved["dmask"][:B] if (drop is not None and "dmask" in op.saved) else None
+        ops.maxpool2_bwd(self.G(op.y, B), op.saved["idx"][:B], self.G(op.x, B), self.impl["pool"], drop, mask)
 
     def _fwd_avgpool(self, op, B, train):
         ops.avgpool_fwd(self.T(op.x, B), self.T(op.y, B), self.impl["pool"])
@@ -444,12 +472,16 @@ class NativeNet:
     # ---- linear -----------------------------------------------------------------------------------------------------
     def _fwd_linear(self, op, B, train):
         x, y = self.T(op.x, B).reshape(B, -1), self.T(op.y, B)
-        ops.linear_fwd(x, self.pwb[op.name + ".weight"], self.pw.get(op.name + ".bias"), y, op.relu, self.impl["linear"])
+        drop = self._drop(op, train)
+        op.saved["drop_on"] = drop is not None
+        ops.linear_fwd(x, self.pwb[op.name + ".weight"], self.pw.get(op.name + ".bias"), y, op.relu, self.impl["linear"], drop)
 
     def _bwd_linear(self, op, B):
         x, y, dy = self.T(op.x, B).reshape(B, -1), self.T(op.y, B), self.G(op.y, B)
         if op.relu:
-            ops.relu_bwd_(dy, y, self.impl["bn"])
+            # fused dropout: y = relu(z) * keep / (1-p) -> (y > 0) is the ReLU mask AND the keep mask; the gradient carries 1/(1-p)
+            scale = 1.0 / (1.0 - op.saved["drop"][0]) if op.saved.get("drop_on", False) else 1.0
+            ops.relu_bwd_(dy, y, self.impl["bn"], scale)
         dx = self.G(op.x, B).reshape(B, -1) if op.need_dx else None
         ops.linear_bwd(x, dy, self.pwb[op.name + ".weight"], dx, self.pg[op.name + ".weight"], self.pg.get(op.name + ".bias"),
                        op.acc_dx, self.impl["linear"], zero=False)

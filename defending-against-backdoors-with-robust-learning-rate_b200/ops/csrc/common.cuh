@@ -4,6 +4,8 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 
+#include "dropspec.h"
+
 #define RLR_CUDA_CHECK(expr)                                                                     \
     do {                                                                                         \
         cudaError_t _e = (expr);                                                                 \
@@ -177,6 +179,22 @@ __device__ __forceinline__ float4 philox_normal4(const Philox& ph, uint64_t ctr,
     sincospif(2.0f * u32_to_unit(u.y), &s0, &c0);
     sincospif(2.0f * u32_to_unit(u.w), &s1, &c1);
     return make_float4(r0 * c0, r0 * s0, r1 * c1, r1 * s1);
+}
+
+// ---- fused dropout --------------------------------------------------------------------------------------------------------------
+// Keep-mask of a tensor viewed as a flat array of elements: the 8 elements [8 q, 8 q + 8) share ONE Philox4x32-10 call keyed by
+// (seed; counter q, stream = (step << 20) ^ node), 16 random bits per element, keep iff bits >= p * 65536.  Every kernel that produces
+// or back-propagates through a dropped tensor (maxpool / GEMM epilogues, their backward kernels, the stand-alone dropout kernels)
+// evaluates THIS function, so no mask tensor is ever written.  Reference: nn.Dropout2d(p=.5) on 2-D activations (src/models.py:17-19,
+// 40-44) = element-wise dropout; bit-parity with torch's Philox stream is not a goal, mask statistics are tested.
+__device__ __forceinline__ uint32_t dropout_keep8(const DropSpec& d, long long q) {     // bit i = element 8 q + i is kept
+    const Philox ph(d.seed);
+    const uint4 u = ph((uint64_t)q, ((uint64_t)(*d.step) << 20) ^ d.stream);
+    const uint32_t r[4] = {u.x, u.y, u.z, u.w};
+    uint32_t keep = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) keep |= (uint32_t)(((r[i >> 1] >> (16 * (i & 1))) & 0xffffu) >= d.thr) << i;
+    return keep;
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

@@ -221,7 +221,8 @@ umma_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         uint8_t* staging = smem;                         // operand ring is idle now: reuse it
         const int col0 = tile_n * BN;
         float* red = reinterpret_cast<float*>(staging + Cfg::kStagingBytes);   // [2][BN] per-tile column sums
-        const bool row_ok = tail->row_index[row] >= 0;
+        const int gi_row = tail->row_index[row];
+        const bool row_ok = gi_row >= 0;
         if (kStats) {
             for (int i = et; i < 2 * BN; i += kEpiThreads) red[i] = 0.f;
             asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -241,12 +242,18 @@ umma_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 const int cc = c0 + h * 32;
                 uint32_t (&v)[32] = vv[h];
                 uint32_t packed[16];
+                uint32_t keep8 = 0xffu;
                 float f1[32], f2[32];
 #pragma unroll
                 for (int j = 0; j < 32; j += 2) {
                     float a = __uint_as_float(v[j]), b = __uint_as_float(v[j + 1]);
                     if (p.bias && col0 + cc + j < p.N) { a += p.bias[col0 + cc + j]; b += p.bias[col0 + cc + j + 1]; }
                     if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+                    if (p.drop.thr) {   // fused dropout (linear layers): one Philox call per 8 output columns of this row
+                        if ((j & 7) == 0) keep8 = dropout_keep8(p.drop, ((long long)(gi_row < 0 ? 0 : gi_row) * p.ldc + col0 + cc + j) >> 3);
+                        a = (keep8 >> (j & 7) & 1) ? a * p.drop.scale : 0.f;
+                        b = (keep8 >> ((j & 7) + 1) & 1) ? b * p.drop.scale : 0.f;
+                    }
                     packed[j >> 1] = pack_bf16x2(a, b);
                     if (kStats) {   // statistics of the bf16-rounded values BatchNorm will read back; masked rows count as zero
                         const float2 rq = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&packed[j >> 1]));
@@ -525,8 +532,9 @@ static int pick_bn(int N) { return (N % 128 == 0) ? 128 : 64; }
 
 // Plain GEMM: out[M][ldc] (bf16) = A[M][K] * B[N][K]^T (+bias)(relu).  K % 64 == 0, N % 64 == 0.
 cudaError_t launch_gemm_bf16(const void* A, const void* B, void* out, int M, int N, int K, int lda, int ldb, int ldc,
-                             const float* bias, int relu, int accumulate, float* stats, cudaStream_t st) {
+                             const float* bias, int relu, int accumulate, float* stats, cudaStream_t st, const DropSpec* drop) {
     if (K % BK || N % 8 || M <= 0) return cudaErrorInvalidValue;
+    if (drop && drop->thr && (accumulate || stats || ldc % 8)) return cudaErrorInvalidValue;
     const int m_tiles = (M + BM - 1) / BM;
     const int bn2 = pair_bn(m_tiles, N, stats == nullptr);
     int bn = bn2 ? bn2 : pick_bn(N);
@@ -548,6 +556,10 @@ cudaError_t launch_gemm_bf16(const void* A, const void* B, void* out, int M, int
     ConvGemmParams p{};
     p.M = M; p.N = N; p.num_kb = K / BK; p.mode = 0; p.in_stride = 1; p.out_stride = 1;
     p.out = out; p.ldc = ldc; p.bias = bias; p.stats = stats; p.relu = relu; p.accumulate = accumulate;
+    if (drop && drop->thr) {      // fused dropout lives in the single-CTA kernel's epilogue
+        p.drop = *drop;
+        return bn == 128 ? launch_bn<128>(tmA, tmB, p, m_tiles, st) : launch_bn<64>(tmA, tmB, p, m_tiles, st);
+    }
     if (bn2) return launch_pair(bn2, tmA, tmB, p, m_tiles, st);
     return bn == 128 ? launch_bn<128>(tmA, tmB, p, m_tiles, st) : launch_bn<64>(tmA, tmB, p, m_tiles, st);
 }

@@ -5,6 +5,8 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 
+#include "dropspec.h"
+
 namespace rlr {
 
 // conv epilogues reduce per-channel statistics into one of kStatSlots partial buffers ([slots][2][C]) chosen by CTA index, so
@@ -31,6 +33,7 @@ struct ConvGemmParams {
     // With wait_flags the producer first acquires the broadcast-ready words [wait_lo, wait_hi] (>= *wait_epoch): b_src then points into
     // the NVLS-multicast parameter shadow that the aggregation kernels of ALL GPUs are still filling -- the first local-forward GEMM of
     // a round starts as soon as the slice holding its filter has landed (broadcast (+) first-GEMM fusion, parallel/fused_agg.py).
+    DropSpec drop;             // thr != 0: dropout fused into the epilogue (after bias / ReLU): keep-mask of output element (row * ldc + col), common.cuh
     int tma_store;             // 1: epilogue writes the tile with TMA tensor stores from a swizzled staging tile (tmC valid; no accumulate / stats)
     int split_prod;            // 1: two TMA producer threads per CTA (warp 0 loads A, warp 2 loads B): two request streams into the TMA unit
     long long* dbg;            // optional [CTAs][8] timeline (globaltimer ns): entry, setup done, first TMA issued, first data landed,
@@ -48,7 +51,7 @@ struct ConvGemmParams {
 };
 
 cudaError_t launch_gemm_bf16(const void* A, const void* B, void* out, int M, int N, int K, int lda, int ldb, int ldc,
-                             const float* bias, int relu, int accumulate, float* stats, cudaStream_t st);
+                             const float* bias, int relu, int accumulate, float* stats, cudaStream_t st, const DropSpec* drop = nullptr);
 // stem GEMM: out[M][N] = A[M][64] * pad64(W[N][kvalid])^T (+bias)(relu); W is read un-padded by the producer warp (optionally after
 // acquiring broadcast-ready flags [wait_lo, wait_hi] >= *wait_epoch -- see ConvGemmParams::b_src)
 cudaError_t launch_stem_gemm_bf16(const void* A, const void* W, void* out, int M, int N, int kvalid, int ldw, const float* bias, int relu,
@@ -59,7 +62,7 @@ void set_pdl(int on);
 // gemm_splitk.cu (opt-in): small-M / deep-K GEMM, grid.z CTAs share a tile's k range and add fp32 partials into `ws` ([M][N], zero on
 // entry and left zero), then one finishing pass applies bias / ReLU and packs bf16
 cudaError_t launch_gemm_splitk_bf16(const void* A, const void* B, void* out, float* ws, int M, int N, int K, const float* bias, int relu,
-                                    int num_sms, cudaStream_t st);
+                                    int num_sms, cudaStream_t st, const DropSpec* drop = nullptr);
 // opt-in CTA-pair kernel (gemm_2cta.cu: tcgen05.mma.cta_group::2, M = 256, half a B tile per CTA); default: RLR_CONV_2CTA env, off
 void set_conv_2cta(int on);
 // opt-in persistent tile scheduler for the generic conv / GEMM kernel (gemm_persistent.cu); default: RLR_PERSISTENT_CONV env
@@ -114,9 +117,13 @@ cudaError_t launch_bn_bwd_reduce(const __nv_bfloat16* dy, const __nv_bfloat16* y
 cudaError_t launch_bn_bwd_apply(const __nv_bfloat16* dy, const __nv_bfloat16* y, const __nv_bfloat16* x, const float* gamma,
                                 const float* mean_rstd, const float* dsum, __nv_bfloat16* dx, __nv_bfloat16* dres, float* dgamma,
                                 float* dbeta, long long M, int C, int relu, int num_sms, cudaStream_t st, const float* beta = nullptr, int nslots = 1);
-cudaError_t launch_relu_bwd(__nv_bfloat16* dy, const __nv_bfloat16* y, long long n, int num_sms, cudaStream_t st);
-cudaError_t launch_maxpool2_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, uint8_t* idx, int B, int H, int W, int C, cudaStream_t st);
-cudaError_t launch_maxpool2_bwd(const __nv_bfloat16* dy, const uint8_t* idx, __nv_bfloat16* dx, int B, int H, int W, int C, cudaStream_t st);
+// scale != 1: the output went through fused dropout (mask = y > 0 covers ReLU and dropout together)
+cudaError_t launch_relu_bwd(__nv_bfloat16* dy, const __nv_bfloat16* y, long long n, int num_sms, cudaStream_t st, float scale = 1.0f);
+// drop_p > 0: dropout fused into the pooling kernel (Philox keep-mask of the pooled element, recomputed by the backward kernel; no mask tensor)
+cudaError_t launch_maxpool2_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, uint8_t* idx, int B, int H, int W, int C, cudaStream_t st,
+                                float drop_p = 0.f, uint64_t seed = 0, const long long* step = nullptr, uint64_t stream = 0);
+cudaError_t launch_maxpool2_bwd(const __nv_bfloat16* dy, const uint8_t* idx, __nv_bfloat16* dx, int B, int H, int W, int C, cudaStream_t st,
+                                float drop_p = 0.f, uint64_t seed = 0, const long long* step = nullptr, uint64_t stream = 0);
 cudaError_t launch_avgpool_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, int B, int HW, int C, cudaStream_t st);
 cudaError_t launch_avgpool_bwd(const __nv_bfloat16* dy, __nv_bfloat16* dx, int B, int HW, int C, cudaStream_t st);
 cudaError_t launch_dropout_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, uint8_t* mask, long long n, float p, uint64_t seed,

@@ -26,14 +26,26 @@ inline float* f32(const at::Tensor& t) {
 }
 
 // out[M][N] = A[M][K] @ B[N][K]^T (+bias)(relu)
+// fused-dropout arguments of the python API: p in (0, 1) (0 = off), Philox seed, device int64 step counter, node id
+static rlr::DropSpec drop_spec(double p, int64_t seed, const c10::optional<at::Tensor>& step, int64_t stream) {
+    rlr::DropSpec d{};
+    if (p > 0.0) {
+        TORCH_CHECK(p < 1.0 && step.has_value() && step->defined() && step->scalar_type() == at::kLong, "fused dropout needs p < 1 and an int64 step counter");
+        d.thr = (uint32_t)(p * 65536.0); d.scale = (float)(1.0 / (1.0 - p)); d.seed = (uint64_t)seed; d.stream = (uint64_t)stream;
+        d.step = reinterpret_cast<const long long*>(step->data_ptr<int64_t>());
+    }
+    return d;
+}
+
 void gemm_bf16(at::Tensor A, at::Tensor B, at::Tensor out, c10::optional<at::Tensor> bias, bool relu, bool accumulate,
-               c10::optional<at::Tensor> stats) {
+               c10::optional<at::Tensor> stats, double drop_p, int64_t drop_seed, c10::optional<at::Tensor> drop_step, int64_t drop_stream) {
     c10::cuda::CUDAGuard g(A.device());
+    const rlr::DropSpec drop = drop_spec(drop_p, drop_seed, drop_step, drop_stream);
     const int M = A.size(0), K = A.size(1), N = B.size(0);
     TORCH_CHECK(B.size(1) == K && out.size(0) == M && out.size(1) == N);
     TORCH_CHECK(!stats.has_value() || !stats->defined() || stats->numel() == (int64_t)rlr::kStatSlots * 2 * N, "stats must be [STAT_SLOTS,2,N]");
     check(rlr::launch_gemm_bf16(bf(A), bf(B), bfm(out), M, N, K, K, K, N, opt<const float>(bias), relu, accumulate, opt<float>(stats),
-                                cur_stream()), "gemm_bf16");
+                                cur_stream(), drop.thr ? &drop : nullptr), "gemm_bf16");
 }
 
 // stem convolution as one 64-deep GEMM: out[M][N] = A[M][64] @ pad64(W[N][kvalid])^T; W is the UN-padded filter, gathered by the kernel's
@@ -70,12 +82,14 @@ void conv_bf16(at::Tensor x, at::Tensor w, at::Tensor out, int64_t NB, int64_t p
 }
 
 // out[M][N] = act(A[M][K] @ B[N][K]^T + bias) with split-K partial sums in ws ([M][N] fp32, zero on entry, left zero)
-void gemm_splitk_bf16(at::Tensor A, at::Tensor B, at::Tensor out, at::Tensor ws, c10::optional<at::Tensor> bias, bool relu) {
+void gemm_splitk_bf16(at::Tensor A, at::Tensor B, at::Tensor out, at::Tensor ws, c10::optional<at::Tensor> bias, bool relu, double drop_p,
+                      int64_t drop_seed, c10::optional<at::Tensor> drop_step, int64_t drop_stream) {
     c10::cuda::CUDAGuard g(A.device());
+    const rlr::DropSpec drop = drop_spec(drop_p, drop_seed, drop_step, drop_stream);
     const int M = A.size(0), K = A.size(1), N = B.size(0);
     TORCH_CHECK(B.size(1) == K && out.size(0) == M && out.size(1) == N && ws.numel() == (int64_t)M * N);
-    check(rlr::launch_gemm_splitk_bf16(bf(A), bf(B), bfm(out), f32(ws), M, N, K, opt<const float>(bias), relu, num_sms(), cur_stream()),
-          "gemm_splitk_bf16");
+    check(rlr::launch_gemm_splitk_bf16(bf(A), bf(B), bfm(out), f32(ws), M, N, K, opt<const float>(bias), relu, num_sms(), cur_stream(),
+                                       drop.thr ? &drop : nullptr), "gemm_splitk_bf16");
 }
 
 // Strided variant without parity-split copies: x [NB,Hin,Win,Cin] is the ORIGINAL input, read through a TMA box with element
@@ -231,17 +245,21 @@ void bn_bwd_recompute(at::Tensor dy, at::Tensor x, at::Tensor gamma, at::Tensor 
                                    (float*)dgamma.data_ptr(), (float*)dbeta.data_ptr(), M, C, 2, num_sms(), cur_stream(),
                                    (const float*)beta.data_ptr(), nslots), "bn_bwd_apply(recompute)");
 }
-void relu_bwd(at::Tensor dy, at::Tensor y) {
+void relu_bwd(at::Tensor dy, at::Tensor y, double scale) {
     c10::cuda::CUDAGuard g(dy.device());
-    check(rlr::launch_relu_bwd(bfm(dy), bf(y), dy.numel(), num_sms(), cur_stream()), "relu_bwd");
+    check(rlr::launch_relu_bwd(bfm(dy), bf(y), dy.numel(), num_sms(), cur_stream(), (float)scale), "relu_bwd");
 }
-void maxpool2_fwd(at::Tensor x, at::Tensor y, at::Tensor idx) {
+void maxpool2_fwd(at::Tensor x, at::Tensor y, at::Tensor idx, double drop_p, int64_t drop_seed, c10::optional<at::Tensor> drop_step, int64_t drop_stream) {
     c10::cuda::CUDAGuard g(x.device());
-    check(rlr::launch_maxpool2_fwd(bf(x), bfm(y), (uint8_t*)idx.data_ptr(), x.size(0), x.size(1), x.size(2), x.size(3), cur_stream()), "maxpool2_fwd");
+    const rlr::DropSpec d = drop_spec(drop_p, drop_seed, drop_step, drop_stream);
+    check(rlr::launch_maxpool2_fwd(bf(x), bfm(y), (uint8_t*)idx.data_ptr(), x.size(0), x.size(1), x.size(2), x.size(3), cur_stream(),
+                                   (float)drop_p, d.seed, d.step, d.stream), "maxpool2_fwd");
 }
-void maxpool2_bwd(at::Tensor dy, at::Tensor idx, at::Tensor dx) {
+void maxpool2_bwd(at::Tensor dy, at::Tensor idx, at::Tensor dx, double drop_p, int64_t drop_seed, c10::optional<at::Tensor> drop_step, int64_t drop_stream) {
     c10::cuda::CUDAGuard g(dx.device());
-    check(rlr::launch_maxpool2_bwd(bf(dy), (const uint8_t*)idx.data_ptr(), bfm(dx), dx.size(0), dx.size(1), dx.size(2), dx.size(3), cur_stream()), "maxpool2_bwd");
+    const rlr::DropSpec d = drop_spec(drop_p, drop_seed, drop_step, drop_stream);
+    check(rlr::launch_maxpool2_bwd(bf(dy), (const uint8_t*)idx.data_ptr(), bfm(dx), dx.size(0), dx.size(1), dx.size(2), dx.size(3), cur_stream(),
+                                   (float)drop_p, d.seed, d.step, d.stream), "maxpool2_bwd");
 }
 void avgpool_fwd(at::Tensor x, at::Tensor y) {
     c10::cuda::CUDAGuard g(x.device());
@@ -321,10 +339,12 @@ void register_gemm_bindings(py::module_& m) {
     m.def("set_conv_trace", [](c10::optional<at::Tensor> buf) {   // int64 [CTAs * 8] timeline buffer for the next generic conv / GEMM launches
         rlr::set_conv_trace(buf.has_value() && buf->defined() ? reinterpret_cast<long long*>(buf->data_ptr<int64_t>()) : nullptr);
     });
-    m.def("gemm_bf16", &gemm_bf16);
+    m.def("gemm_bf16", &gemm_bf16, py::arg("A"), py::arg("B"), py::arg("out"), py::arg("bias"), py::arg("relu"), py::arg("accumulate"), py::arg("stats"),
+          py::arg("drop_p") = 0.0, py::arg("drop_seed") = 0, py::arg("drop_step") = py::none(), py::arg("drop_stream") = 0);
     m.def("stem_gemm_bf16", &stem_gemm_bf16, py::arg("A"), py::arg("W"), py::arg("out"), py::arg("bias"), py::arg("relu"), py::arg("stats"),
           py::arg("ready_ptr") = 0, py::arg("lo") = 0, py::arg("hi") = 0, py::arg("epoch") = py::none());
-    m.def("gemm_splitk_bf16", &gemm_splitk_bf16);
+    m.def("gemm_splitk_bf16", &gemm_splitk_bf16, py::arg("A"), py::arg("B"), py::arg("out"), py::arg("ws"), py::arg("bias"), py::arg("relu"),
+          py::arg("drop_p") = 0.0, py::arg("drop_seed") = 0, py::arg("drop_step") = py::none(), py::arg("drop_stream") = 0);
     m.def("conv_bf16", &conv_bf16);
     m.def("conv_bf16_strided", &conv_bf16_strided);
     m.def("conv_wgrad_bf16_strided", &conv_wgrad_bf16_strided);
@@ -339,9 +359,11 @@ void register_gemm_bindings(py::module_& m) {
     m.def("bn_apply", &bn_apply);
     m.def("bn_bwd", &bn_bwd);
     m.def("bn_bwd_recompute", &bn_bwd_recompute);
-    m.def("relu_bwd", &relu_bwd);
-    m.def("maxpool2_fwd", &maxpool2_fwd);
-    m.def("maxpool2_bwd", &maxpool2_bwd);
+    m.def("relu_bwd", &relu_bwd, py::arg("dy"), py::arg("y"), py::arg("scale") = 1.0);
+    m.def("maxpool2_fwd", &maxpool2_fwd, py::arg("x"), py::arg("y"), py::arg("idx"), py::arg("drop_p") = 0.0, py::arg("drop_seed") = 0,
+          py::arg("drop_step") = py::none(), py::arg("drop_stream") = 0);
+    m.def("maxpool2_bwd", &maxpool2_bwd, py::arg("dy"), py::arg("idx"), py::arg("dx"), py::arg("drop_p") = 0.0, py::arg("drop_seed") = 0,
+          py::arg("drop_step") = py::none(), py::arg("drop_stream") = 0);
     m.def("avgpool_fwd", &avgpool_fwd);
     m.def("avgpool_bwd", &avgpool_bwd);
     m.def("dropout_fwd", &dropout_fwd);

@@ -119,8 +119,9 @@ umma_gemm_splitk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 }
 
 // out = bf16(act(ws + bias)); also re-zeroes the workspace so the next call needs no memset
+// drop.thr != 0: dropout fused into this finishing pass (keep-mask of output element 4 q + i, common.cuh: dropout_keep8)
 __global__ void __launch_bounds__(256) splitk_finish_kernel(float* __restrict__ ws, const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
-                                                              long long n4, int N, int relu) {
+                                                              long long n4, int N, int relu, DropSpec drop) {
     pdl_wait();
     pdl_trigger();
     for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (long long)gridDim.x * blockDim.x) {
@@ -131,6 +132,11 @@ __global__ void __launch_bounds__(256) splitk_finish_kernel(float* __restrict__ 
             v.x += bias[c]; v.y += bias[c + 1]; v.z += bias[c + 2]; v.w += bias[c + 3];
         }
         if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        if (drop.thr) {
+            const uint32_t keep = dropout_keep8(drop, q >> 1) >> ((q & 1) * 4);       // elements 4 q .. 4 q + 3 of their group of eight
+            v.x = (keep & 1) ? v.x * drop.scale : 0.f; v.y = (keep & 2) ? v.y * drop.scale : 0.f;
+            v.z = (keep & 4) ? v.z * drop.scale : 0.f; v.w = (keep & 8) ? v.w * drop.scale : 0.f;
+        }
         *reinterpret_cast<uint2*>(out + 4 * q) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
     }
 }
@@ -139,7 +145,7 @@ __global__ void __launch_bounds__(256) splitk_finish_kernel(float* __restrict__ 
 
 // out[M][N] (bf16) = act(A[M][K] B[N][K]^T + bias) through `ws` ([M][N] fp32, ZERO on entry; left zero on exit).  K % 64 == 0, N % 8 == 0.
 cudaError_t launch_gemm_splitk_bf16(const void* A, const void* B, void* out, float* ws, int M, int N, int K, const float* bias, int relu,
-                                    int num_sms, cudaStream_t st) {
+                                    int num_sms, cudaStream_t st, const DropSpec* drop) {
     if (K % SBK || N % 8 || M <= 0) return cudaErrorInvalidValue;
     static bool configured = false;
     if (!configured) {
@@ -170,7 +176,7 @@ cudaError_t launch_gemm_splitk_bf16(const void* A, const void* B, void* out, flo
     long long blocks = (n4 + 255) / 256;
     if (blocks > num_sms * 4) blocks = num_sms * 4;
     return launch_kernel(splitk_finish_kernel, dim3((int)blocks), dim3(256), (size_t)0, st, ws, bias, reinterpret_cast<__nv_bfloat16*>(out), n4, N,
-                         relu);
+                         relu, drop ? *drop : DropSpec{});
 }
 
 }  // namespace rlr

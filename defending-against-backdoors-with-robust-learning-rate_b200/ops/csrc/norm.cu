@@ -346,26 +346,30 @@ cudaError_t launch_bn_bwd_apply(const __nv_bfloat16* dy, const __nv_bfloat16* y,
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) relu_bwd_kernel(__nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y, long long n8) {
+// dy <- dy * (y > 0) * scale.  scale != 1: the layer's output went through fused dropout (y = relu(z) * keep / (1 - p)): y > 0 exactly where
+// the element was kept AND z > 0, so the ReLU mask and the dropout mask are read off y together and no mask is stored or recomputed.
+__global__ void __launch_bounds__(256) relu_bwd_kernel(__nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y, long long n8, float scale) {
     for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n8; q += (long long)gridDim.x * blockDim.x) {
         bf8 d = load8(dy + 8 * q);
         const bf8 yv = load8(y + 8 * q);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) d.v[i] = yv.v[i] > 0.f ? d.v[i] : 0.f;
+        for (int i = 0; i < 8; ++i) d.v[i] = yv.v[i] > 0.f ? d.v[i] * scale : 0.f;
         store8(dy + 8 * q, d);
     }
 }
-cudaError_t launch_relu_bwd(__nv_bfloat16* dy, const __nv_bfloat16* y, long long n, int num_sms, cudaStream_t st) {
+cudaError_t launch_relu_bwd(__nv_bfloat16* dy, const __nv_bfloat16* y, long long n, int num_sms, cudaStream_t st, float scale) {
     if (n % 8) return cudaErrorInvalidValue;
-    relu_bwd_kernel<<<rows_grid(n / 8, 256, num_sms, 8), 256, 0, st>>>(dy, y, n / 8);
+    relu_bwd_kernel<<<rows_grid(n / 8, 256, num_sms, 8), 256, 0, st>>>(dy, y, n / 8, scale);
     return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // 2x2 / stride-2 max-pool (floor mode, like nn.MaxPool2d(2,2)); idx = 2*dy+dx of the first maximum
 // ---------------------------------------------------------------------------------------------------------------------
+// drop.thr != 0: dropout fused into the pooling epilogue -- the pooled value is scaled / zeroed by the Philox keep-mask of its output
+// element (dropout_keep8); the backward kernel re-evaluates the same mask, nothing is stored.
 __global__ void __launch_bounds__(256) maxpool2_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
-                                                             uint8_t* __restrict__ idx, int B, int H, int W, int C) {
+                                                             uint8_t* __restrict__ idx, int B, int H, int W, int C, DropSpec drop) {
     const int Ho = H / 2, Wo = W / 2, cg_n = C / 8;
     const long long total = (long long)B * Ho * Wo * cg_n;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
@@ -384,6 +388,11 @@ __global__ void __launch_bounds__(256) maxpool2_fwd_kernel(const __nv_bfloat16* 
             for (int i = 0; i < 8; ++i) if (v.v[i] > best.v[i]) { best.v[i] = v.v[i]; bi[i] = (uint8_t)k; }
         }
         const size_t o = (((size_t)b * Ho + ho) * Wo + wo) * C + cg * 8;
+        if (drop.thr) {
+            const uint32_t keep = dropout_keep8(drop, (long long)(o >> 3));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) best.v[i] = (keep >> i & 1) ? best.v[i] * drop.scale : 0.f;
+        }
         store8(y + o, best);
         uint2 pk;
         pk.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
@@ -392,7 +401,7 @@ __global__ void __launch_bounds__(256) maxpool2_fwd_kernel(const __nv_bfloat16* 
     }
 }
 __global__ void __launch_bounds__(256) maxpool2_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx,
-                                                             __nv_bfloat16* __restrict__ dx, int B, int H, int W, int C) {
+                                                             __nv_bfloat16* __restrict__ dx, int B, int H, int W, int C, DropSpec drop) {
     const int Ho = H / 2, Wo = W / 2, cg_n = C / 8;
     const long long total = (long long)B * H * W * cg_n;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
@@ -407,7 +416,12 @@ __global__ void __launch_bounds__(256) maxpool2_bwd_kernel(const __nv_bfloat16* 
         const int ho = h >> 1, wo = w >> 1;
         if (ho < Ho && wo < Wo) {
             const size_t src = (((size_t)b * Ho + ho) * Wo + wo) * C + cg * 8;
-            const bf8 g = load8(dy + src);
+            bf8 g = load8(dy + src);
+            if (drop.thr) {     // gradient of the fused dropout: the forward's keep-mask of this pooled element, recomputed
+                const uint32_t keep = dropout_keep8(drop, (long long)(src >> 3));
+#pragma unroll
+                for (int i = 0; i < 8; ++i) g.v[i] = (keep >> i & 1) ? g.v[i] * drop.scale : 0.f;
+            }
             const uint2 pk = *reinterpret_cast<const uint2*>(idx + src);
             const int me = (h & 1) * 2 + (w & 1);
 #pragma unroll
@@ -419,16 +433,23 @@ __global__ void __launch_bounds__(256) maxpool2_bwd_kernel(const __nv_bfloat16* 
         store8(dx + (((size_t)b * H + h) * W + w) * C + cg * 8, o);
     }
 }
-cudaError_t launch_maxpool2_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, uint8_t* idx, int B, int H, int W, int C, cudaStream_t st) {
+static DropSpec make_drop(float p, uint64_t seed, const long long* step, uint64_t stream) {
+    DropSpec d{};
+    if (p > 0.f && step) { d.thr = (uint32_t)(p * 65536.0f); d.scale = 1.0f / (1.0f - p); d.seed = seed; d.stream = stream; d.step = step; }
+    return d;
+}
+cudaError_t launch_maxpool2_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, uint8_t* idx, int B, int H, int W, int C, cudaStream_t st, float drop_p,
+                                uint64_t seed, const long long* step, uint64_t stream) {
     if (C % 8) return cudaErrorInvalidValue;
     const long long total = (long long)B * (H / 2) * (W / 2) * (C / 8);
-    maxpool2_fwd_kernel<<<rows_grid(total, 256, 148, 8), 256, 0, st>>>(x, y, idx, B, H, W, C);
+    maxpool2_fwd_kernel<<<rows_grid(total, 256, 148, 8), 256, 0, st>>>(x, y, idx, B, H, W, C, make_drop(drop_p, seed, step, stream));
     return cudaGetLastError();
 }
-cudaError_t launch_maxpool2_bwd(const __nv_bfloat16* dy, const uint8_t* idx, __nv_bfloat16* dx, int B, int H, int W, int C, cudaStream_t st) {
+cudaError_t launch_maxpool2_bwd(const __nv_bfloat16* dy, const uint8_t* idx, __nv_bfloat16* dx, int B, int H, int W, int C, cudaStream_t st, float drop_p,
+                                uint64_t seed, const long long* step, uint64_t stream) {
     if (C % 8) return cudaErrorInvalidValue;
     const long long total = (long long)B * H * W * (C / 8);
-    maxpool2_bwd_kernel<<<rows_grid(total, 256, 148, 8), 256, 0, st>>>(dy, idx, dx, B, H, W, C);
+    maxpool2_bwd_kernel<<<rows_grid(total, 256, 148, 8), 256, 0, st>>>(dy, idx, dx, B, H, W, C, make_drop(drop_p, seed, step, stream));
     return cudaGetLastError();
 }
 
@@ -479,19 +500,15 @@ cudaError_t launch_avgpool_bwd(const __nv_bfloat16* dy, __nv_bfloat16* dx, int B
 __global__ void __launch_bounds__(256) dropout_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                                             uint8_t* __restrict__ mask, long long n8, float p, uint64_t seed,
                                                             const long long* __restrict__ step, uint64_t stream) {
-    const Philox ph(seed);
-    const uint64_t str = ((uint64_t)(*step) << 20) ^ stream;
-    const uint32_t thr = (uint32_t)(p * 65536.0f);
-    const float scale = 1.0f / (1.0f - p);
+    DropSpec d{(uint32_t)(p * 65536.0f), 1.0f / (1.0f - p), seed, stream, step};
+    const float scale = d.scale;
     for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n8; q += (long long)gridDim.x * blockDim.x) {
-        const uint4 u = ph((uint64_t)q, str);
-        const uint32_t r[4] = {u.x, u.y, u.z, u.w};
+        const uint32_t keep = dropout_keep8(d, q);
         bf8 v = load8(x + 8 * q);
         uint8_t m[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const uint32_t bits = (r[i >> 1] >> (16 * (i & 1))) & 0xffffu;
-            m[i] = bits >= thr;
+            m[i] = keep >> i & 1;
             v.v[i] = m[i] ? v.v[i] * scale : 0.f;
         }
         store8(y + 8 * q, v);

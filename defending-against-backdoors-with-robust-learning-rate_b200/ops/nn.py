@@ -368,21 +368,28 @@ def bn_bwd(dy, y, x, gamma, mean_rstd, dsum, dx, dres, dgamma, dbeta, relu, impl
     dx.copy_((gamma * mean_rstd[1] * (dz - s0 / M - xhat * s1 / M)).reshape(dx.shape))
 
 
-def relu_bwd_(dy, y, impl):
+def relu_bwd_(dy, y, impl, scale=1.0):
+    """dy <- dy * (y > 0) * scale.  ``scale`` = 1/(1-p) when dropout was fused into the producer of ``y`` (y = relu(z) * keep / (1-p)):
+    y > 0 exactly where the element was kept and z > 0, so one mask read off the output covers ReLU and dropout."""
     if impl == "sm100" and dy.numel() % 8 == 0:
-        _ext().relu_bwd(dy, y)
+        _ext().relu_bwd(dy, y, float(scale))
     else:
         if impl == "sm100":
             _fallback("relu_bwd", f"numel={dy.numel()}")
-        dy.mul_(y > 0)
+        dy.mul_((y > 0).to(dy.dtype) * scale)
 
 
 # =====================================================================================================================
 # pooling / dropout
 # =====================================================================================================================
-def maxpool2_fwd(x, y, idx, impl):
+def maxpool2_fwd(x, y, idx, impl, drop=None, mask=None):
+    """2x2 max-pool; ``drop`` = (p, seed, step counter tensor, node id): dropout fused into the pooling kernel (Philox keep-mask of the
+    pooled element, recomputed by ``maxpool2_bwd`` -- no mask tensor).  The aten back-end draws a torch mask into ``mask`` instead."""
     if impl == "sm100" and x.shape[-1] % 8 == 0:
-        _ext().maxpool2_fwd(x, y, idx)
+        if drop is not None:
+            _ext().maxpool2_fwd(x, y, idx, float(drop[0]), int(drop[1]), drop[2], int(drop[3]))
+        else:
+            _ext().maxpool2_fwd(x, y, idx)
         return
     if impl == "sm100":
         _fallback("maxpool2_fwd", f"C={x.shape[-1]}")
@@ -390,18 +397,27 @@ def maxpool2_fwd(x, y, idx, impl):
     Ho, Wo = H // 2, W // 2
     win = x[:, :Ho * 2, :Wo * 2].reshape(B, Ho, 2, Wo, 2, C).permute(0, 1, 3, 5, 2, 4).reshape(B, Ho, Wo, C, 4)
     v, i = win.float().max(-1)
+    if drop is not None:
+        keep = torch.rand(v.shape, device=v.device) >= drop[0]
+        mask.copy_(keep)
+        v = v * keep / (1 - drop[0])
     y.copy_(v); idx.copy_(i)
 
 
-def maxpool2_bwd(dy, idx, dx, impl):
+def maxpool2_bwd(dy, idx, dx, impl, drop=None, mask=None):
     if impl == "sm100" and dx.shape[-1] % 8 == 0:
-        _ext().maxpool2_bwd(dy, idx, dx)
+        if drop is not None:
+            _ext().maxpool2_bwd(dy, idx, dx, float(drop[0]), int(drop[1]), drop[2], int(drop[3]))
+        else:
+            _ext().maxpool2_bwd(dy, idx, dx)
         return
     if impl == "sm100":
         _fallback("maxpool2_bwd", f"C={dx.shape[-1]}")
     B, H, W, C = dx.shape
     Ho, Wo = H // 2, W // 2
     dx.zero_()
+    if drop is not None:
+        dy = dy * mask.to(dy.dtype) / (1 - drop[0])
     oh = F.one_hot(idx.long(), 4).to(dy.dtype) * dy.unsqueeze(-1)                   # [B,Ho,Wo,C,4]
     dx[:, :Ho * 2, :Wo * 2].copy_(oh.reshape(B, Ho, Wo, C, 2, 2).permute(0, 1, 4, 2, 5, 3).reshape(B, Ho * 2, Wo * 2, C))
 
@@ -443,9 +459,17 @@ def dropout_bwd(dy, mask, dx, p, impl):
 # =====================================================================================================================
 # linear
 # =====================================================================================================================
-def linear_fwd(x, w, bias, y, relu, impl):
-    """y[B,N] = x[B,K] w[N,K]^T + b (ReLU).  N <= 32: CUDA-core head kernel; otherwise the tcgen05 GEMM."""
+def linear_fused_dropout_ok(N, K):
+    """Can dropout be fused into this linear layer's GEMM epilogue (tcgen05 GEMM / split-K finishing pass)?"""
+    return N > 32 and K % 64 == 0 and N % 64 == 0
+
+
+def linear_fwd(x, w, bias, y, relu, impl, drop=None):
+    """y[B,N] = x[B,K] w[N,K]^T + b (ReLU).  N <= 32: CUDA-core head kernel; otherwise the tcgen05 GEMM.  ``drop`` = (p, seed, step
+    counter tensor, node id): dropout fused into the GEMM epilogue after bias / ReLU; the backward pass reads the
+    combined ReLU-and-dropout mask off the output (``relu_bwd_(..., scale=1/(1-p))``)."""
     N, K = w.shape
+    dk = dict(drop_p=float(drop[0]), drop_seed=int(drop[1]), drop_step=drop[2], drop_stream=int(drop[3])) if drop is not None else {}
     if impl == "sm100":
         if N <= 32:
             if USE_HEAD_V2 and K % 2 == 0 and (N * K) % 8 == 0 and N * K * 2 <= 48 * 1024:
@@ -457,14 +481,16 @@ def linear_fwd(x, w, bias, y, relu, impl):
             M = x.shape[0]
             if USE_SPLITK and K >= 1024 and ((M + 127) // 128) * ((N + 127) // 128) <= 16:
                 ws = scratch(("splitk_ws", y.data_ptr()), (M, N), torch.float32, x.device)     # zero at creation, left zero by the kernel
-                _ext().gemm_splitk_bf16(x.contiguous(), w, y, ws, bias, bool(relu))
+                _ext().gemm_splitk_bf16(x.contiguous(), w, y, ws, bias, bool(relu), **dk)
                 return
-            _ext().gemm_bf16(x.contiguous(), w, y, bias, bool(relu), False, None)
+            _ext().gemm_bf16(x.contiguous(), w, y, bias, bool(relu), False, None, **dk)
             return
         _fallback("linear_fwd", f"N={N} K={K}")
     out = F.linear(x, w.to(x.dtype), bias.to(x.dtype) if bias is not None else None)
     if relu:
         out = F.relu(out)
+    if drop is not None:       # aten back-end: torch's own RNG; the backward still reads the mask off y (relu + dropout)
+        out = out * (torch.rand(out.shape, device=out.device) >= drop[0]) / (1 - drop[0])
     y.copy_(out)
 
 

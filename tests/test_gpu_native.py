@@ -461,3 +461,47 @@ def test_fused_handoff_equals_round_init_path(model):
     print(model, f"round 1: unfused-vs-unfused {noise1:.2e}, fused-vs-unfused {diff1:.2e} | round 3: {noise3:.2e} vs {diff3:.2e}")
     assert diff1 <= 3 * noise1 + 1e-5, (diff1, noise1)
     assert diff3 <= 3 * noise3 + 1e-4, (diff3, noise3)
+
+
+def test_fused_dropout_kernels():
+    """Dropout fused into its producers: max-pool kernel, tcgen05 GEMM epilogue, split-K finishing pass.  Keep fraction and
+    1/(1-p) scaling, determinism in (seed, step, node), fresh masks per step, and forward/backward mask consistency (the pooling backward
+    recomputes the Philox mask; the linear backward reads ReLU-and-dropout off the output)."""
+    torch.manual_seed(5)
+    e = ops.ext()
+    step = torch.zeros(1, dtype=torch.int64, device=DEV)
+    p = 0.5
+    # ---- max-pool + dropout ----
+    x = (torch.rand(16, 12, 12, 64, device=DEV) + 0.5).to(BF)                    # strictly positive: zeros in y are dropped elements
+    y0 = torch.empty(16, 6, 6, 64, device=DEV, dtype=BF); idx0 = torch.empty(16, 6, 6, 64, device=DEV, dtype=torch.uint8)
+    ops.maxpool2_fwd(x, y0, idx0, "sm100")
+    y1, idx1 = torch.empty_like(y0), torch.empty_like(idx0)
+    ops.maxpool2_fwd(x, y1, idx1, "sm100", (p, 7, step, 3))
+    keep = y1 != 0
+    assert abs(float(keep.float().mean()) - (1 - p)) < 0.02 and torch.equal(idx0, idx1)
+    torch.testing.assert_close(y1[keep].float(), (y0[keep].float() / (1 - p)).to(BF).float(), rtol=1e-2, atol=1e-2)
+    y2 = torch.empty_like(y0); ops.maxpool2_fwd(x, y2, idx1, "sm100", (p, 7, step, 3))
+    assert torch.equal(y1, y2)                                                    # same (seed, step, node) -> same mask
+    dy = torch.ones_like(y0); dx = torch.empty_like(x)
+    ops.maxpool2_bwd(dy, idx1, dx, "sm100", (p, 7, step, 3))
+    pooled_grad = dx.float().reshape(16, 6, 2, 6, 2, 64).sum((2, 4))             # gradient mass per pooled element
+    torch.testing.assert_close(pooled_grad, keep.float() / (1 - p), rtol=1e-2, atol=1e-2)
+    step += 1
+    y3 = torch.empty_like(y0); ops.maxpool2_fwd(x, y3, idx1, "sm100", (p, 7, step, 3))
+    assert not torch.equal(y1, y3)                                                # next step -> fresh mask
+    # ---- Linear + ReLU + dropout: tcgen05 GEMM epilogue (K = 128) and split-K finishing pass (K = 2048) ----
+    for K in (128, 2048):
+        xx = torch.randn(256, K, device=DEV).to(BF)
+        ww = (torch.randn(128, K, device=DEV) / K ** 0.5).to(BF)
+        bb = torch.randn(128, device=DEV) * 0.1
+        ref = torch.empty(256, 128, device=DEV, dtype=BF); ops.linear_fwd(xx, ww, bb, ref, True, "sm100")
+        out = torch.empty_like(ref); ops.linear_fwd(xx, ww, bb, out, True, "sm100", (p, 9, step, 4))
+        pos = ref.float() > 0
+        kept = (out != 0) & pos
+        assert abs(float(kept.float().sum() / pos.float().sum()) - (1 - p)) < 0.03, K
+        torch.testing.assert_close(out[kept].float(), (ref[kept].float() / (1 - p)).to(BF).float(), rtol=2e-2, atol=2e-2)
+        assert float(out[~pos].abs().max()) == 0.0
+        out2 = torch.empty_like(ref); ops.linear_fwd(xx, ww, bb, out2, True, "sm100", (p, 9, step, 4))
+        assert torch.equal(out, out2)
+        d = torch.ones_like(out); ops.relu_bwd_(d, out, "sm100", 1.0 / (1 - p))
+        torch.testing.assert_close(d.float(), kept.float() / (1 - p), rtol=1e-2, atol=1e-2)

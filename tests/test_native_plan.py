@@ -57,3 +57,44 @@ def test_eval_mode_uses_running_stats_and_no_dropout():
     ref = GraphNet(lay, w.clone(), None).eval()
     torch.testing.assert_close(a, b)
     torch.testing.assert_close(a, ref(x.permute(0, 3, 1, 2)).detach(), atol=1e-4, rtol=1e-4)
+
+
+def test_dropout_layers_are_fused_into_their_producers():
+    """every dropout of the reference CNNs follows a max-pool or a Linear+ReLU (src/models.py:25-30,50-57) and is folded
+    into that producer -- the plan has no stand-alone dropout op and no mask tensor; evaluation mode applies no dropout; training mode
+    drops about p of the fused output and the backward pass zeroes exactly the dropped positions."""
+    import torch
+    from rlr_b200.models import get_layout
+    from rlr_b200.models import native as nat
+    for model, n_drop in (("cnn_mnist", 2), ("cnn_cifar", 3)):
+        lay = get_layout(model)
+        net = nat.NativeNet(lay, "cpu", 16, impl="aten", act_dtype=torch.float32)
+        assert sum(op.kind == "dropout" for op in net.plan) == 0
+        assert sum("drop" in op.saved for op in net.plan) == n_drop
+        w = lay.init_(torch.zeros(lay.n_total), 3)
+        g = torch.zeros_like(w)
+        net.bind(w, w.clone(), g)
+        C, H, W = lay.in_shape
+        x = torch.randn(16, H, W, C)
+        torch.manual_seed(0)
+        a = net.forward(x, False).clone()
+        b = net.forward(x, False).clone()
+        assert torch.equal(a, b)                                   # evaluation: deterministic, no dropout
+        t1 = net.forward(x, True).clone()
+        t2 = net.forward(x, True).clone()
+        assert not torch.equal(t1, t2)                             # training: fresh masks
+        fused = [op for op in net.plan if "drop" in op.saved and op.kind == "linear"][0]
+        y = net.T(fused.y, 16)
+        frac_zero = float((y == 0).float().mean())
+        assert frac_zero > 0.45                                    # >= p dropped (+ ReLU zeros)
+        _, dl = __import__("rlr_b200").ops.softmax_xent(t2, torch.randint(0, 10, (16,)))
+        net.backward(dl)
+        gy = net.G(fused.y, 16)
+        assert float(gy[y == 0].abs().max()) == 0.0               # gradient is zero exactly where the output was dropped / clamped
+    old = nat.FUSE_DROPOUT
+    try:
+        nat.FUSE_DROPOUT = False
+        net = nat.NativeNet(get_layout("cnn_mnist"), "cpu", 4, impl="aten", act_dtype=torch.float32)
+        assert sum(op.kind == "dropout" for op in net.plan) == 2
+    finally:
+        nat.FUSE_DROPOUT = old
