@@ -50,6 +50,7 @@ def parse():
     p.add_argument("--agents_in_flight", type=int, default=1, help="agents a GPU trains concurrently (ours only)")
     p.add_argument("--agent_frac", type=float, default=1.0, help="fraction of the agents sampled per round (reference --agent_frac)")
     p.add_argument("--pattern_type", type=str, default="plus")
+    p.add_argument("--no_fused_handoff", action="store_true", help="ours: keep round_init + the aggregation kernel's barrier-out (A/B of the hand-off fusion)")
     return p.parse_args()
 
 
@@ -202,7 +203,7 @@ def run_ours(a):
         args = make_args(data=a.data, model=a.model, num_agents=a.agents or n, agents_in_flight=a.agents_in_flight, local_ep=a.local_ep, bs=a.bs,
                          aggr=a.aggr,
                          robustLR_threshold=a.theta, num_corrupt=a.num_corrupt, poison_frac=a.poison_frac, agent_frac=a.agent_frac,
-                         pattern_type=a.pattern_type,
+                         pattern_type=a.pattern_type, no_fused_handoff=a.no_fused_handoff,
                          synthetic=a.train_size, synthetic_val=1000, snap=10 ** 9, rounds=10 ** 9, log_dir="",
                          trainer=trainer, backend=a.backend, dtype=a.dtype, seed=0)
         return FLEngine(args, ctx=ctx, verbose=False)

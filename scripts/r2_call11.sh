@@ -12,3 +12,4 @@ for nf in 2 4; do
 import json,sys
 d=json.loads(sys.stdin.read()); print('readme_fmnist_10 agents_in_flight=$nf: %.1f ms/round' % d['ms_per_step'])" | tee -a gpurun_out/c11_configs_ours.txt
 done
+timeout 600 python scripts/bench_aggregate.py 2>&1 | tee gpurun_out/c11_bench_aggregate.txt
