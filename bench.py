@@ -47,7 +47,7 @@ def parse():
     p.add_argument("--agents", type=int, default=0,
                    help="number of FL agents (default 0 = one per GPU, the headline config); more agents than GPUs are time-multiplexed "
                         "-- e.g. --agents 10 --gpus 1 is the reference README's FMNIST setting")
-    p.add_argument("--agents_in_flight", type=int, default=1, help="agents a GPU trains concurrently (ours only)")
+    p.add_argument("--agents_in_flight", type=int, default=0, help="agents a GPU trains concurrently (ours only; 0 = the engine's auto rule)")
     p.add_argument("--agent_frac", type=float, default=1.0, help="fraction of the agents sampled per round (reference --agent_frac)")
     p.add_argument("--pattern_type", type=str, default="plus")
     p.add_argument("--no_fused_handoff", action="store_true", help="ours: keep round_init + the aggregation kernel's barrier-out (A/B of the hand-off fusion)")
@@ -100,7 +100,7 @@ class ClockSampler:
 def config_dict(a, n, impl):
     k = a.agents or n                     # agents: one per GPU unless --agents
     return {"model": a.model, "dataset": f"{a.data} (synthetic, {a.train_size} train images)", "num_agents": k,
-            "agents_per_gpu": (k + n - 1) // n if impl == "ours" else k, "agents_in_flight": a.agents_in_flight if impl == "ours" else 1,
+            "agents_per_gpu": (k + n - 1) // n if impl == "ours" else k, "agents_in_flight": (a.agents_in_flight or "auto") if impl == "ours" else 1,
             "global_batch": a.bs * n if impl == "ours" else a.bs,
             "local_batch": a.bs, "local_ep": a.local_ep, "aggr": a.aggr, "robustLR_threshold": a.theta,
             "num_corrupt": a.num_corrupt, "poison_frac": a.poison_frac, "agent_frac": a.agent_frac, "seq_len": None,
@@ -280,7 +280,7 @@ def run_ours(a):
                "config": {**config_dict(a, n, "ours"), "trainer": eng.trainer.name, "agg_backend": eng.fused.backend,
                           "symm_provider": eng.fused.buf.provider, "multicast": bool(getattr(eng.fused, "use_multimem", False)),
                           "local_steps_per_round_per_gpu": info["steps"], "n_params": eng.layout.n_params,
-                          "fused_handoff": bool(eng.handoff)},
+                          "fused_handoff": bool(eng.handoff), "agents_in_flight_used": len(eng.trainers)},
                "clocks": ck, "e2e": e2e, "gpu_launches": int(launches), "notes": notes,
                "library_fallbacks": ops_fallbacks(), "agg_check": agg_check,
                "phase_ms_per_round_rank0": {k: v / a.steps for k, v in phases.items()}}

@@ -97,7 +97,12 @@ class FLEngine:
         self.trainer = make_trainer(args.trainer, self.layout, args, dev, max_shard)
         # Several agents per GPU and round can be trained concurrently: trainer i (own parameters, activations, CUDA graphs) runs
         # on stream i.  The small reference CNNs are launch-latency bound at batch 256, so two to four agents in flight fill the GPU.
-        n_flight = min(max(1, int(getattr(args, "agents_in_flight", 1))), max_slots)
+        n_flight = int(getattr(args, "agents_in_flight", 0))
+        if n_flight <= 0:
+            # auto: the small reference CNNs (~1 M parameters) are launch / latency bound at batch 256 -- two agents in flight fill the GPU
+            # (FMNIST CNN, 10 agents, one B200: 160 -> 120 ms per round); the large models already fill it with one
+            n_flight = 2 if (dev.type == "cuda" and self.layout.n_params < 4_000_000) else 1
+        n_flight = min(max(1, n_flight), max_slots)
         self.trainers = [self.trainer] + [make_trainer(args.trainer, self.layout, args, dev, max_shard) for _ in range(n_flight - 1)]
         # (on CPU the extra trainers are still used round-robin -- same bookkeeping, no overlap)
         self.streams = [torch.cuda.Stream(dev) for _ in range(n_flight)] if (n_flight > 1 and dev.type == "cuda") else None
@@ -160,22 +165,26 @@ class FLEngine:
         pin = (lambda t: t.cpu().pin_memory()) if dev.type == "cuda" else (lambda t: t.cpu().clone())
         total, n_max = 0, max(a.n_data for a in self.agents)
         ref = self.agents[0].dataset
-        buf = DeviceDataset(ref.name, torch.zeros((n_max, *ref.data.shape[1:]), dtype=ref.data.dtype, device=dev),
-                            torch.zeros(n_max, dtype=torch.int64, device=dev))
+        # one staging dataset per in-flight trainer: trainer i always trains out of buffer i, so its CUDA graphs keep their addresses
+        self._stream_bufs = [DeviceDataset(ref.name, torch.zeros((n_max, *ref.data.shape[1:]), dtype=ref.data.dtype, device=dev),
+                                           torch.zeros(n_max, dtype=torch.int64, device=dev)) for _ in self.trainers]
         for a in self.agents:
             x, y = a.dataset.data[a.idxs].contiguous(), a.dataset.targets[a.idxs].contiguous()
             self._stream_src[a.id] = (pin(x), pin(y))
-            a.dataset = buf                                          # all agents train out of the staging buffer ...
+            a.dataset = self._stream_bufs[0]                         # re-pointed to its trainer's buffer right before training
             a.idxs = torch.arange(a.n_data, device=dev)              # ... with local indices
             total += x.numel() * x.element_size() + y.numel() * y.element_size()
-        self._stream_buf = buf
+        self._stream_buf = self._stream_bufs[0]
         return total
 
-    def _upload_shard(self, agent):
+    def _upload_shard(self, agent, buf=None):
+        """Host->device copy of one agent's shard (pinned source, current stream) into a staging dataset; the agent then trains out of it."""
+        buf = buf if buf is not None else self._stream_buf
         x, y = self._stream_src[agent.id]
         n = agent.n_data
-        self._stream_buf.data[:n].copy_(x, non_blocking=True)
-        self._stream_buf.targets[:n].copy_(y, non_blocking=True)
+        buf.data[:n].copy_(x, non_blocking=True)
+        buf.targets[:n].copy_(y, non_blocking=True)
+        agent.dataset = buf
         return x.numel() * x.element_size() + y.numel() * y.element_size()
 
     # ---- one federated round (src/federated.py:66-74) --------------------------------------------------------
@@ -186,7 +195,7 @@ class FLEngine:
         steps = 0
         h2d = 0
         self.timer.start("local_train")
-        concurrent = len(self.trainers) > 1 and not stream_inputs       # streamed inputs share one staging buffer: sequential
+        concurrent = len(self.trainers) > 1
         if concurrent:
             for part in self._loss_parts:
                 part.zero_()
@@ -203,6 +212,8 @@ class FLEngine:
             if concurrent:
                 i = k % len(self.trainers)
                 with (torch.cuda.stream(self.streams[i]) if self.streams is not None else contextlib.nullcontext()):
+                    if stream_inputs:
+                        h2d += self._upload_shard(agent, self._stream_bufs[i])     # on stream i: ordered after trainer i's previous agent
                     st = agent.local_train(self.trainers[i], self.w_global, fused.slots[s], rnd)
                     self._loss_parts[i] += st["loss_sum"]
             else:

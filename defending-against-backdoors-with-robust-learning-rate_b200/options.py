@@ -54,9 +54,10 @@ def build_parser() -> argparse.ArgumentParser:
                    help="activation/GEMM-operand dtype on GPU (master params, updates, aggregation stay fp32)")
     p.add_argument("--backend", type=str, default="auto", choices=("auto", "fused", "nccl", "gloo", "local"),
                    help="aggregation transport: fused = P2P/multicast sm_100a kernel; nccl/gloo = all_gather + kernel")
-    p.add_argument("--agents_in_flight", type=int, default=1,
+    p.add_argument("--agents_in_flight", type=int, default=0,
                    help="agents a GPU trains CONCURRENTLY when it hosts several per round (one trainer + CUDA stream each); helps the "
-                        "small launch-bound CNNs, costs one set of activation buffers per extra agent")
+                        "small launch-bound CNNs, costs one set of activation buffers per extra agent.  0 = auto (2 for models under 4 M "
+                        "parameters on a GPU, else 1)")
     p.add_argument("--no_fused_handoff", action="store_true",
                    help="keep the separate round_init pass and the aggregation kernel's barrier-out instead of fusing the parameter "
                         "hand-off of a round with the first local GEMM (native trainer; on by default)")
