@@ -39,7 +39,8 @@ constexpr int HL_STAGING = 128 * HL_PITCH_OUT + 2 * 64 * 4;
 constexpr int HL_SMEM = HL_W_BYTES + HL_STAGES * HL_HALO_BYTES + HL_STAGING + 1024 + 1024;
 
 struct HaloParams {
-    int NB, H, W;                 // output == input spatial size (pad 1)
+    int NB, H, W;                 // OUTPUT spatial size; input = output + 2 - 2*pad
+    int pad;                      // 0 (valid conv), 1 (same), 2 (full: data gradient of a valid conv)
     int tiles_h, tiles_w, num_tiles;
     int N;                        // Cout (valid columns of this launch's n-tile range)
     void* out; int ldc;
@@ -105,7 +106,7 @@ umma_conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
                 const int h0 = (r / p.tiles_w) * HL_TH, w0 = (r % p.tiles_w) * HL_TW;
                 mbar_wait(&sh->halo_empty[stage], phase ^ 1);
                 mbar_expect_tx(&sh->halo_full[stage], HL_HALO_BYTES);
-                tma_load_4d(&tmX, &sh->halo_full[stage], s_halo + stage * HL_HALO_BYTES, 0, w0 - 1, h0 - 1, n);
+                tma_load_4d(&tmX, &sh->halo_full[stage], s_halo + stage * HL_HALO_BYTES, 0, w0 - p.pad, h0 - p.pad, n);
                 if (++stage == HL_STAGES) { stage = 0; phase ^= 1; }
             }
         }
@@ -200,7 +201,7 @@ umma_conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
                 uint4* dst = reinterpret_cast<uint4*>(s_stage + row * HL_PITCH_OUT + c0 * 2);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) dst[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
-                if (kStats) {   // every tile row is a valid pixel (H % 16 == 0, W % 8 == 0): warp-level column sums
+                if (kStats) {   // every tile row is a valid pixel (the launcher refuses statistics on partial tiles): warp-level column sums
                     const float c1 = warp_transpose_sum32(f1, lane), c2 = warp_transpose_sum32(f2, lane);
                     atomicAdd(&red[c0 + lane], c1);
                     atomicAdd(&red[64 + c0 + lane], c2);
@@ -247,10 +248,14 @@ umma_conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
     if (warp == 2) tmem_dealloc(tmem_acc, 128);
 }
 
-// y[NB][H][W][Cout] = conv3x3(x[NB][H][W][64], w[Cout][9*64]), stride 1, pad 1; H % 16 == 0 and W % 8 == 0.
-cudaError_t launch_conv3x3_halo_bf16(const void* x, const void* w, void* out, int NB, int H, int W, int Cout, const float* bias, int relu,
-                                     int accumulate, float* stats, int bo_mode, long long* dbg, int num_sms, cudaStream_t st) {
-    if (H % HL_TH || W % HL_TW || Cout % 8) return cudaErrorInvalidValue;
+// y[NB][H][W][Cout] = conv3x3(x[NB][Hin][Win][64], w[Cout][9*64]), stride 1, padding pad = (H - Hin + 2) / 2 in {0, 1, 2} (valid / same /
+// full).  Any H, W: the image is covered by ceil(H/16) x ceil(W/8) tiles, pixels beyond the output are masked in the epilogue and input
+// pixels beyond the image are the TMA unit's zero fill.  BatchNorm statistics need whole tiles (H % 16 == 0, W % 8 == 0).
+cudaError_t launch_conv3x3_halo_bf16(const void* x, const void* w, void* out, int NB, int Hin, int Win, int H, int W, int Cout, const float* bias,
+                                     int relu, int accumulate, float* stats, int bo_mode, long long* dbg, int num_sms, cudaStream_t st) {
+    const int pad = (H - Hin + 2) / 2;
+    if (pad < 0 || pad > 2 || H != Hin + 2 * pad - 2 || W != Win + 2 * pad - 2 || H < 1 || W < 1 || Cout % 8) return cudaErrorInvalidValue;
+    if (stats && (H % HL_TH || W % HL_TW)) return cudaErrorInvalidValue;
     static bool configured = false;
     if (!configured) {
         RLR_CUDA_CHECK(cudaFuncSetAttribute(umma_conv3x3_halo_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, HL_SMEM));
@@ -260,12 +265,13 @@ cudaError_t launch_conv3x3_halo_bf16(const void* x, const void* w, void* out, in
     }
     if (stats && accumulate) return cudaErrorInvalidValue;
     HaloParams p{};
-    p.NB = NB; p.H = H; p.W = W; p.tiles_h = H / HL_TH; p.tiles_w = W / HL_TW; p.num_tiles = NB * p.tiles_h * p.tiles_w;
+    p.NB = NB; p.H = H; p.W = W; p.pad = pad;
+    p.tiles_h = (H + HL_TH - 1) / HL_TH; p.tiles_w = (W + HL_TW - 1) / HL_TW; p.num_tiles = NB * p.tiles_h * p.tiles_w;
     p.N = Cout; p.out = out; p.ldc = Cout; p.bias = bias; p.stats = stats; p.relu = relu; p.accumulate = accumulate; p.bo_mode = bo_mode; p.dbg = dbg;
     CUtensorMap tmX, tmW;
     {
-        const uint64_t d[4] = {64, (uint64_t)W, (uint64_t)H, (uint64_t)NB};
-        const uint64_t s[3] = {128, (uint64_t)W * 128, (uint64_t)H * W * 128};
+        const uint64_t d[4] = {64, (uint64_t)Win, (uint64_t)Hin, (uint64_t)NB};
+        const uint64_t s[3] = {128, (uint64_t)Win * 128, (uint64_t)Hin * Win * 128};
         const uint32_t b[4] = {64, HL_PITCH, HL_TH + 2, 1};
         RLR_CUDA_CHECK(make_tmap_bf16(&tmX, x, 4, d, s, b));
     }

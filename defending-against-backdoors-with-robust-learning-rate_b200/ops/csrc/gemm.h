@@ -80,8 +80,8 @@ cudaError_t launch_conv_bf16(const void* x, const void* w, void* out, int NB, in
                              int in_stride = 1, int out_stride = 1, int out_ph = 0, int out_pw = 0);
 
 // ---- conv_halo.cu: persistent 3x3/s1/p1 conv for 64 input channels with smem halo reuse + resident filter ------------------
-cudaError_t launch_conv3x3_halo_bf16(const void* x, const void* w, void* out, int NB, int H, int W, int Cout, const float* bias, int relu,
-                                     int accumulate, float* stats, int bo_mode, long long* dbg, int num_sms, cudaStream_t st);
+cudaError_t launch_conv3x3_halo_bf16(const void* x, const void* w, void* out, int NB, int Hin, int Win, int H, int W, int Cout, const float* bias,
+                                     int relu, int accumulate, float* stats, int bo_mode, long long* dbg, int num_sms, cudaStream_t st);
 
 // ---- conv_halo3.cu (opt-in): the three taps of a filter row in ONE N = 192 MMA, column shift-add in the epilogue -----------------
 cudaError_t launch_conv3x3_halo3_bf16(const void* x, const void* w, void* out, int NB, int H, int W, int Cout, const float* bias, int relu,

@@ -120,9 +120,9 @@ void conv3x3_halo_bf16(at::Tensor x, at::Tensor w, at::Tensor out, c10::optional
                        c10::optional<at::Tensor> stats, int64_t bo_mode, c10::optional<at::Tensor> dbg) {
     c10::cuda::CUDAGuard g(x.device());
     TORCH_CHECK(x.dim() == 4 && x.size(3) == 64 && out.dim() == 4 && w.dim() == 2 && w.size(1) == 9 * 64 && w.size(0) == out.size(3));
-    TORCH_CHECK(out.size(0) == x.size(0) && out.size(1) == x.size(1) && out.size(2) == x.size(2));
+    TORCH_CHECK(out.size(0) == x.size(0) && out.size(1) - x.size(1) == out.size(2) - x.size(2), "halo conv: output = input + 2*pad - 2, pad in {0,1,2}");
     TORCH_CHECK(!stats.has_value() || !stats->defined() || stats->numel() == (int64_t)rlr::kStatSlots * 2 * out.size(3), "stats must be [STAT_SLOTS,2,Cout]");
-    check(rlr::launch_conv3x3_halo_bf16(bf(x), bf(w), bfm(out), x.size(0), x.size(1), x.size(2), out.size(3), opt<const float>(bias), relu,
+    check(rlr::launch_conv3x3_halo_bf16(bf(x), bf(w), bfm(out), x.size(0), x.size(1), x.size(2), out.size(1), out.size(2), out.size(3), opt<const float>(bias), relu,
                                         accumulate, opt<float>(stats), (int)bo_mode, opt<long long>(dbg), num_sms(), cur_stream()), "conv3x3_halo_bf16");
 }
 

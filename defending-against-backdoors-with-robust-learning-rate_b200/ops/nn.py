@@ -32,6 +32,8 @@ USE_BN_RECOMPUTE = bool(int(os.environ.get("RLR_BN_RECOMPUTE", "1")))
 # 3x3/s1/p1 convs with 64 input channels: three filter taps per N = 192 MMA with a lane shift-add epilogue (conv_halo3.cu) instead of
 # nine N = 64 MMAs per k-step.  Opt-in until measured on hardware (RLR_HALO3=1).
 USE_HALO3 = bool(int(os.environ.get("RLR_HALO3", "0")))
+# halo-reuse kernel also for valid / full 3x3 convs and sizes that are not whole 16x8 tiles (reference CNNs: conv2 and its data gradient)
+USE_HALO_ANY = bool(int(os.environ.get("RLR_HALO_ANY", "1")))
 # Dense layers with few output tiles and a deep reduction (FMNIST CNN fc1: 256 x 128 x 9216): split-K GEMM with an fp32 workspace
 # (gemm_splitk.cu).  Opt-in until measured on hardware (RLR_SPLITK=1).
 USE_SPLITK = bool(int(os.environ.get("RLR_SPLITK", "1")))
@@ -97,7 +99,24 @@ def conv_supported(in_shape, a, kind):
     return False
 
 
-def _halo_ok(k, stride, pad, cin, h, w):
+def _halo_ok(k, stride, pad, cin, h, w, stats=False):
+    """Can the persistent halo-reuse kernel (conv_halo.cu) take this 3x3 / stride-1 conv of a 64-channel [h, w] input?  Padding 0 / 1 / 2
+    (valid, same, full = the data gradient of a valid conv); any output size -- the image is covered by 16 x 8 pixel tiles and pixels
+    beyond it are masked -- as long as at least half of the tile area is real output (below that the generic implicit GEMM, which
+    packs the pixels of several images into one 128-row tile, wastes fewer MMAs).  BatchNorm statistics need whole tiles."""
+    if not (k == 3 and stride == 1 and cin == 64 and pad in (0, 1, 2)):
+        return False
+    if not USE_HALO_ANY:                                     # round-1 predicate: 'same' convs on whole tiles only
+        return pad == 1 and h % 16 == 0 and w % 8 == 0
+    ho, wo = h + 2 * pad - 2, w + 2 * pad - 2
+    if ho < 1 or wo < 1:
+        return False
+    if stats and (ho % 16 or wo % 8):
+        return False
+    return 2 * ho * wo >= (-(-ho // 16) * 16) * (-(-wo // 8) * 8)
+
+
+def _wgrad_halo_ok(k, stride, pad, cin, h, w):
     return k == 3 and stride == 1 and pad == 1 and cin == 64 and h % 16 == 0 and w % 8 == 0
 
 
@@ -144,9 +163,9 @@ def conv2d_fwd_sm100(x, w, bias, y, stride, pad, relu, stats, tag="fwd", zero_st
         wp = scratch(("wpad", tag, w.data_ptr()), (Cout, k, k, cp), w.dtype, w.device)
         e.pad_rows(w.reshape(Cout * k * k, Cin), wp.view(Cout * k * k, cp))
         x, w, Cin = xp, wp, cp
-    if _halo_ok(k, stride, pad, Cin, H, W):
+    if _halo_ok(k, stride, pad, Cin, H, W, stats is not None):
         # persistent halo-reuse kernel (conv_halo.cu): 36 KB of L2 traffic per 128-pixel tile instead of 216 KB
-        if USE_HALO3 and stats is None:
+        if USE_HALO3 and stats is None and pad == 1 and H % 16 == 0:
             e.conv3x3_halo3_bf16(x, w.reshape(Cout, 9 * 64), y, bias, bool(relu), False)
             return y
         if stats is not None and zero_stats:
@@ -182,10 +201,10 @@ def conv2d_dgrad_sm100(dy, w, dx, stride, pad, accumulate):
     B = dy.shape[0]
     if stride == 2:
         return _conv2d_dgrad_s2(e, dy, w, dx, pad, accumulate)
-    if _halo_ok(k, 1, k - 1 - pad, Cout, dy.shape[1], dy.shape[2]) and dx.shape[1:3] == dy.shape[1:3]:
-        wt = scratch(("wt", w.data_ptr()), (Cin, k * k * Cout), w.dtype, w.device)   # resident-filter kernel wants K-major taps
+    if _halo_ok(k, 1, k - 1 - pad, Cout, dy.shape[1], dy.shape[2]) and dx.shape[-1] % 8 == 0:
+        wt = scratch(("wt", w.data_ptr(), dx.data_ptr()), (Cin, k * k * Cout), w.dtype, w.device)   # resident-filter kernel wants K-major taps
         e.filter_transpose(w, wt, Cout, k * k, Cin)
-        if USE_HALO3:
+        if USE_HALO3 and pad == 1 and dy.shape[1] % 16 == 0:
             e.conv3x3_halo3_bf16(dy, wt, dx, None, False, bool(accumulate))
         else:
             e.conv3x3_halo_bf16(dy, wt, dx, None, False, bool(accumulate), None, 0, None)
@@ -197,7 +216,7 @@ def conv2d_dgrad_sm100(dy, w, dx, stride, pad, accumulate):
         e.conv_bf16(dy, w.reshape(Cout, T * Cin), dx, B, 1, dh, dw, pl, None, False, bool(accumulate), None,
                     [T - 1 - t for t in range(T)], T)
         return dx
-    wt = scratch(("wt", w.data_ptr()), (Cin, k * k * Cout), w.dtype, w.device)
+    wt = scratch(("wt", w.data_ptr(), dx.data_ptr()), (Cin, k * k * Cout), w.dtype, w.device)
     e.filter_transpose(w, wt, Cout, k * k, Cin)
     e.conv_bf16(dy, wt, dx, B, 1, dh, dw, pl, None, False, bool(accumulate), None, [], 0)
     return dx
@@ -228,7 +247,7 @@ def _conv2d_dgrad_s2(e, dy, w, dx, pad, accumulate):
         for pi, pj, taps, dh, dw in plan:
             e.conv_bf16_strided(dy, w.reshape(Cout, k * k * Cin), dx, dh, dw, None, False, bool(accumulate), taps, k * k, 1, 2, pi, pj)
         return dx
-    dx4 = scratch(("dx4", w.data_ptr()), (4 * B, Ho, Wo, Cin), dy.dtype, dy.device)
+    dx4 = scratch(("dx4", w.data_ptr(), dx.data_ptr()), (4 * B, Ho, Wo, Cin), dy.dtype, dy.device)
     mask = 0
     for pi, pj, taps, dh, dw in plan:
         plane = pi * 2 + pj
@@ -237,7 +256,7 @@ def _conv2d_dgrad_s2(e, dy, w, dx, pad, accumulate):
             e.conv_bf16(dy, w.reshape(Cout, k * k * Cin), dx4[plane * B:(plane + 1) * B], B, 1, dh, dw, [0] * len(taps), None,
                         False, False, None, taps, k * k)
             continue
-        wt = scratch(("wt_s2", w.data_ptr(), plane), (Cin, len(taps) * Cout), w.dtype, w.device)
+        wt = scratch(("wt_s2", w.data_ptr(), dx.data_ptr(), plane), (Cin, len(taps) * Cout), w.dtype, w.device)
         e.filter_gather_transpose(w, wt, Cout, k * k, Cin, taps)
         e.conv_bf16(dy, wt, dx4[plane * B:(plane + 1) * B], B, 1, dh, dw, [0] * len(taps), None, False, False, None, [], 0)
     e.depth_to_space(dx4, dx, bool(accumulate), mask)
@@ -279,7 +298,7 @@ def conv2d_wgrad_sm100(x, dy, gw, gb, stride, pad, tag="fwd", zero=True):
     if strided:
         e.conv_wgrad_bf16_strided(dy, x, gw, cin_valid, [dy_ - pad for dy_ in range(k) for _ in range(k)],
                                   [dx_ - pad for _ in range(k) for dx_ in range(k)], 2)
-    elif USE_WGRAD_HALO and _halo_ok(k, stride, pad, Cin, H, W) and (Cout <= 64 or Cout % 128 == 0):
+    elif USE_WGRAD_HALO and _wgrad_halo_ok(k, stride, pad, Cin, H, W) and (Cout <= 64 or Cout % 128 == 0):
         e.conv_wgrad_halo_bf16(dy, x, gw, cin_valid)
     else:
         e.conv_wgrad_bf16(dy, x, gw, B, planes, cin_valid, dh, dw, pl)
@@ -525,7 +544,7 @@ def linear_bwd(x, dy, w, dx, dw, db, acc_dx, impl, zero=True):
             db.copy_(dyf.float().sum(0))
     if dx is not None:
         if sm:   # dx = dy @ W  ==  GEMM with the transposed weight as the K-major B operand
-            wt = scratch(("wt_lin", w.data_ptr()), (K, N), w.dtype, w.device)
+            wt = scratch(("wt_lin", w.data_ptr(), dx.data_ptr()), (K, N), w.dtype, w.device)   # per consumer: trainers in flight may share w (broadcast buffer)
             _ext().filter_transpose(w, wt, N, 1, K)
             _ext().gemm_bf16(dy.contiguous(), wt, dx, None, False, bool(acc_dx), None)
             return

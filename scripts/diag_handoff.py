@@ -15,7 +15,7 @@ model = sys.argv[2] if len(sys.argv) > 2 else "cnn_mnist"
 
 def run(fused):
     args = make_args(data="fmnist" if model != "resnet18" else "cifar10", model=model, num_agents=3, local_ep=1, bs=64, synthetic=192,
-                     synthetic_val=64, log_dir="", device="cuda", seed=4, no_fused_handoff=not fused, agents_in_flight=nf)
+                     synthetic_val=64, log_dir="", device="cuda:0", seed=4, no_fused_handoff=not fused, agents_in_flight=nf)
     eng = FLEngine(args, verbose=False)
     snaps = []
     for r in range(1, 4):

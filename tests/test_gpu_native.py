@@ -343,6 +343,36 @@ def test_conv3x3_halo_kernel(B, H, W, Cout, acc):
     assert s_ok
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout,pad", [(32, 26, 26, 32, 64, 0), (16, 15, 15, 64, 128, 0), (9, 13, 21, 64, 64, 0), (8, 24, 24, 64, 64, 1)])
+def test_halo_conv_valid_and_full_padding_any_size(B, H, W, Cin, Cout, pad):
+    """The halo-reuse kernel beyond 'same' convs on whole tiles: valid convs (reference CNN_MNIST conv2 26x26x32 -> 24x24x64, CNN_CIFAR
+    conv2 15x15x64 -> 13x13x128, src/models.py:15,37), their data gradients (a FULL conv, pad 2) and sizes that are not multiples of the
+    16 x 8 tile (masked pixels, zero-filled halo).  Through the public wrappers, which also pad 32 -> 64 channels; vs fp32 conv2d."""
+    torch.manual_seed(B + H + Cout)
+    x = torch.randn(B, H, W, Cin, device=DEV).to(BF)
+    w = (torch.randn(Cout, 3, 3, Cin, device=DEV) / (9 * Cin) ** 0.5).to(BF)
+    bias = torch.randn(Cout, device=DEV) * 0.1
+    Ho, Wo = H + 2 * pad - 2, W + 2 * pad - 2
+    dy = torch.randn(B, Ho, Wo, Cout, device=DEV).to(BF)
+    xn = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    ref = F.conv2d(xn, w.float().permute(0, 3, 1, 2), bias, 1, pad)
+    ref.backward(dy.float().permute(0, 3, 1, 2))
+    ops.reset_fallbacks()
+    before = ops.launch_calls()
+    y = torch.full((B, Ho, Wo, Cout), 3.0, device=DEV, dtype=BF)
+    ops.conv2d_fwd_sm100(x, w, bias, y, 1, pad, True, None, tag=("halo_any", B, H))
+    assert ops.nn._halo_ok(3, 1, pad, 64, H, W)
+    assert _rel(y, F.relu(ref).detach().permute(0, 2, 3, 1)) < 1e-2 and _rms_rel(y, F.relu(ref).detach().permute(0, 2, 3, 1)) < 1e-2
+    base = torch.randn(B, H, W, Cin, device=DEV).to(BF)
+    dx0, dx1 = torch.full_like(base, 7.0), base.clone()
+    ops.conv2d_dgrad_sm100(dy, w, dx0, 1, pad, False)
+    ops.conv2d_dgrad_sm100(dy, w, dx1, 1, pad, True)
+    g = xn.grad.permute(0, 2, 3, 1)
+    assert _rel(dx0, g) < 1e-2 and _rms_rel(dx0, g) < 1e-2, (_rel(dx0, g), _rms_rel(dx0, g))
+    assert _rel(dx1, g + base.float()) < 1.5e-2
+    assert ops.launch_calls() > before and not ops.fallback_calls()
+
+
 def test_streaming_mode_after_resident_rounds_uses_valid_indices():
     """Regression: switching to per-round input streaming (compact per-agent shards) after rounds on the resident dataset must
     not replay graph warm-ups with the old dataset's (out-of-range) sample indices."""

@@ -92,8 +92,11 @@ class FakeExt:
 
     def conv3x3_halo_bf16(self, x, w, out, bias, relu, accumulate, stats, bo_mode, dbg):
         self.calls.append("conv3x3_halo_bf16")
-        dh = [d - 1 for d in range(3) for _ in range(3)]
-        dw = [d - 1 for _ in range(3) for d in range(3)]
+        pad = (out.shape[1] - x.shape[1] + 2) // 2                       # valid / same / full (conv_halo.cu launcher contract)
+        assert pad in (0, 1, 2) and out.shape[1] == x.shape[1] + 2 * pad - 2 and out.shape[2] == x.shape[2] + 2 * pad - 2
+        assert x.shape[3] == 64 and (stats is None or (out.shape[1] % 16 == 0 and out.shape[2] % 8 == 0))
+        dh = [d - pad for d in range(3) for _ in range(3)]
+        dw = [d - pad for _ in range(3) for d in range(3)]
         self._conv(x, w, out, x.shape[0], dh, dw, [0] * 9, bias, relu, accumulate, [], 0, 1, 1, 0, 0)
 
     def conv3x3_halo3_bf16(self, x, w, out, bias, relu, accumulate):
@@ -238,6 +241,7 @@ def _reference(x, w, bias, dy, s, p):
 CASES = [  # B, H, W, Cin, Cout, k, stride, pad
     (2, 8, 8, 64, 128, 3, 2, 1), (2, 8, 8, 64, 128, 1, 2, 0), (3, 4, 8, 128, 64, 3, 2, 1), (2, 16, 8, 64, 64, 3, 1, 1), (2, 6, 6, 64, 128, 3, 1, 0),
     (2, 8, 8, 128, 128, 3, 1, 1), (2, 8, 8, 3, 64, 3, 1, 1), (2, 10, 10, 1, 32, 3, 1, 0), (2, 8, 8, 128, 64, 1, 1, 0),
+    (2, 26, 26, 32, 64, 3, 1, 0), (2, 15, 15, 64, 128, 3, 1, 0),          # valid convs of the reference CNNs: halo kernel, pad 0 / full dgrad
 ]
 
 
@@ -280,8 +284,11 @@ def test_conv_wrappers_hand_the_kernels_the_right_problem(fake, monkeypatch, mod
         assert "space_to_depth" in fake.calls
     if mode == "stem" and Cin * k * k <= 64 and s == 1:
         assert fake.calls.count("im2col_small") == 1 and "stem_gemm_bf16" in fake.calls and "linear_wgrad_bf16" in fake.calls
-    if mode == "halo3" and nn._halo_ok(k, s, p, Cin, H, W):
+    if mode == "halo3" and nn._halo_ok(k, s, p, Cin, H, W) and p == 1 and H % 16 == 0:
         assert "conv3x3_halo3_bf16" in fake.calls and "conv3x3_halo_bf16" not in fake.calls
+    if mode == "default" and (H, p) in ((26, 0), (15, 0)):
+        # forward through the halo kernel; the data gradient too when ITS input (dy) has 64 channels
+        assert fake.calls.count("conv3x3_halo_bf16") == (3 if Cout == 64 else 1) and ("conv_bf16" in fake.calls) == (Cout != 64)
 
 
 def test_shared_parity_copy_is_made_once_per_forward(fake):
