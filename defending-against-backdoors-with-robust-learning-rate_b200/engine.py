@@ -101,7 +101,10 @@ class FLEngine:
         if n_flight <= 0:
             # auto: the small reference CNNs (~1 M parameters) are launch / latency bound at batch 256 -- two agents in flight fill the GPU
             # (FMNIST CNN, 10 agents, one B200: 160 -> 120 ms per round); the large models already fill it with one
-            n_flight = 2 if (dev.type == "cuda" and self.layout.n_params < 4_000_000) else 1
+            # Native trainer only: its step is a fixed kernel sequence on explicit streams.  The autograd trainer drives cuDNN from
+            # PyTorch's backward threads; two of those capturing / replaying graphs on two streams is not a combination we turn on
+            # by default (ask for it with --agents_in_flight N).
+            n_flight = 2 if (dev.type == "cuda" and self.layout.n_params < 4_000_000 and self.trainer.name == "native") else 1
         n_flight = min(max(1, n_flight), max_slots)
         self.trainers = [self.trainer] + [make_trainer(args.trainer, self.layout, args, dev, max_shard) for _ in range(n_flight - 1)]
         # (on CPU the extra trainers are still used round-robin -- same bookkeeping, no overlap)

@@ -84,7 +84,7 @@ umma_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         if (p.tma_store) prefetch_tmap(&tmC);
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&tail->full[s], p.split_prod ? 2 : 1); mbar_init(&tail->empty[s], 1); }
+        for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&tail->full[s], (p.split_prod || p.b_src) ? 2 : 1); mbar_init(&tail->empty[s], 1); }
         mbar_init(&tail->tmem_full, 1);
         fence_barrier_init();
     }
@@ -113,8 +113,14 @@ umma_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (warp == 0) {
         // ================================ TMA producer =====================================================================
         if (p.b_src) {
-            // stem GEMM (one k-block): the whole warp gathers the B tile from the un-padded filter.  First acquire the broadcast-ready
-            // words of the slices that hold it: the filter may still be in flight from the other GPUs' aggregation kernels.
+            // stem GEMM (ONE k-block, mode 0): the A tile is requested first, then -- while it is in flight -- the whole warp builds the
+            // B tile from the un-padded filter; full[0] takes two arrivals (the TMA transaction and this warp).
+            if (lane == 0) {
+                mbar_expect_tx(&tail->full[0], Cfg::kABytes);
+                tma_load_2d(&tmA, &tail->full[0], smem, 0, tile_m * BM);
+            }
+            // acquire the broadcast-ready words of the slices that hold the filter: it may still be in flight from the other GPUs'
+            // aggregation kernels
             if (p.wait_flags) {
                 const uint32_t epoch = *p.wait_epoch;
                 for (int r = p.wait_lo + lane; r <= p.wait_hi; r += 32)
@@ -122,21 +128,34 @@ umma_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 __syncwarp();
             }
             uint8_t* sb0 = smem + Cfg::kABytes;                      // stage 0
-            for (int idx = lane; idx < BN * 8; idx += 32) {
-                const int r = idx >> 3, c = idx & 7, n = tile_n * BN + r;
-                uint32_t h[8];
+            // zero the tile (K padding and rows beyond N), then scatter the valid elements: consecutive lanes read consecutive filter
+            // elements (coalesced, 8 independent loads in flight per lane) and store them at their 128-byte-swizzled position:
+            // 16-byte chunk c of row r lives at chunk (c ^ (r & 7)) of that row
+            for (int i = lane; i < BN * 8; i += 32) *reinterpret_cast<uint4*>(sb0 + i * 16) = make_uint4(0, 0, 0, 0);
+            __syncwarp();
+            const int rows = min(BN, p.N - tile_n * BN), total = rows * p.b_kvalid;
+            const __nv_bfloat16* src = p.b_src + (size_t)tile_n * BN * p.b_ld;
+            for (int e0 = 0; e0 < total; e0 += 32 * 8) {
+                unsigned short v[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const int col = c * 8 + j;
-                    h[j] = (n < p.N && col < p.b_kvalid) ? (uint32_t)__bfloat16_as_ushort(p.b_src[(size_t)n * p.b_ld + col]) : 0u;
+                    const int e = e0 + j * 32 + lane;
+                    const int r = e / p.b_kvalid, col = e - r * p.b_kvalid;
+                    v[j] = e < total ? __bfloat16_as_ushort(src[(size_t)r * p.b_ld + col]) : (unsigned short)0;
                 }
-                // 128-byte swizzle of a K-major tile: 16-byte chunk c of row r lives at chunk (c ^ (r & 7)) of that row
-                *reinterpret_cast<uint4*>(sb0 + r * 128 + ((c ^ (r & 7)) << 4)) =
-                    make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int e = e0 + j * 32 + lane;
+                    if (e < total) {
+                        const int r = e / p.b_kvalid, col = e - r * p.b_kvalid;
+                        *reinterpret_cast<unsigned short*>(sb0 + r * 128 + (((col >> 3) ^ (r & 7)) << 4) + (col & 7) * 2) = v[j];
+                    }
+                }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes above -> tensor-core (async proxy) reads
             __syncwarp();
-        }
+            if (lane == 0) mbar_arrive(&tail->full[0]);
+        } else
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;

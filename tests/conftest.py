@@ -16,6 +16,12 @@ def pytest_configure(config):
 def pytest_collection_modifyitems(config, items):
     import torch
     if torch.cuda.is_available():
+        # a GPU test that deadlocks (spin-wait protocols, graph capture) must fail with a stack dump, not stall the whole suite:
+        # pytest-timeout's "thread" method also fires while the main thread sits inside a CUDA synchronise
+        if config.pluginmanager.hasplugin("timeout"):
+            for it in items:
+                if "gpu" in it.keywords and it.get_closest_marker("timeout") is None:
+                    it.add_marker(pytest.mark.timeout(300, method="thread"))
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for it in items:
