@@ -21,6 +21,7 @@
 
 #include "common.cuh"
 #include "gemm.h"
+#include "stem_gather.cuh"
 #include "umma.cuh"
 
 namespace rlr {
@@ -119,41 +120,7 @@ umma_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 mbar_expect_tx(&tail->full[0], Cfg::kABytes);
                 tma_load_2d(&tmA, &tail->full[0], smem, 0, tile_m * BM);
             }
-            // acquire the broadcast-ready words of the slices that hold the filter: it may still be in flight from the other GPUs'
-            // aggregation kernels
-            if (p.wait_flags) {
-                const uint32_t epoch = *p.wait_epoch;
-                for (int r = p.wait_lo + lane; r <= p.wait_hi; r += 32)
-                    while ((int32_t)(ld_acquire_sys(p.wait_flags + r) - epoch) < 0) { __nanosleep(32); }
-                __syncwarp();
-            }
-            uint8_t* sb0 = smem + Cfg::kABytes;                      // stage 0
-            // zero the tile (K padding and rows beyond N), then scatter the valid elements: consecutive lanes read consecutive filter
-            // elements (coalesced, 8 independent loads in flight per lane) and store them at their 128-byte-swizzled position:
-            // 16-byte chunk c of row r lives at chunk (c ^ (r & 7)) of that row
-            for (int i = lane; i < BN * 8; i += 32) *reinterpret_cast<uint4*>(sb0 + i * 16) = make_uint4(0, 0, 0, 0);
-            __syncwarp();
-            const int rows = min(BN, p.N - tile_n * BN), total = rows * p.b_kvalid;
-            const __nv_bfloat16* src = p.b_src + (size_t)tile_n * BN * p.b_ld;
-            for (int e0 = 0; e0 < total; e0 += 32 * 8) {
-                unsigned short v[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int e = e0 + j * 32 + lane;
-                    const int r = e / p.b_kvalid, col = e - r * p.b_kvalid;
-                    v[j] = e < total ? __bfloat16_as_ushort(src[(size_t)r * p.b_ld + col]) : (unsigned short)0;
-                }
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int e = e0 + j * 32 + lane;
-                    if (e < total) {
-                        const int r = e / p.b_kvalid, col = e - r * p.b_kvalid;
-                        *reinterpret_cast<unsigned short*>(sb0 + r * 128 + (((col >> 3) ^ (r & 7)) << 4) + (col & 7) * 2) = v[j];
-                    }
-                }
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes above -> tensor-core (async proxy) reads
-            __syncwarp();
+            stem_gather_b(p, smem + Cfg::kABytes, BN, tile_n, lane);               // stage 0's B slot
             if (lane == 0) mbar_arrive(&tail->full[0]);
         } else
         if (lane == 0) {
@@ -531,6 +498,13 @@ static cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, con
         p.tma_store = 1;
     if (g_split_prod < 0) { const char* e = getenv("RLR_SPLIT_PRODUCER"); g_split_prod = (e && atoi(e) == 0) ? 0 : 1; }   // default on: -2.2 % per round (profiles/r2_step_ab.md)
     p.split_prod = (g_split_prod && !p.b_src) ? 1 : 0;
+    if (p.b_src && !p.stats && p.N <= BN) {
+        // stem GEMM: ONE k-block per output tile, so a one-tile CTA is all fixed cost (set-up, the filter gather, a lone TMA round trip).
+        // The persistent kernel builds the B tile once per SM, streams the A tiles through its ring and overlaps every tile's epilogue
+        // with the next tile's MMAs (double-buffered TMEM).  RLR_STEM_PERSISTENT=0 restores the one-tile-per-CTA launch.
+        static const int stem_persistent = [] { const char* e = getenv("RLR_STEM_PERSISTENT"); return (e && atoi(e) == 0) ? 0 : 1; }();
+        if (stem_persistent && m_tiles >= 2 * sm_count()) return launch_persistent_bn<BN>(tmA, tmB, p, m_tiles, sm_count(), st);
+    }
     if (!p.stats && !p.b_src && persistent_sms() > 0 && m_tiles * ((p.N + BN - 1) / BN) > persistent_sms())
         return launch_persistent_bn<BN>(tmA, tmB, p, m_tiles, persistent_sms(), st);
     if (!p.stats && conv_occ3() >= (BN == 64 ? 1 : 2)) return launch_bn_occ3<BN>(tmA, tmB, tmC, p, m_tiles, st);

@@ -10,6 +10,7 @@
 
 #include "common.cuh"
 #include "gemm.h"
+#include "stem_gather.cuh"
 #include "umma.cuh"
 
 namespace rlr {
@@ -74,6 +75,9 @@ umma_conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const 
     };
 
     if (warp == 0) {
+        // stem GEMM (b_src: one k-block, one n-tile): the B tile is built ONCE per CTA by this warp in the B slot of stage 0 (no stage ever
+        // loads a B tile in this mode, so the slot is never overwritten) and every tile's MMAs read it there; per tile only A is fetched
+        if (p.b_src) stem_gather_b(p, smem + Cfg::kABytes, BN, 0, lane);
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
@@ -84,12 +88,14 @@ umma_conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const 
                     mbar_wait(&sh->empty[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * Cfg::kStageBytes;
                     uint8_t* sb = sa + Cfg::kABytes;
-                    mbar_expect_tx(&sh->full[stage], Cfg::kStageBytes);
+                    mbar_expect_tx(&sh->full[stage], p.b_src ? Cfg::kABytes : Cfg::kStageBytes);
                     const int tap = p.mode == 1 ? kb / p.cblocks : 0, cb = p.mode == 1 ? kb - tap * p.cblocks : 0;
                     if (p.mode == 1) tma_load_4d(&tmA, &sh->full[stage], sa, cb * PBK, w0 * p.in_stride + p.dw[tap], h0 * p.in_stride + p.dh[tap],
                                                 n0 + p.dn[tap]);
                     else tma_load_2d(&tmA, &sh->full[stage], sa, kb * PBK, tile_m * PBM);
-                    if (kBMN) {
+                    if (p.b_src) {
+                        // resident B tile (above)
+                    } else if (kBMN) {
                         for (int g = 0; g < BN / 64; ++g)
                             tma_load_2d(&tmB, &sh->full[stage], sb + g * 8192, p.wtap[tap] * p.wcols + tile_n * BN + g * 64, cb * PBK);
                     } else {
@@ -112,7 +118,7 @@ umma_conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const 
                     mbar_wait(&sh->full[stage], phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-                    const uint32_t sb = sa + Cfg::kABytes;
+                    const uint32_t sb = p.b_src ? smem_u32(smem + Cfg::kABytes) : sa + Cfg::kABytes;
 #pragma unroll
                     for (int k = 0; k < PBK / 16; ++k) {
                         const uint64_t da = smem_desc_sw128(sa + k * 32, 16, 1024);

@@ -439,10 +439,12 @@ def test_persistent_conv_matches_default(B, H, W, Cin, Cout, k, s, p):
             assert torch.equal(a, b), mode
 
 
-@pytest.mark.parametrize("N,kvalid,M,relu", [(64, 27, 1000, True), (32, 9, 300, False), (128, 27, 4096, True), (64, 64, 129, False)])
+@pytest.mark.parametrize("N,kvalid,M,relu", [(64, 27, 1000, True), (32, 9, 300, False), (128, 27, 4096, True), (64, 64, 129, False),
+                                             (64, 27, 65536 + 77, True), (32, 9, 173056, True), (128, 27, 40000, False)])   # persistent path (>= 2 tiles per SM)
 def test_stem_gemm_gathers_unpadded_filter(N, kvalid, M, relu):
     """Stem convolution as one 64-deep tcgen05 GEMM whose B tile is gathered + zero-padded + swizzled by the producer warp from the
-    UN-padded filter (gemm.cu b_src path; the same path reads the multicast broadcast buffer behind ready flags)."""
+    UN-padded filter (stem_gather.cuh; the same path reads the multicast broadcast buffer behind ready flags).  Small M: one tile per
+    CTA (gemm.cu); from two tiles per SM upwards: the persistent kernel (gemm_persistent.cu) that builds the B tile once per SM."""
     torch.manual_seed(N + kvalid + M)
     A = torch.zeros(M, 64, device=DEV, dtype=BF)
     A[:, :kvalid] = torch.randn(M, kvalid, device=DEV).to(BF)
