@@ -105,6 +105,12 @@ class FLEngine:
             # PyTorch's backward threads; two of those capturing / replaying graphs on two streams is not a combination we turn on
             # by default (ask for it with --agents_in_flight N).
             n_flight = 2 if (dev.type == "cuda" and self.layout.n_params < 4_000_000 and self.trainer.name == "native") else 1
+        if n_flight > 1 and dev.type == "cuda" and self.trainer.name != "native":
+            # measured (scripts/stress_inflight.py torch 2): two autograd trainers replaying cuDNN / cuBLAS graphs on two streams dead-lock
+            # the device within a few rounds (library kernels whose CTAs wait for each other while the other graph holds the SMs)
+            if ctx.is_main:
+                print(f"[engine] --agents_in_flight {n_flight} needs the native trainer; the {self.trainer.name} trainer trains one agent at a time")
+            n_flight = 1
         n_flight = min(max(1, n_flight), max_slots)
         self.trainers = [self.trainer] + [make_trainer(args.trainer, self.layout, args, dev, max_shard) for _ in range(n_flight - 1)]
         # (on CPU the extra trainers are still used round-robin -- same bookkeeping, no overlap)
