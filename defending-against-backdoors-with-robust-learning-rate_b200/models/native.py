@@ -40,6 +40,8 @@ ACT = torch.bfloat16   # default activation / GEMM-operand dtype on GPU (tests m
 # Philox keep-mask, the backward recomputes it (pool) or reads it off the output together with the ReLU mask (linear).  RLR_FUSE_DROPOUT=0
 # restores the stand-alone dropout kernels.
 FUSE_DROPOUT = bool(int(os.environ.get("RLR_FUSE_DROPOUT", "1")))
+# ReLU of a conv whose only consumer is a max-pool: back-propagated inside the pooling backward kernel (no relu_bwd pass over the un-pooled tensor)
+FUSE_RELU_POOL = bool(int(os.environ.get("RLR_FUSE_RELU_POOL", "1")))
 FWD_SLOTS = BWD_SLOTS = max(1, int(os.environ.get("RLR_BN_SLOTS", "1")))
 WGRAD_OVERLAP = bool(int(os.environ.get("RLR_WGRAD_OVERLAP", "1")))
 
@@ -214,6 +216,16 @@ class NativeNet:
                 plan.append(op)
             else:
                 raise NotImplementedError(nd.op)
+        # ReLU fused into a conv's epilogue and consumed ONLY by a max-pool: its backward rides on the pooling backward (the arg-max
+        # is positive iff the pooled value is) instead of a relu_bwd pass over the un-pooled tensor
+        for op in plan:
+            if op.kind != "maxpool":
+                continue
+            prod = next((q for q in plan if q.y == op.x), None)
+            users = [q for q in plan if q.x == op.x or q.res == op.x]
+            if prod is not None and prod.kind == "conv" and prod.relu and len(users) == 1 and FUSE_RELU_POOL:
+                op.saved["relu_bwd_here"] = True
+                prod.saved["relu_bwd_fused"] = True
         self.plan = plan
         self.alias = alias
         self.out_tid = alias.get(tid("x"), tid("x"))
@@ -372,7 +384,7 @@ class NativeNet:
     def _bwd_conv(self, op, B):
         a = op.attrs
         x, y, dy = self.T(op.x, B), self.T(op.y, B), self.G(op.y, B)
-        if op.relu:  # dy <- dy * (y > 0), in place (y is the post-ReLU output)
+        if op.relu and not op.saved.get("relu_bwd_fused"):  # dy <- dy * (y > 0), in place (y is the post-ReLU output)
             ops.relu_bwd_(dy, y, self.impl["bn"])
         name = op.name + ".weight"
         gw, gb = self.pg[name], self.pg.get(op.name + ".bias")
@@ -448,7 +460,8 @@ class NativeNet:
     def _bwd_maxpool(self, op, B):
         drop = self._drop(op, op.saved.get("drop_on", False))
         mask = op.saved["dmask"][:B] if (drop is not None and "dmask" in op.saved) else None
-        ops.maxpool2_bwd(self.G(op.y, B), op.saved["idx"][:B], self.G(op.x, B), self.impl["pool"], drop, mask)
+        ops.maxpool2_bwd(self.G(op.y, B), op.saved["idx"][:B], self.G(op.x, B), self.impl["pool"], drop, mask,
+                         relu_out=self.T(op.y, B) if op.saved.get("relu_bwd_here") else None)
 
     def _fwd_avgpool(self, op, B, train):
         ops.avgpool_fwd(self.T(op.x, B), self.T(op.y, B), self.impl["pool"])

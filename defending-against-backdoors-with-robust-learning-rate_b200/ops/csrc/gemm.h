@@ -123,7 +123,7 @@ cudaError_t launch_relu_bwd(__nv_bfloat16* dy, const __nv_bfloat16* y, long long
 cudaError_t launch_maxpool2_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, uint8_t* idx, int B, int H, int W, int C, cudaStream_t st,
                                 float drop_p = 0.f, uint64_t seed = 0, const long long* step = nullptr, uint64_t stream = 0);
 cudaError_t launch_maxpool2_bwd(const __nv_bfloat16* dy, const uint8_t* idx, __nv_bfloat16* dx, int B, int H, int W, int C, cudaStream_t st,
-                                float drop_p = 0.f, uint64_t seed = 0, const long long* step = nullptr, uint64_t stream = 0);
+                                float drop_p, uint64_t seed, const long long* step, uint64_t stream, const __nv_bfloat16* zmask);
 cudaError_t launch_avgpool_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, int B, int HW, int C, cudaStream_t st);
 cudaError_t launch_avgpool_bwd(const __nv_bfloat16* dy, __nv_bfloat16* dx, int B, int HW, int C, cudaStream_t st);
 cudaError_t launch_dropout_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, uint8_t* mask, long long n, float p, uint64_t seed,

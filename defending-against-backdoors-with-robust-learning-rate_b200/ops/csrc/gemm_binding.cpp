@@ -255,11 +255,16 @@ void maxpool2_fwd(at::Tensor x, at::Tensor y, at::Tensor idx, double drop_p, int
     check(rlr::launch_maxpool2_fwd(bf(x), bfm(y), (uint8_t*)idx.data_ptr(), x.size(0), x.size(1), x.size(2), x.size(3), cur_stream(),
                                    (float)drop_p, d.seed, d.step, d.stream), "maxpool2_fwd");
 }
-void maxpool2_bwd(at::Tensor dy, at::Tensor idx, at::Tensor dx, double drop_p, int64_t drop_seed, c10::optional<at::Tensor> drop_step, int64_t drop_stream) {
+// relu_out (optional) = the pooled forward output: back-propagates the producer's fused ReLU in the same pass (see norm.cu)
+void maxpool2_bwd(at::Tensor dy, at::Tensor idx, at::Tensor dx, double drop_p, int64_t drop_seed, c10::optional<at::Tensor> drop_step, int64_t drop_stream,
+                  c10::optional<at::Tensor> relu_out) {
     c10::cuda::CUDAGuard g(dx.device());
     const rlr::DropSpec d = drop_spec(drop_p, drop_seed, drop_step, drop_stream);
+    const bool zm = relu_out.has_value() && relu_out->defined();
+    TORCH_CHECK(!zm || (relu_out->scalar_type() == at::kBFloat16 && relu_out->is_contiguous() && relu_out->numel() == dy.numel()), "relu_out must match dy");
+    TORCH_CHECK(dy.is_contiguous() && dx.is_contiguous() && idx.is_contiguous() && dy.size(1) == dx.size(1) / 2 && dy.size(2) == dx.size(2) / 2);
     check(rlr::launch_maxpool2_bwd(bf(dy), (const uint8_t*)idx.data_ptr(), bfm(dx), dx.size(0), dx.size(1), dx.size(2), dx.size(3), cur_stream(),
-                                   (float)drop_p, d.seed, d.step, d.stream), "maxpool2_bwd");
+                                   (float)drop_p, d.seed, d.step, d.stream, zm ? bf(*relu_out) : nullptr), "maxpool2_bwd");
 }
 void avgpool_fwd(at::Tensor x, at::Tensor y) {
     c10::cuda::CUDAGuard g(x.device());
@@ -363,7 +368,7 @@ void register_gemm_bindings(py::module_& m) {
     m.def("maxpool2_fwd", &maxpool2_fwd, py::arg("x"), py::arg("y"), py::arg("idx"), py::arg("drop_p") = 0.0, py::arg("drop_seed") = 0,
           py::arg("drop_step") = py::none(), py::arg("drop_stream") = 0);
     m.def("maxpool2_bwd", &maxpool2_bwd, py::arg("dy"), py::arg("idx"), py::arg("dx"), py::arg("drop_p") = 0.0, py::arg("drop_seed") = 0,
-          py::arg("drop_step") = py::none(), py::arg("drop_stream") = 0);
+          py::arg("drop_step") = py::none(), py::arg("drop_stream") = 0, py::arg("relu_out") = py::none());
     m.def("avgpool_fwd", &avgpool_fwd);
     m.def("avgpool_bwd", &avgpool_bwd);
     m.def("dropout_fwd", &dropout_fwd);

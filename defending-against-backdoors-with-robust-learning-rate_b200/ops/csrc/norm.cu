@@ -400,37 +400,57 @@ __global__ void __launch_bounds__(256) maxpool2_fwd_kernel(const __nv_bfloat16* 
         *reinterpret_cast<uint2*>(idx + o) = pk;
     }
 }
+// One thread per POOLED element x 8 channels: reads dy / the arg-max index (/ the pooled output) once and writes the four input pixels of its
+// window (zeros except at the arg-max); rows / columns of an odd-sized input that no window covers are zeroed by the last windows.
+// ``zmask`` (optional) = the pooled forward output: the producer's fused ReLU is back-propagated here -- the arg-max element is positive iff
+// the pooled value is (ReLU'(0) = 0, like torch), so the separate relu_bwd pass over the 4x larger tensor disappears.
 __global__ void __launch_bounds__(256) maxpool2_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx,
-                                                             __nv_bfloat16* __restrict__ dx, int B, int H, int W, int C, DropSpec drop) {
+                                                             __nv_bfloat16* __restrict__ dx, const __nv_bfloat16* __restrict__ zmask,
+                                                             int B, int H, int W, int C, DropSpec drop) {
     const int Ho = H / 2, Wo = W / 2, cg_n = C / 8;
-    const long long total = (long long)B * H * W * cg_n;
+    const long long total = (long long)B * Ho * Wo * cg_n;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
         const int cg = (int)(t % cg_n);
         long long r = t / cg_n;
-        const int w = (int)(r % W); r /= W;
-        const int h = (int)(r % H);
-        const int b = (int)(r / H);
-        bf8 o;
+        const int wo = (int)(r % Wo); r /= Wo;
+        const int ho = (int)(r % Ho);
+        const int b = (int)(r / Ho);
+        const size_t src = (size_t)t * 8;                       // == (((b * Ho + ho) * Wo + wo) * C + cg * 8
+        bf8 g = load8(dy + src);
+        if (drop.thr) {     // gradient of the fused dropout: the forward's keep-mask of this pooled element, recomputed
+            const uint32_t keep = dropout_keep8(drop, (long long)(src >> 3));
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o.v[i] = 0.f;
-        const int ho = h >> 1, wo = w >> 1;
-        if (ho < Ho && wo < Wo) {
-            const size_t src = (((size_t)b * Ho + ho) * Wo + wo) * C + cg * 8;
-            bf8 g = load8(dy + src);
-            if (drop.thr) {     // gradient of the fused dropout: the forward's keep-mask of this pooled element, recomputed
-                const uint32_t keep = dropout_keep8(drop, (long long)(src >> 3));
+            for (int i = 0; i < 8; ++i) g.v[i] = (keep >> i & 1) ? g.v[i] * drop.scale : 0.f;
+        }
+        if (zmask) {
+            const bf8 z = load8(zmask + src);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) g.v[i] = (keep >> i & 1) ? g.v[i] * drop.scale : 0.f;
-            }
-            const uint2 pk = *reinterpret_cast<const uint2*>(idx + src);
-            const int me = (h & 1) * 2 + (w & 1);
+            for (int i = 0; i < 8; ++i) g.v[i] = z.v[i] > 0.f ? g.v[i] : 0.f;
+        }
+        const uint2 pk = *reinterpret_cast<const uint2*>(idx + src);
+        bf8 zero;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) zero.v[i] = 0.f;
+#pragma unroll
+        for (int me = 0; me < 4; ++me) {
+            bf8 o;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int k = ((i < 4 ? pk.x : pk.y) >> (8 * (i & 3))) & 0xff;
                 o.v[i] = (k == me) ? g.v[i] : 0.f;
             }
+            store8(dx + (((size_t)b * H + 2 * ho + (me >> 1)) * W + 2 * wo + (me & 1)) * C + cg * 8, o);
         }
-        store8(dx + (((size_t)b * H + h) * W + w) * C + cg * 8, o);
+        const bool last_w = (W & 1) && wo == Wo - 1, last_h = (H & 1) && ho == Ho - 1;
+        if (last_w) {
+            store8(dx + (((size_t)b * H + 2 * ho) * W + W - 1) * C + cg * 8, zero);
+            store8(dx + (((size_t)b * H + 2 * ho + 1) * W + W - 1) * C + cg * 8, zero);
+        }
+        if (last_h) {
+            store8(dx + (((size_t)b * H + H - 1) * W + 2 * wo) * C + cg * 8, zero);
+            store8(dx + (((size_t)b * H + H - 1) * W + 2 * wo + 1) * C + cg * 8, zero);
+            if (last_w) store8(dx + (((size_t)b * H + H - 1) * W + W - 1) * C + cg * 8, zero);
+        }
     }
 }
 static DropSpec make_drop(float p, uint64_t seed, const long long* step, uint64_t stream) {
@@ -446,10 +466,10 @@ cudaError_t launch_maxpool2_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, uint8_
     return cudaGetLastError();
 }
 cudaError_t launch_maxpool2_bwd(const __nv_bfloat16* dy, const uint8_t* idx, __nv_bfloat16* dx, int B, int H, int W, int C, cudaStream_t st, float drop_p,
-                                uint64_t seed, const long long* step, uint64_t stream) {
-    if (C % 8) return cudaErrorInvalidValue;
-    const long long total = (long long)B * H * W * (C / 8);
-    maxpool2_bwd_kernel<<<rows_grid(total, 256, 148, 8), 256, 0, st>>>(dy, idx, dx, B, H, W, C, make_drop(drop_p, seed, step, stream));
+                                uint64_t seed, const long long* step, uint64_t stream, const __nv_bfloat16* zmask) {
+    if (C % 8 || H < 2 || W < 2) return cudaErrorInvalidValue;
+    const long long total = (long long)B * (H / 2) * (W / 2) * (C / 8);
+    maxpool2_bwd_kernel<<<rows_grid(total, 256, 148, 8), 256, 0, st>>>(dy, idx, dx, zmask, B, H, W, C, make_drop(drop_p, seed, step, stream));
     return cudaGetLastError();
 }
 

@@ -423,15 +423,21 @@ def maxpool2_fwd(x, y, idx, impl, drop=None, mask=None):
     y.copy_(v); idx.copy_(i)
 
 
-def maxpool2_bwd(dy, idx, dx, impl, drop=None, mask=None):
+def maxpool2_bwd(dy, idx, dx, impl, drop=None, mask=None, relu_out=None):
+    """dx[B,H,W,C] = gradient of the 2x2 max-pool (zeros except at each window's arg-max).  ``drop`` = the dropout fused into the pooling
+    forward (mask recomputed); ``relu_out`` = the pooled forward output when the ReLU fused into the PRODUCER of the pooled tensor is
+    back-propagated here as well: the arg-max is positive iff the pooled value is, so no separate pass over the 4x larger tensor."""
     if impl == "sm100" and dx.shape[-1] % 8 == 0:
+        kw = dict(relu_out=relu_out.contiguous()) if relu_out is not None else {}
         if drop is not None:
-            _ext().maxpool2_bwd(dy, idx, dx, float(drop[0]), int(drop[1]), drop[2], int(drop[3]))
+            _ext().maxpool2_bwd(dy, idx, dx, float(drop[0]), int(drop[1]), drop[2], int(drop[3]), **kw)
         else:
-            _ext().maxpool2_bwd(dy, idx, dx)
+            _ext().maxpool2_bwd(dy, idx, dx, **kw)
         return
     if impl == "sm100":
         _fallback("maxpool2_bwd", f"C={dx.shape[-1]}")
+    if relu_out is not None:
+        dy = dy * (relu_out > 0).to(dy.dtype)
     B, H, W, C = dx.shape
     Ho, Wo = H // 2, W // 2
     dx.zero_()

@@ -195,6 +195,15 @@ def test_pool_dropout_s2d_transpose_linear_small():
             ry, rdx = y.clone(), dx.clone()
     ref = F.max_pool2d(x.float().permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1)
     assert torch.equal(y.float(), ref) and torch.equal(ry, y) and torch.equal(rdx, dx)
+    # producer's ReLU back-propagated inside the pooling backward: gradient only where the pooled output is positive; rows / columns of
+    # the odd-sized input that no window covers stay zero
+    z = (y.float() - 0.8).to(BF)
+    dz_a, dz_s = torch.full_like(x, 9.0), torch.full_like(x, 9.0)
+    ops.maxpool2_bwd(y, idx, dz_a, "aten", relu_out=z)
+    ops.maxpool2_bwd(y, idx, dz_s, "sm100", relu_out=z)
+    keep = (z > 0).repeat_interleave(2, 1).repeat_interleave(2, 2)
+    assert torch.equal(dz_a, dz_s) and torch.equal(dz_s[:, :12, :12], rdx[:, :12, :12] * keep) and float(dz_s[:, 12].abs().max()) == 0
+    assert 0.2 < float((z > 0).float().mean()) < 0.9
     a = torch.randn(7, 4, 4, 512, device=DEV).to(BF)
     p = torch.empty(7, 1, 1, 512, device=DEV, dtype=BF); ops.avgpool_fwd(a, p, "sm100")
     assert _rel(p, a.float().mean((1, 2), keepdim=True)) < 1e-2
