@@ -160,6 +160,12 @@ umma_conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
         int acc = 0;
         uint32_t acc_phase = 0;
         if (kStats) red[et] = 0.f;                                 // per-CTA statistics, flushed once at the end
+        // without statistics the same 512 bytes hold this n-tile's bias values: read once per CTA, not once per element and tile
+        const bool bias_smem = !kStats && p.bias != nullptr;
+        if (bias_smem) {
+            if (et < 64) red[et] = (col0 + et < p.N) ? p.bias[col0 + et] : 0.f;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             const int n = tile / tiles_per_img, r = tile - n * tiles_per_img;
             const int h0 = (r / p.tiles_w) * HL_TH, w0 = (r % p.tiles_w) * HL_TW;
@@ -190,7 +196,8 @@ umma_conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
 #pragma unroll
                 for (int j = 0; j < 32; j += 2) {
                     float a = __uint_as_float(v[j]), b = __uint_as_float(v[j + 1]);
-                    if (p.bias && col0 + c0 + j < p.N) { a += p.bias[col0 + c0 + j]; b += p.bias[col0 + c0 + j + 1]; }
+                    if (bias_smem) { a += red[c0 + j]; b += red[c0 + j + 1]; }
+                    else if (p.bias && col0 + c0 + j < p.N) { a += p.bias[col0 + c0 + j]; b += p.bias[col0 + c0 + j + 1]; }
                     if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
                     packed[j >> 1] = pack_bf16x2(a, b);
                     if (kStats) {   // statistics of the bf16-rounded values that BatchNorm will read back

@@ -44,7 +44,8 @@ struct TileCfg {
     static constexpr int kStagingBytes = BM * kPitch;
     static constexpr int kRingBytes = kStages * kStageBytes;
     static_assert(kStagingBytes + 2 * BN * 4 <= kRingBytes, "staging aliases the operand ring");
-    static constexpr int kSmemBytes = kRingBytes + 1024 /*align slack*/ + 1024 /*barriers, row index*/;
+    static constexpr int kTailBytes = BN == 128 ? 2048 : 1024;   // barriers, row index (640 B) + the tile's bias values (BN floats)
+    static constexpr int kSmemBytes = kRingBytes + 1024 /*align slack*/ + kTailBytes;
 };
 
 struct __align__(8) SharedTail {
@@ -55,6 +56,7 @@ struct __align__(8) SharedTail {
     uint32_t pad;
     int row_index[BM];   // global output row of each tile row, -1 = masked
 };
+static_assert(sizeof(SharedTail) <= 640, "the bias slice starts 640 bytes into the tail");
 
 template <int BN, bool kStats, bool kBMN, int kOcc = 2>
 __global__ void __launch_bounds__(kThreads, kOcc)
@@ -200,12 +202,21 @@ umma_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
             }
         }
+        // the tile's bias values go to shared memory while the main loop runs (128 dependent global loads per thread in the epilogue
+        // cost 2.4 us per launch, scripts/bench_small_gemm.py)
+        const int col0 = tile_n * BN;
+        const bool has_bias = !kBMN && p.bias != nullptr;   // data gradients (MN-major B) never carry a bias
+        if (has_bias) {
+            float* bw = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(tail) + 640);
+            for (int i = et; i < BN; i += kEpiThreads) bw[i] = (col0 + i < p.N) ? p.bias[col0 + i] : 0.f;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
         __syncwarp();
         mbar_wait(&tail->tmem_full, 0);
         tc_fence_after();
+        const float* bias_s = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(tail) + 640);
         if (dbg && et == 0) dbg[5] = (long long)gtimer();
         uint8_t* staging = smem;                         // operand ring is idle now: reuse it
-        const int col0 = tile_n * BN;
         float* red = reinterpret_cast<float*>(staging + Cfg::kStagingBytes);   // [2][BN] per-tile column sums
         const int gi_row = tail->row_index[row];
         const bool row_ok = gi_row >= 0;
@@ -233,7 +244,7 @@ umma_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll
                 for (int j = 0; j < 32; j += 2) {
                     float a = __uint_as_float(v[j]), b = __uint_as_float(v[j + 1]);
-                    if (p.bias && col0 + cc + j < p.N) { a += p.bias[col0 + cc + j]; b += p.bias[col0 + cc + j + 1]; }
+                    if (has_bias) { a += bias_s[cc + j]; b += bias_s[cc + j + 1]; }
                     if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
                     if (p.drop.thr) {   // fused dropout (linear layers): one Philox call per 8 output columns of this row
                         if ((j & 7) == 0) keep8 = dropout_keep8(p.drop, ((long long)(gi_row < 0 ? 0 : gi_row) * p.ldc + col0 + cc + j) >> 3);
@@ -624,6 +635,7 @@ cudaError_t launch_conv_bf16(const void* x, const void* w, void* out, int NB, in
     }
     if (wtap) {
         // data gradient on the un-transposed filter: w is the forward filter [K = Cin of this call][w_taps_total * Cout of this call]
+        if (bias) return cudaErrorInvalidValue;                 // the MN-major (data-gradient) kernels are compiled without the bias path
         p.b_mn = 1; p.wcols = Cout;
         for (int t = 0; t < ntaps; ++t) p.wtap[t] = wtap[t];
         const uint64_t cols = (uint64_t)w_taps_total * Cout;

@@ -28,7 +28,8 @@ struct PCfg {
     static constexpr int kPitch = BN * 2 + 16;
     static constexpr int kStagingBytes = PBM * kPitch;
     static constexpr int kRingBytes = kStages * kStageBytes;
-    static constexpr int kSmemBytes = kRingBytes + kStagingBytes + 1024 + 1024;
+    static constexpr int kTailBytes = BN == 128 ? 2048 : 1024;    // PShared (704 B) + the n-tile's bias values (BN floats)
+    static constexpr int kSmemBytes = kRingBytes + kStagingBytes + 1024 + kTailBytes;
 };
 
 struct __align__(8) PShared {
@@ -40,6 +41,7 @@ struct __align__(8) PShared {
     uint32_t pad;
     int row_index[PBM];
 };
+static_assert(sizeof(PShared) <= 704, "the bias slice starts 704 bytes into the tail");
 
 template <int BN, bool kBMN>
 __global__ void __launch_bounds__(PThreads, 1)
@@ -142,10 +144,18 @@ umma_conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const 
         constexpr int kIters = PBM * kChunks / 128;
         int acc = 0;
         uint32_t acc_phase = 0;
+        float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sh) + 704);
+        int bias_tile_n = -1;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             int tile_m, tile_n, n0, h0, w0;
             origin(tile, tile_m, tile_n, n0, h0, w0);
             const int col0 = tile_n * BN;
+            if (p.bias && tile_n != bias_tile_n) {   // (re)load this n-tile's bias values; consecutive tiles share the n-tile
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                for (int i = et; i < BN; i += 128) bias_s[i] = (col0 + i < p.N) ? p.bias[col0 + i] : 0.f;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                bias_tile_n = tile_n;
+            }
             {   // global output row of my tile row (-1 = masked); staging / row_index of the previous tile are free (end-of-tile barrier)
                 int gi;
                 if (p.mode == 1) {
@@ -169,7 +179,7 @@ umma_conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const 
 #pragma unroll
                 for (int j = 0; j < 32; j += 2) {
                     float a = __uint_as_float(v[j]), b = __uint_as_float(v[j + 1]);
-                    if (p.bias && col0 + c0 + j < p.N) { a += p.bias[col0 + c0 + j]; b += p.bias[col0 + c0 + j + 1]; }
+                    if (p.bias) { a += bias_s[c0 + j]; b += bias_s[c0 + j + 1]; }
                     if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
                     packed[j >> 1] = pack_bf16x2(a, b);
                 }
