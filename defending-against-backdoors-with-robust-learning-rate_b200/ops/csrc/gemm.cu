@@ -392,7 +392,7 @@ cudaError_t make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const u
 // gemm_persistent.cu (opt-in, RLR_PERSISTENT_CONV=1): one CTA per SM looping over tiles, double-buffered TMEM accumulators
 template <int BN>
 cudaError_t launch_persistent_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, int m_tiles, int num_sms,
-                                 cudaStream_t st);
+                                 cudaStream_t st, int occ = 1);
 
 // 0: two CTAs per SM for every tile | 1 (default, measured -1.4 % / round): three for the 64-wide tile | 2 (not yet measured): also
 // for the 128-wide tile (2-stage ring).  -1: take RLR_CONV_OCC3 from the environment on first use.
@@ -513,8 +513,10 @@ static cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, con
         // stem GEMM: ONE k-block per output tile, so a one-tile CTA is all fixed cost (set-up, the filter gather, a lone TMA round trip).
         // The persistent kernel builds the B tile once per SM, streams the A tiles through its ring and overlaps every tile's epilogue
         // with the next tile's MMAs (double-buffered TMEM).  RLR_STEM_PERSISTENT=0 restores the one-tile-per-CTA launch.
-        static const int stem_persistent = [] { const char* e = getenv("RLR_STEM_PERSISTENT"); return (e && atoi(e) == 0) ? 0 : 1; }();
-        if (stem_persistent && m_tiles >= 2 * sm_count()) return launch_persistent_bn<BN>(tmA, tmB, p, m_tiles, sm_count(), st);
+        // (RLR_STEM_PERSISTENT=1: one CTA per SM with the deep ring; default 2: two CTAs per SM, 3-stage rings -- the tiles are epilogue bound)
+        static const int stem_persistent = [] { const char* e = getenv("RLR_STEM_PERSISTENT"); return e ? atoi(e) : 2; }();
+        if (stem_persistent && m_tiles >= 2 * sm_count())
+            return launch_persistent_bn<BN>(tmA, tmB, p, m_tiles, sm_count(), st, stem_persistent == 2 ? 2 : 1);
     }
     if (!p.stats && !p.b_src && persistent_sms() > 0 && m_tiles * ((p.N + BN - 1) / BN) > persistent_sms())
         return launch_persistent_bn<BN>(tmA, tmB, p, m_tiles, persistent_sms(), st);

@@ -19,9 +19,11 @@ using namespace umma;
 
 constexpr int PBM = 128, PBK = 64, PThreads = 192;
 
-template <int BN>
+// kOcc = 1: one CTA per SM with a deep ring (7 x 24 KB / 5 x 32 KB).  kOcc = 2: two CTAs per SM with a 3-stage ring -- for the stem GEMM,
+// whose one-k-block tiles are EPILOGUE bound: two CTAs give the SM two epilogue warp-groups (and two TMA streams) to drain them.
+template <int BN, int kOcc = 1>
 struct PCfg {
-    static constexpr int kStages = BN == 64 ? 7 : 5;
+    static constexpr int kStages = kOcc == 2 ? 3 : (BN == 64 ? 7 : 5);
     static constexpr int kABytes = PBM * PBK * 2;
     static constexpr int kBBytes = BN * PBK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
@@ -43,11 +45,11 @@ struct __align__(8) PShared {
 };
 static_assert(sizeof(PShared) <= 704, "the bias slice starts 704 bytes into the tail");
 
-template <int BN, bool kBMN>
-__global__ void __launch_bounds__(PThreads, 1)
+template <int BN, bool kBMN, int kOcc = 1>
+__global__ void __launch_bounds__(PThreads, kOcc)
 umma_conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvGemmParams p,
                                  const int m_tiles, const int total_tiles) {
-    using Cfg = PCfg<BN>;
+    using Cfg = PCfg<BN, kOcc>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* staging = smem + Cfg::kRingBytes;
@@ -232,7 +234,20 @@ umma_conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const 
 
 template <int BN>
 cudaError_t launch_persistent_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, int m_tiles, int num_sms,
-                                 cudaStream_t st) {
+                                 cudaStream_t st, int occ) {
+    const int n_tiles = (p.N + BN - 1) / BN;
+    const int total = m_tiles * n_tiles;
+    if (occ == 2 && !p.b_mn) {
+        using Cfg = PCfg<BN, 2>;
+        static bool configured2 = false;
+        if (!configured2) {
+            RLR_CUDA_CHECK(cudaFuncSetAttribute(umma_conv_gemm_persistent_kernel<BN, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+            configured2 = true;
+        }
+        const int grid = total < 2 * num_sms ? total : 2 * num_sms;
+        umma_conv_gemm_persistent_kernel<BN, false, 2><<<grid, PThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p, m_tiles, total);
+        return cudaGetLastError();
+    }
     using Cfg = PCfg<BN>;
     static bool configured = false;
     if (!configured) {
@@ -240,14 +255,12 @@ cudaError_t launch_persistent_bn(const CUtensorMap& tmA, const CUtensorMap& tmB,
         RLR_CUDA_CHECK(cudaFuncSetAttribute(umma_conv_gemm_persistent_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         configured = true;
     }
-    const int n_tiles = (p.N + BN - 1) / BN;
-    const int total = m_tiles * n_tiles;
     const int grid = total < num_sms ? total : num_sms;
     if (p.b_mn) umma_conv_gemm_persistent_kernel<BN, true><<<grid, PThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p, m_tiles, total);
     else umma_conv_gemm_persistent_kernel<BN, false><<<grid, PThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p, m_tiles, total);
     return cudaGetLastError();
 }
-template cudaError_t launch_persistent_bn<64>(const CUtensorMap&, const CUtensorMap&, const ConvGemmParams&, int, int, cudaStream_t);
-template cudaError_t launch_persistent_bn<128>(const CUtensorMap&, const CUtensorMap&, const ConvGemmParams&, int, int, cudaStream_t);
+template cudaError_t launch_persistent_bn<64>(const CUtensorMap&, const CUtensorMap&, const ConvGemmParams&, int, int, cudaStream_t, int);
+template cudaError_t launch_persistent_bn<128>(const CUtensorMap&, const CUtensorMap&, const ConvGemmParams&, int, int, cudaStream_t, int);
 
 }  // namespace rlr
