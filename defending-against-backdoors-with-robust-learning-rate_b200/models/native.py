@@ -42,6 +42,8 @@ ACT = torch.bfloat16   # default activation / GEMM-operand dtype on GPU (tests m
 FUSE_DROPOUT = bool(int(os.environ.get("RLR_FUSE_DROPOUT", "1")))
 # ReLU of a conv whose only consumer is a max-pool: back-propagated inside the pooling backward kernel (no relu_bwd pass over the un-pooled tensor)
 FUSE_RELU_POOL = bool(int(os.environ.get("RLR_FUSE_RELU_POOL", "1")))
+# BatchNorm statistics from the conv epilogue where they are free (generic kernel, TMA-store epilogue: sums taken while the store drains)
+EPILOGUE_BN_STATS = bool(int(os.environ.get("RLR_EPILOGUE_BN_STATS", "1")))
 FWD_SLOTS = BWD_SLOTS = max(1, int(os.environ.get("RLR_BN_SLOTS", "1")))
 WGRAD_OVERLAP = bool(int(os.environ.get("RLR_WGRAD_OVERLAP", "1")))
 
@@ -359,13 +361,24 @@ class NativeNet:
             self._side = None
 
     # ---- conv ---------------------------------------------------------------------------------------------------
+    def _epilogue_stats_free(self, op):
+        """BatchNorm statistics in the conv epilogue cost nothing where the conv runs the generic kernel's TMA-store epilogue: the
+        column sums are taken from the staged tile while the TMA unit drains it (gemm.cu).  That is every stride-1 conv on whole
+        64-channel groups except the 64-channel 3x3 layers (halo kernel) -- ResNet-18: 9 of 20 BatchNorm inputs; the others keep the
+        streaming statistics pass."""
+        if not EPILOGUE_BN_STATS or self.impl["conv_fwd"] != "sm100":
+            return False
+        a = op.attrs
+        return a.get("stride", 1) == 1 and a["cin"] % 64 == 0 and a["cout"] % 64 == 0 and not (a["k"] == 3 and a["cin"] == 64)
+
     def _fwd_conv(self, op, B, train):
         a = op.attrs
         x, y = self.T(op.x, B), self.T(op.y, B)
         bias = self.pw.get(op.name + ".bias")
         # BatchNorm statistics: fused into the conv epilogue (FUSE_BN_STATS) or taken by one streaming pass over the conv output
         # while it is still L2-resident (default: measured cheaper than the in-epilogue reduction, profiles/r1c notes)
-        stats = op.saved.get("stats") if (train and op.saved.get("want_stats") and self.fuse_bn_stats) else None
+        stats = op.saved.get("stats") if (train and op.saved.get("want_stats") and (self.fuse_bn_stats or self._epilogue_stats_free(op))) else None
+        op.saved["stats_done"] = stats is not None
         if self.impl["conv_fwd"] == "sm100" and ops.conv_supported(op.in_shape, a, "fwd"):
             ops.conv2d_fwd_sm100(x, self.pwb[op.name + ".weight"], bias, y, a.get("stride", 1), a.get("pad", 0), op.relu, stats, tag=(id(self), op.name),
                                  zero_stats=False, s2d_epoch=self._epoch, wait=self.first_wait if (op is self.plan[0] and x.dim() == 2) else None)
@@ -430,7 +443,7 @@ class NativeNet:
         gamma, beta = self.pw[op.name + ".weight"], self.pw[op.name + ".bias"]
         rm, rv = self.pw[op.name + ".running_mean"], self.pw[op.name + ".running_var"]
         prod = op.saved["producer"]
-        stats = prod.saved["stats"] if (prod is not None and prod.saved.get("want_stats") and self.fuse_bn_stats) else None
+        stats = prod.saved["stats"] if (train and prod is not None and prod.saved.get("stats_done")) else None
         count = x.numel() // x.shape[-1]
         ops.bn_fwd(x, y, res, gamma, beta, rm, rv, stats, op.saved["mean_rstd"], count, a.get("eps", 1e-5),
                    a.get("momentum", 0.1), train, op.relu, self.impl["bn"],

@@ -291,7 +291,31 @@ umma_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     if (p.mode == 1) tma_store_4d(&tmC, staging + g * (BM * 128), col0 + g * 64, w0, h0, n0);
                     else tma_store_2d(&tmC, staging + g * (BM * 128), col0 + g * 64, tile_m * BM);
                 }
-                tma_store_commit_and_wait_read();
+                tma_store_commit();
+            }
+            if (p.stats) {
+                // BatchNorm statistics of this tile while the TMA unit drains it: thread = one output column (BN = 64: two threads per
+                // column, 64 rows each), walking the staged bf16 tile -- exactly the values BatchNorm will read back -- down its rows
+                // (masked rows skipped); ONE pair of global reductions per column and CTA, spread over kStatSlots partial buffers
+                const int c = BN == 128 ? et : (et & 63);
+                const int r_lo = BN == 128 ? 0 : (et >> 6) * (BM / 2), r_hi = BN == 128 ? BM : r_lo + BM / 2;
+                const uint8_t* colp = staging + (c >> 6) * (BM * 128) + (c & 7) * 2;
+                const int chunk = (c & 63) >> 3;
+                float s1 = 0.f, s2 = 0.f;
+#pragma unroll 8
+                for (int r = r_lo; r < r_hi; ++r) {
+                    if (tail->row_index[r] < 0) continue;
+                    const float v = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(colp + r * 128 + ((chunk ^ (r & 7)) << 4)));
+                    s1 += v; s2 += v * v;
+                }
+                if (col0 + c < p.N) {
+                    float* dst = p.stats + (size_t)(blockIdx.x % kStatSlots) * 2 * p.N + col0 + c;
+                    atomicAdd(dst, s1);
+                    atomicAdd(dst + p.N, s2);
+                }
+            }
+            if (et == 0) {
+                tma_store_wait_read();
                 if (dbg) dbg[6] = (long long)gtimer();
             }
         } else {
@@ -505,7 +529,7 @@ static cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, con
     p.dbg = g_trace;
     CUtensorMap tmC = tmA;                                       // dummy unless the TMA-store epilogue applies
     p.tma_store = 0;
-    if (tma_store_enabled() && !p.accumulate && !p.stats && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) && make_out_tmap(&tmC, p) == cudaSuccess)
+    if (tma_store_enabled() && !p.accumulate && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) && make_out_tmap(&tmC, p) == cudaSuccess)
         p.tma_store = 1;
     if (g_split_prod < 0) { const char* e = getenv("RLR_SPLIT_PRODUCER"); g_split_prod = (e && atoi(e) == 0) ? 0 : 1; }   // default on: -2.2 % per round (profiles/r2_step_ab.md)
     p.split_prod = (g_split_prod && !p.b_src) ? 1 : 0;
@@ -520,7 +544,8 @@ static cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, con
     }
     if (!p.stats && !p.b_src && persistent_sms() > 0 && m_tiles * ((p.N + BN - 1) / BN) > persistent_sms())
         return launch_persistent_bn<BN>(tmA, tmB, p, m_tiles, persistent_sms(), st);
-    if (!p.stats && conv_occ3() >= (BN == 64 ? 1 : 2)) return launch_bn_occ3<BN>(tmA, tmB, tmC, p, m_tiles, st);
+    // statistics ride on the TMA-store epilogue of the plain instantiation (runtime p.stats); without TMA stores: the kStats variant below
+    if ((!p.stats || p.tma_store) && conv_occ3() >= (BN == 64 ? 1 : 2)) return launch_bn_occ3<BN>(tmA, tmB, tmC, p, m_tiles, st);
     static bool configured = false;
     if (!configured) {
         RLR_CUDA_CHECK(cudaFuncSetAttribute(umma_conv_gemm_kernel<BN, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -530,7 +555,7 @@ static cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, con
     }
     dim3 grid(m_tiles, (p.N + BN - 1) / BN);
     if (p.b_mn) return launch_kernel(umma_conv_gemm_kernel<BN, false, true>, grid, dim3(kThreads), Cfg::kSmemBytes, st, tmA, tmB, tmC, p);
-    if (p.stats) return launch_kernel(umma_conv_gemm_kernel<BN, true, false>, grid, dim3(kThreads), Cfg::kSmemBytes, st, tmA, tmB, tmC, p);
+    if (p.stats && !p.tma_store) return launch_kernel(umma_conv_gemm_kernel<BN, true, false>, grid, dim3(kThreads), Cfg::kSmemBytes, st, tmA, tmB, tmC, p);
     return launch_kernel(umma_conv_gemm_kernel<BN, false, false>, grid, dim3(kThreads), Cfg::kSmemBytes, st, tmA, tmB, tmC, p);
 }
 

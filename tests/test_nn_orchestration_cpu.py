@@ -82,8 +82,14 @@ class FakeExt:
 
     def conv_bf16(self, x, w, out, NB, planes, dh, dw, dplane, bias, relu, accumulate, stats, wtap, w_taps_total):
         self.calls.append("conv_bf16")
-        assert x.shape[0] == planes * NB and out.shape[0] == NB and stats is None
+        assert x.shape[0] == planes * NB and out.shape[0] == NB
         self._conv(x, w, out, NB, dh, dw, dplane, bias, relu, accumulate, list(wtap), w_taps_total, 1, 1, 0, 0)
+        if stats is not None:                       # epilogue statistics: [slots][sum, sum^2][Cout] partials ADDED to (kernel contract)
+            assert not accumulate and not wtap and stats.shape[-2:] == (2, out.shape[3])
+            self.calls.append("conv_bf16+stats")
+            o = out.reshape(-1, out.shape[3]).float()
+            stats.reshape(-1, 2, out.shape[3])[0, 0] += o.sum(0)
+            stats.reshape(-1, 2, out.shape[3])[0, 1] += (o * o).sum(0)
 
     def conv_bf16_strided(self, x, w, out, dh, dw, bias, relu, accumulate, wtap, w_taps_total, in_stride, out_stride, ph, pw):
         self.calls.append("conv_bf16_strided")
@@ -336,6 +342,8 @@ def test_native_plan_with_kernel_conv_paths_matches_library_convs(fake, monkeypa
     cos = F.cosine_similarity(res["kern"][1].double(), res["lib"][1].double(), dim=0)
     assert float(cos) > 0.9999, float(cos)
     assert "conv_bf16" in fake.calls or "conv_bf16_strided" in fake.calls or "gemm_bf16" in fake.calls
+    if model == "resnet18":     # BatchNorm statistics came out of the conv epilogue for the stride-1 convs on the generic kernel (9 of 20)
+        assert fake.calls.count("conv_bf16+stats") == 9 and fake.calls.count("channel_stats") == 0   # (bn impl is aten here: no stats kernel at all)
 
 
 @pytest.mark.parametrize("recompute", [False, True])
