@@ -43,7 +43,8 @@ FUSE_DROPOUT = bool(int(os.environ.get("RLR_FUSE_DROPOUT", "1")))
 # ReLU of a conv whose only consumer is a max-pool: back-propagated inside the pooling backward kernel (no relu_bwd pass over the un-pooled tensor)
 FUSE_RELU_POOL = bool(int(os.environ.get("RLR_FUSE_RELU_POOL", "1")))
 # BatchNorm statistics from the conv epilogue where they are free (generic kernel, TMA-store epilogue: sums taken while the store drains)
-EPILOGUE_BN_STATS = bool(int(os.environ.get("RLR_EPILOGUE_BN_STATS", "1")))
+EPILOGUE_BN_STATS = bool(int(os.environ.get("RLR_EPILOGUE_BN_STATS", "0")))
+EPI_STAT_SLOTS = min(16, max(1, int(os.environ.get("RLR_EPI_STAT_SLOTS", "2"))))
 FWD_SLOTS = BWD_SLOTS = max(1, int(os.environ.get("RLR_BN_SLOTS", "1")))
 WGRAD_OVERLAP = bool(int(os.environ.get("RLR_WGRAD_OVERLAP", "1")))
 
@@ -444,6 +445,8 @@ class NativeNet:
         rm, rv = self.pw[op.name + ".running_mean"], self.pw[op.name + ".running_var"]
         prod = op.saved["producer"]
         stats = prod.saved["stats"] if (train and prod is not None and prod.saved.get("stats_done")) else None
+        if stats is not None and not self.fuse_bn_stats:
+            stats = stats[0:EPI_STAT_SLOTS]     # the TMA-store epilogue spreads its atomics over this prefix only (gemm.cu, same variable)
         count = x.numel() // x.shape[-1]
         ops.bn_fwd(x, y, res, gamma, beta, rm, rv, stats, op.saved["mean_rstd"], count, a.get("eps", 1e-5),
                    a.get("momentum", 0.1), train, op.relu, self.impl["bn"],

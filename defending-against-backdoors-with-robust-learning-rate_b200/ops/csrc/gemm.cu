@@ -309,7 +309,7 @@ umma_conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     s1 += v; s2 += v * v;
                 }
                 if (col0 + c < p.N) {
-                    float* dst = p.stats + (size_t)(blockIdx.x % kStatSlots) * 2 * p.N + col0 + c;
+                    float* dst = p.stats + (size_t)(blockIdx.x % p.stat_slots) * 2 * p.N + col0 + c;
                     atomicAdd(dst, s1);
                     atomicAdd(dst + p.N, s2);
                 }
@@ -528,6 +528,10 @@ static cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, con
     ConvGemmParams p = p_in;
     p.dbg = g_trace;
     CUtensorMap tmC = tmA;                                       // dummy unless the TMA-store epilogue applies
+    {   // slots used by the TMA-store epilogue's statistics (RLR_EPI_STAT_SLOTS; python reads the same variable for the prefix it reduces)
+        static const int epi_slots = [] { const char* e = getenv("RLR_EPI_STAT_SLOTS"); int v = e ? atoi(e) : 2; return v < 1 ? 1 : (v > kStatSlots ? kStatSlots : v); }();
+        p.stat_slots = epi_slots;
+    }
     p.tma_store = 0;
     if (tma_store_enabled() && !p.accumulate && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) && make_out_tmap(&tmC, p) == cudaSuccess)
         p.tma_store = 1;

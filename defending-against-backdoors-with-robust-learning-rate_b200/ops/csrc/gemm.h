@@ -46,7 +46,8 @@ struct ConvGemmParams {
     void* out;                 // bf16 [M][ldc]
     int ldc;
     const float* bias;         // [N] or null
-    float* stats;              // [2][N] (sum, sum of squares) or null
+    float* stats;              // [slots][2][N] (sum, sum of squares) partial buffers or null
+    int stat_slots;            // TMA-store epilogue: CTA b adds into slot b % stat_slots (0 -> kStatSlots); the caller reduces over that prefix
     int relu, accumulate;
 };
 

@@ -44,5 +44,8 @@ b fmnist10_stem2 RLR_STEM_PERSISTENT=2 $F
 b fmnist10_stem1 RLR_STEM_PERSISTENT=1 $F
 b cifar40_stem2 RLR_STEM_PERSISTENT=2 $C
 b cifar40_stem1 RLR_STEM_PERSISTENT=1 $C
-b headline_stem2 RLR_STEM_PERSISTENT=2
-b headline_stem1 RLR_STEM_PERSISTENT=1
+b headline_stats1 RLR_EPILOGUE_BN_STATS=1
+b headline_stats0 RLR_EPILOGUE_BN_STATS=0
+b headline_stats1b RLR_EPILOGUE_BN_STATS=1
+b vgg11_stats1 RLR_EPILOGUE_BN_STATS=1 --model vgg11 --agents 8 --aggr comed
+b vgg11_stats0 RLR_EPILOGUE_BN_STATS=0 --model vgg11 --agents 8 --aggr comed
