@@ -44,6 +44,8 @@ FUSE_DROPOUT = bool(int(os.environ.get("RLR_FUSE_DROPOUT", "1")))
 FUSE_RELU_POOL = bool(int(os.environ.get("RLR_FUSE_RELU_POOL", "1")))
 # BatchNorm statistics from the conv epilogue where they are free (generic kernel, TMA-store epilogue: sums taken while the store drains)
 EPILOGUE_BN_STATS = bool(int(os.environ.get("RLR_EPILOGUE_BN_STATS", "0")))
+# projection shortcuts (1x1 conv + BatchNorm) of residual blocks on a second stream during the forward pass
+FWD_BRANCH = bool(int(os.environ.get("RLR_FWD_BRANCH", "1")))
 EPI_STAT_SLOTS = min(16, max(1, int(os.environ.get("RLR_EPI_STAT_SLOTS", "2"))))
 FWD_SLOTS = BWD_SLOTS = max(1, int(os.environ.get("RLR_BN_SLOTS", "1")))
 WGRAD_OVERLAP = bool(int(os.environ.get("RLR_WGRAD_OVERLAP", "1")))
@@ -279,6 +281,20 @@ class NativeNet:
             if op.kind == "dropout":
                 op.saved["mask"] = torch.empty((B, *op.out_shape), dtype=torch.uint8, device=dev)
         self._bn_src = {}
+        # Side branch of a residual block with a projection shortcut (1x1 conv + BatchNorm on the block input): independent of the main
+        # path until the fused bn2 + add, so in the forward pass it runs on a second stream forked where the block input is ready --
+        # in the captured step graph a parallel branch whose small kernels fill the tails of the main path's conv waves.
+        for i, op in enumerate(self.plan):
+            if not (FWD_BRANCH and op.kind == "conv" and ".downsample." in (op.name or "")):
+                continue
+            nxt = self.plan[i + 1] if i + 1 < len(self.plan) else None
+            first = next((q for q in self.plan[:i] if q.x == op.x and q is not op), None)            # the block's conv1 reads the same input
+            join = next((q for q in self.plan[i + 1:] if nxt is not None and q.res == nxt.y), None)  # the fused bn2 + add
+            if nxt is None or nxt.kind != "bn" or nxt.x != op.y or first is None or join is None:
+                continue
+            first.saved["fork_before"] = True
+            op.saved["side_branch"] = nxt.saved["side_branch"] = True
+            join.saved["join_before"] = True
         for i, op in enumerate(self.plan):   # a BN op reads the statistics its producer conv accumulated
             if op.kind == "bn":
                 prod = next((q for q in self.plan[:i] if q.y == op.x and q.kind == "conv"), None)
@@ -331,8 +347,19 @@ class NativeNet:
         self._epoch = getattr(self, "_epoch", 0) + 1     # forward-pass id: lets stride-2 convs share their parity-split input copy
         if train:
             ops.zero_(self.stats_arena)
+        branch = FWD_BRANCH and self.device.type == "cuda" and ops.nn.USE_STRIDED_TMA and self.impl["conv_fwd"] == "sm100"
+        if branch and getattr(self, "_branch_stream", None) is None:
+            self._branch_stream = torch.cuda.Stream(self.device)
         for i, op in enumerate(self.plan):
-            getattr(self, "_fwd_" + op.kind)(op, B, train)
+            if branch and op.saved.get("fork_before"):
+                self._branch_stream.wait_stream(torch.cuda.current_stream(self.device))      # the block input is final
+            if branch and op.saved.get("join_before"):
+                torch.cuda.current_stream(self.device).wait_stream(self._branch_stream)      # shortcut output ready for bn2 + add
+            if branch and op.saved.get("side_branch"):
+                with torch.cuda.stream(self._branch_stream):
+                    getattr(self, "_fwd_" + op.kind)(op, B, train)
+            else:
+                getattr(self, "_fwd_" + op.kind)(op, B, train)
             if i == 0 and self.after_first_op is not None:
                 self.after_first_op()        # hand-off: acquire the rest of the broadcast once the first-layer GEMM is queued
         return self.T(self.out_tid, B).reshape(B, -1)
