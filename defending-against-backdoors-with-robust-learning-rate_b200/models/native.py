@@ -46,6 +46,7 @@ FUSE_RELU_POOL = bool(int(os.environ.get("RLR_FUSE_RELU_POOL", "1")))
 EPILOGUE_BN_STATS = bool(int(os.environ.get("RLR_EPILOGUE_BN_STATS", "0")))
 # projection shortcuts (1x1 conv + BatchNorm) of residual blocks on a second stream during the forward pass
 FWD_BRANCH = bool(int(os.environ.get("RLR_FWD_BRANCH", "1")))
+BWD_BRANCH = bool(int(os.environ.get("RLR_BWD_BRANCH", "1")))     # ... and their backward (needs RLR_FWD_BRANCH)
 EPI_STAT_SLOTS = min(16, max(1, int(os.environ.get("RLR_EPI_STAT_SLOTS", "2"))))
 FWD_SLOTS = BWD_SLOTS = max(1, int(os.environ.get("RLR_BN_SLOTS", "1")))
 WGRAD_OVERLAP = bool(int(os.environ.get("RLR_WGRAD_OVERLAP", "1")))
@@ -382,8 +383,22 @@ class NativeNet:
                 self._side_stream = torch.cuda.Stream(self.device)
             self._side = self._side_stream
             self._side.wait_stream(torch.cuda.current_stream(self.device))       # the flat gradient is zeroed
+        branch = (BWD_BRANCH and FWD_BRANCH and self.device.type == "cuda" and ops.nn.USE_STRIDED_TMA and self.impl["conv_fwd"] == "sm100"
+                  and getattr(self, "_branch_stream", None) is not None)
+        cur = torch.cuda.current_stream(self.device) if branch else None
         for op in reversed(self.plan):
-            getattr(self, "_bwd_" + op.kind)(op, B)
+            # projection shortcut (see _alloc): its backward -- BatchNorm backward, 1x1 weight and data gradients -- only needs the
+            # residual gradient that the fused bn2 + add backward just wrote, and must be complete before conv1's data gradient
+            # ACCUMULATES into the block-input gradient the shortcut's data gradient stored first
+            if branch and op.saved.get("fork_before"):
+                cur.wait_stream(self._branch_stream)
+            if branch and op.saved.get("side_branch"):
+                if op.kind == "bn":
+                    self._branch_stream.wait_stream(cur)
+                with torch.cuda.stream(self._branch_stream):
+                    getattr(self, "_bwd_" + op.kind)(op, B)
+            else:
+                getattr(self, "_bwd_" + op.kind)(op, B)
         if self._side is not None:
             torch.cuda.current_stream(self.device).wait_stream(self._side)       # every weight gradient has landed before the optimizer
             self._side = None
