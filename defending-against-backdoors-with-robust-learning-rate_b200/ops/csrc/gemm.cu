@@ -418,7 +418,7 @@ template <int BN>
 cudaError_t launch_persistent_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, int m_tiles, int num_sms,
                                  cudaStream_t st, int occ = 1);
 
-// 0: two CTAs per SM for every tile | 1 (default, measured -1.4 % / round): three for the 64-wide tile | 2 (not yet measured): also
+// 0: two CTAs per SM for every tile | 1 (default, measured -1.4 % / round): three for the 64-wide tile | 2 (measured: 1072 vs 1065 ms, no gain): also
 // for the 128-wide tile (2-stage ring).  -1: take RLR_CONV_OCC3 from the environment on first use.
 static int g_occ3 = -1;
 void set_conv_occ3(int level) { g_occ3 = level < 0 ? 0 : (level > 2 ? 2 : level); }
@@ -573,7 +573,7 @@ cudaError_t launch_gemm_bf16(const void* A, const void* B, void* out, int M, int
     const int m_tiles = (M + BM - 1) / BM;
     const int bn2 = pair_bn(m_tiles, N, stats == nullptr);
     int bn = bn2 ? bn2 : pick_bn(N);
-    {   // opt-in (RLR_GEMM_SMALL_BN64=1, not yet measured): small-batch linear layers (M = 256: two M tiles) get twice the CTAs
+    {   // opt-in (RLR_GEMM_SMALL_BN64=1; measured 256x128x1024: 15.2 -> 11.5 us, 256x256x128: 11.2 -> 9.3 us, profiles/raw/r2_experiments_summary.txt): small-batch linear layers (M = 256: two M tiles) get twice the CTAs
         static const int small64 = [] { const char* e = getenv("RLR_GEMM_SMALL_BN64"); return e ? atoi(e) : 0; }();
         if (small64 && !bn2 && bn == 128 && m_tiles * (N / 128) < sm_count()) bn = 64;
     }

@@ -1,4 +1,6 @@
-// CTA-pair variant of the implicit-GEMM conv / GEMM kernel of gemm.cu (opt-in: RLR_CONV_2CTA=1, not yet measured on hardware).
+// CTA-pair variant of the implicit-GEMM conv / GEMM kernel of gemm.cu (opt-in: RLR_CONV_2CTA=1).
+// Verified on B200 (tests/test_gpu_variants.py); its main loop is faster (layer 3: 11.1 vs 13.6 us) but the 128 x 256 epilogue and the
+// single TMA stream per SM make the round 1-3 % slower than the default (profiles/r2_step_ab.md, profiles/r2_ncu_generic_conv.md).
 //
 // A thread-block cluster of two CTAs (adjacent M tiles, same N tile) runs ONE tcgen05.mma.cta_group::2 stream: the instruction
 // has M = 256 (128 rows from each CTA's shared memory, 128 accumulator lanes in each CTA's TMEM) and N = BN, and each CTA stages

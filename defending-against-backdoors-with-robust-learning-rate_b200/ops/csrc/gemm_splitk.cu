@@ -1,4 +1,5 @@
-// Split-K variant of the plain tcgen05 GEMM for small-M / deep-K problems (opt-in: RLR_SPLITK=1, not yet measured on hardware).
+// Split-K variant of the plain tcgen05 GEMM for small-M / deep-K problems (default for K >= 1024 with at most 16 output
+// tiles, e.g. fc1 of the reference CNNs; verified on B200, RLR_SPLITK=0 turns it off).
 //
 // The first dense layer of the reference's FMNIST CNN is out[256][128] = x[256][9216] W[128][9216]^T: two 128 x 128 output tiles
 // that each walk 144 k-blocks in sequence (~40 us of pure pipeline latency on two of 148 SMs); at the runner's batch size 64 it is a

@@ -24,21 +24,23 @@ USE_STRIDED_TMA = bool(int(os.environ.get("RLR_STRIDED_TMA", "1")))
 # Stem convolutions (Cin * k * k <= 64, stride 1): gather the k x k x Cin patch of every output pixel into ONE 64-wide K block
 # (im2col_small, or -- in the training step -- directly by the batch-assembly kernel gather_im2col) and run the plain tcgen05 GEMM on
 # it, instead of k*k k-blocks of a 64-channel zero-padded input; the weight gradient is a [Cout x 64] GEMM over the same matrix.
-# Verified on B200 (tests/test_gpu_experimental.py::test_im2col_stem_conv_and_wgrad); RLR_IM2COL_STEM=0 restores the padded conv.
+# Verified on B200 (tests/test_gpu_variants.py::test_im2col_stem_conv_and_wgrad, tests/test_gpu_native.py::test_stem_gemm_*);
+# RLR_IM2COL_STEM=0 restores the padded conv.
 USE_IM2COL_STEM = bool(int(os.environ.get("RLR_IM2COL_STEM", "1")))
 # BatchNorm(+ReLU, no residual) backward without reading the layer output: the mask is recomputed from x with the forward's own
-# scale/shift expression.  Opt-in until measured on hardware (RLR_BN_RECOMPUTE=1).
+# scale/shift expression.  Measured on B200: within noise on the round, one activation read less per backward pass; default on
+# (RLR_BN_RECOMPUTE=0 reads the stored output instead).
 USE_BN_RECOMPUTE = bool(int(os.environ.get("RLR_BN_RECOMPUTE", "1")))
 # 3x3/s1/p1 convs with 64 input channels: three filter taps per N = 192 MMA with a lane shift-add epilogue (conv_halo3.cu) instead of
-# nine N = 64 MMAs per k-step.  Opt-in until measured on hardware (RLR_HALO3=1).
+# nine N = 64 MMAs per k-step.  Measured on B200: correct, +7 % per round (epilogue shuffles, 33 % more tiles): opt-in (RLR_HALO3=1).
 USE_HALO3 = bool(int(os.environ.get("RLR_HALO3", "0")))
 # halo-reuse kernel also for valid / full 3x3 convs and sizes that are not whole 16x8 tiles (reference CNNs: conv2 and its data gradient)
 USE_HALO_ANY = bool(int(os.environ.get("RLR_HALO_ANY", "1")))
 # Dense layers with few output tiles and a deep reduction (FMNIST CNN fc1: 256 x 128 x 9216): split-K GEMM with an fp32 workspace
-# (gemm_splitk.cu).  Opt-in until measured on hardware (RLR_SPLITK=1).
+# (gemm_splitk.cu).  Verified and default on (RLR_SPLITK=0 runs the single-pass GEMM).
 USE_SPLITK = bool(int(os.environ.get("RLR_SPLITK", "1")))
 # Classifier-head kernels v2 (weights staged in shared memory, weight gradient spread over K/64 x B/16 blocks with float atomics).
-# Opt-in until measured on hardware (RLR_HEAD_V2=1).
+# Measured on B200: 49 -> 13 us per step; default on (RLR_HEAD_V2=0 restores the first kernels).
 USE_HEAD_V2 = bool(int(os.environ.get("RLR_HEAD_V2", "1")))
 
 
