@@ -98,3 +98,32 @@ def test_dropout_layers_are_fused_into_their_producers():
         assert sum(op.kind == "dropout" for op in net.plan) == 2
     finally:
         nat.FUSE_DROPOUT = old
+
+
+def test_shortcut_branches_and_relu_pool_fusion_are_planned_where_they_are_legal():
+    """Static plan analysis behind two graph-level optimisations of models/native.py:
+    * projection shortcuts (1x1 conv + BatchNorm on the block input) become a parallel branch: forked before the block's conv1 (which
+      reads the same input), joined at the fused bn2 + add that consumes the shortcut output -- ResNet-18 / -34 have three, every other
+      model none;
+    * the ReLU of a conv whose ONLY consumer is a max-pool is back-propagated by the pooling backward (reference CNNs), never for
+      BatchNorm models (their ReLU is fused into the BatchNorm op)."""
+    impl = dict(conv_fwd="aten", conv_dgrad="aten", conv_wgrad="aten", bn="aten", pool="aten", linear="aten", dropout="aten")
+    for name, n_branch, n_relu_pool in (("resnet18", 3, 0), ("resnet34", 3, 0), ("vgg11", 0, 0), ("cnn_mnist", 0, 1), ("cnn_cifar", 0, 3)):
+        net = NativeNet(get_layout(name), "cpu", 2, impl=impl, act_dtype=torch.float32)
+        plan = net.plan
+        side = [op for op in plan if op.saved.get("side_branch")]
+        forks = [op for op in plan if op.saved.get("fork_before")]
+        joins = [op for op in plan if op.saved.get("join_before")]
+        assert len(forks) == len(joins) == n_branch and len(side) == 2 * n_branch, name
+        for f, j in zip(forks, joins):
+            i_f, i_j = plan.index(f), plan.index(j)
+            mine = [op for op in side if i_f < plan.index(op) < i_j]
+            assert [op.kind for op in mine] == ["conv", "bn"] and ".downsample." in mine[0].name, name
+            assert mine[0].x == f.x and mine[1].x == mine[0].y and j.res == mine[1].y            # same input as conv1; feeds the add
+            assert all(op.x != mine[0].y and op.x != mine[1].y for op in plan[i_f:i_j] if op not in mine)   # nobody on the main path reads it
+        pools = [op for op in plan if op.kind == "maxpool" and op.saved.get("relu_bwd_here")]
+        convs = [op for op in plan if op.kind == "conv" and op.saved.get("relu_bwd_fused")]
+        assert len(pools) == len(convs) == n_relu_pool, name
+        for pool in pools:
+            prod = next(q for q in plan if q.y == pool.x)
+            assert prod in convs and prod.relu and sum(1 for q in plan if q.x == pool.x or q.res == pool.x) == 1
