@@ -222,3 +222,16 @@ def test_first_step_from_broadcast_buffer_equals_round_init_plus_step(pgd):
     ops.FlatSGD(n, "cpu", 0.1, 0.9, 10.0, pgd, n_pgd=n_vote).step(w_b, g, m_b, w0=w_global, w_in=w_global)
     torch.testing.assert_close(w_b, w_a, rtol=1e-6, atol=1e-6)      # (w - lr*m vs w.add_(m, alpha=-lr): last-bit rounding only)
     torch.testing.assert_close(m_b, m_a, rtol=1e-6, atol=1e-6)
+
+
+def test_agents_in_flight_rule_and_round_robin_on_cpu():
+    """--agents_in_flight: 0 = auto (two trainers on the native CUDA path, one elsewhere); an explicit N builds N trainers that are used
+    round-robin (on CPU without overlap) and changes nothing in the result."""
+    a = _engine(rounds=1)
+    assert len(a.trainers) == 1 and a.streams is None                                # CPU: auto = 1
+    b = _engine(rounds=1, agents_in_flight=3)
+    assert len(b.trainers) == min(3, b.fused.max_slots if hasattr(b.fused, "max_slots") else 3) and b.streams is None
+    for r in (1, 2):
+        a.run_round(r); b.run_round(r)
+    torch.testing.assert_close(a.global_params(), b.global_params(), rtol=1e-5, atol=1e-6)
+    a.close(); b.close()

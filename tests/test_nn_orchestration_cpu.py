@@ -478,3 +478,21 @@ def test_kernel_index_arithmetic_for_strided_input_and_output(B, H, W, Cin, Cout
     xn = x.permute(0, 3, 1, 2).clone().requires_grad_(True)
     F.conv2d(xn, w.permute(0, 3, 1, 2), None, 2, p).backward(dy.permute(0, 3, 1, 2))
     torch.testing.assert_close(dx, xn.grad.permute(0, 2, 3, 1), rtol=1e-4, atol=1e-4)
+
+
+def test_halo_kernel_predicate(monkeypatch):
+    """ops/nn.py:_halo_ok -- which 3x3 / stride-1 / 64-channel convs go to the halo-reuse kernel: valid / same / full padding, any size whose
+    16 x 8 tiling is at least half real output, whole tiles only when the epilogue also takes BatchNorm statistics."""
+    ok = nn._halo_ok
+    assert ok(3, 1, 1, 64, 32, 32) and ok(3, 1, 1, 64, 32, 32, True)                 # ResNet layer 1 / VGG
+    assert ok(3, 1, 0, 64, 26, 26) and ok(3, 1, 2, 64, 24, 24)                      # CNN_MNIST conv2 (channel-padded) and its data gradient
+    assert ok(3, 1, 0, 64, 15, 15) and not ok(3, 1, 0, 64, 15, 15, True)            # CNN_CIFAR conv2: partial tiles, so no statistics
+    assert not ok(3, 1, 0, 64, 6, 6)                                                # 4 x 4 output: 16 of 128 tile pixels -> generic kernel
+    assert not ok(3, 2, 1, 64, 32, 32) and not ok(1, 1, 0, 64, 32, 32) and not ok(3, 1, 1, 128, 16, 16) and not ok(3, 1, 3, 64, 8, 8)
+    for h in range(3, 40):                                                          # the utilisation rule, against its definition
+        for pad in (0, 1, 2):
+            ho = h + 2 * pad - 2
+            tiles = -(-ho // 16) * 16 * (-(-ho // 8) * 8)
+            assert ok(3, 1, pad, 64, h, h) == (ho >= 1 and 2 * ho * ho >= tiles), (h, pad)
+    monkeypatch.setattr(nn, "USE_HALO_ANY", False)                                  # round-1 predicate
+    assert ok(3, 1, 1, 64, 32, 32) and not ok(3, 1, 0, 64, 26, 26) and not ok(3, 1, 1, 64, 24, 24)
